@@ -1,0 +1,475 @@
+"""Workload builders for the BASELINE.json configs and for parity fuzzing.
+
+A Scene is a backend-neutral description: pipeline state, named byte buffers, render-target images, one draw.
+`materialize()` turns it into the C-ABI PODs (cpvk_cuda.h) given an allocator that places bytes somewhere and
+returns an address — host memory for the CPU oracle, HBM for libcpvk_cuda.so. Inputs follow the reference's
+samples (Samples/15-draw_cube, Samples/draw_textured_cube, Samples/utils/util_init.cpp) in layout and state;
+geometry and matrices are generated here, not copied.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import capi, spvasm
+
+SHADER_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shaders")
+
+# VkFormat
+R8G8B8A8_UNORM, B8G8R8A8_UNORM, R16G16B16A16_SFLOAT = 37, 44, 97
+R32_SFLOAT, R32G32_SFLOAT, R32G32B32_SFLOAT, R32G32B32A32_SFLOAT = 100, 103, 106, 109
+D16_UNORM, D32_SFLOAT, D24_UNORM_S8_UINT = 124, 126, 129
+# VkPrimitiveTopology / VkCullMode / VkFrontFace / VkCompareOp
+TRIANGLE_LIST, TRIANGLE_STRIP, TRIANGLE_FAN = 3, 4, 5
+CULL_NONE, CULL_FRONT, CULL_BACK = 0, 1, 2
+FRONT_CCW, FRONT_CW = 0, 1
+NEVER, LESS, EQUAL, LESS_OR_EQUAL, GREATER, NOT_EQUAL, GREATER_OR_EQUAL, ALWAYS = range(8)
+# VkFilter / VkSamplerAddressMode
+NEAREST, LINEAR = 0, 1
+REPEAT, MIRRORED_REPEAT, CLAMP_TO_EDGE, CLAMP_TO_BORDER, MIRROR_CLAMP_TO_EDGE = range(5)
+# VkBlendFactor / VkBlendOp
+BF_ZERO, BF_ONE, BF_SRC_COLOR, BF_ONE_MINUS_SRC_COLOR, BF_DST_COLOR, BF_ONE_MINUS_DST_COLOR, BF_SRC_ALPHA, \
+    BF_ONE_MINUS_SRC_ALPHA, BF_DST_ALPHA, BF_ONE_MINUS_DST_ALPHA = range(10)
+BO_ADD, BO_SUBTRACT, BO_REVERSE_SUBTRACT, BO_MIN, BO_MAX = range(5)
+
+TEXEL_SIZE = {R8G8B8A8_UNORM: 4, B8G8R8A8_UNORM: 4, R16G16B16A16_SFLOAT: 8, D16_UNORM: 2, D32_SFLOAT: 4,
+              D24_UNORM_S8_UINT: 4, R32_SFLOAT: 4, R32G32B32A32_SFLOAT: 16}
+
+_shader_cache = {}
+
+
+def shader(name):
+    """SPIR-V words (numpy uint32) of cpvulkan_b200/shaders/<name>.spvasm."""
+    if name not in _shader_cache:
+        with open(os.path.join(SHADER_DIR, name + ".spvasm")) as f:
+            _shader_cache[name] = np.array(spvasm.assemble(f.read()), dtype=np.uint32)
+    return _shader_cache[name]
+
+
+class Image:
+    def __init__(self, fmt, width, height, data=None, clear=None):
+        self.format, self.width, self.height = fmt, width, height
+        self.pitch = TEXEL_SIZE[fmt] * width  # Stride = texel * width (CPVulkanBase/Formats.cpp:455-483)
+        self.data = data      # optional initial bytes (np.uint8, pitch*height)
+        self.clear = clear    # ('color', (r,g,b,a)) or ('depth', (d, s)) applied before the draw
+
+    @property
+    def nbytes(self):
+        return self.pitch * self.height
+
+
+class Texture:
+    def __init__(self, binding, image, filt=NEAREST, address=CLAMP_TO_EDGE, set_=0):
+        self.set, self.binding, self.image, self.filter, self.address = set_, binding, image, filt, address
+
+
+class Scene:
+    def __init__(self, name):
+        self.name = name
+        self.vs = self.fs = None                 # shader names
+        self.bindings = []                       # (binding, stride, inputRate)
+        self.attributes = []                     # (location, binding, format, offset)
+        self.topology = TRIANGLE_LIST
+        self.cull, self.front_face = CULL_NONE, FRONT_CCW
+        self.depth_test = self.depth_write = False
+        self.depth_op = LESS_OR_EQUAL
+        self.blend = None                        # dict(src, dst, op, srcA, dstA, opA) or None
+        self.write_mask = 0xF
+        self.buffers = {}                        # name -> np.uint8 array
+        self.vertex_buffers = {}                 # binding -> buffer name
+        self.index_buffer, self.index_stride = None, 0
+        self.uniforms = []                       # (set, binding, buffer name)
+        self.textures = []                       # Texture
+        self.color = None                        # Image
+        self.depth = None                        # Image or None
+        self.viewport = None                     # (x, y, w, h, minDepth, maxDepth)
+        self.count, self.instances, self.first, self.vertex_offset, self.first_instance = 0, 1, 0, 0, 0
+        self.push_constants = b""
+
+
+class Materialized:
+    """ctypes PODs + the keep-alive objects behind their pointers."""
+
+    def __init__(self):
+        self.desc = capi.PipelineDesc()
+        self.state = capi.DrawState()
+        self.addr = {}      # resource name -> address
+        self.keep = []
+        self.color_attachment = None
+        self.depth_attachment = None
+
+
+def materialize(scene, alloc):
+    """alloc(name, nbytes, init_bytes_or_None) -> address (int)."""
+    m = Materialized()
+    d, s = m.desc, m.state
+    vsw, fsw = shader(scene.vs), (shader(scene.fs) if scene.fs else None)
+    m.keep += [vsw, fsw]
+    d.vertex.spirv = vsw.ctypes.data_as(C.POINTER(C.c_uint32))
+    d.vertex.wordCount = len(vsw)
+    d.vertex.entryPoint = b"main"
+    if fsw is not None:
+        d.fragment.spirv = fsw.ctypes.data_as(C.POINTER(C.c_uint32))
+        d.fragment.wordCount = len(fsw)
+        d.fragment.entryPoint = b"main"
+    d.bindingCount = len(scene.bindings)
+    for i, (b, stride, rate) in enumerate(scene.bindings):
+        d.bindings[i] = capi.VertexBinding(b, stride, rate)
+    d.attributeCount = len(scene.attributes)
+    for i, a in enumerate(scene.attributes):
+        d.attributes[i] = capi.VertexAttribute(*a)
+    d.topology = scene.topology
+    d.polygonMode, d.cullMode, d.frontFace, d.lineWidth = 0, scene.cull, scene.front_face, 1.0
+    d.rasterizationSamples = 1
+    d.depthTestEnable, d.depthWriteEnable, d.depthCompareOp = int(scene.depth_test), int(scene.depth_write), scene.depth_op
+    d.minDepthBounds, d.maxDepthBounds = 0.0, 1.0
+    d.colorAttachmentCount = 1
+    d.colorFormats[0] = scene.color.format
+    bl = d.blend[0]
+    bl.colorWriteMask = scene.write_mask
+    if scene.blend:
+        bl.blendEnable = 1
+        bl.srcColorBlendFactor, bl.dstColorBlendFactor, bl.colorBlendOp = scene.blend["src"], scene.blend["dst"], scene.blend["op"]
+        bl.srcAlphaBlendFactor = scene.blend.get("srcA", scene.blend["src"])
+        bl.dstAlphaBlendFactor = scene.blend.get("dstA", scene.blend["dst"])
+        bl.alphaBlendOp = scene.blend.get("opA", scene.blend["op"])
+    d.depthStencilFormat = scene.depth.format if scene.depth else 0
+    d.dynamicViewport = 1
+
+    for name, data in scene.buffers.items():
+        m.addr[name] = alloc(name, data.nbytes, data)
+    vp = scene.viewport or (0.0, 0.0, float(scene.color.width), float(scene.color.height), 0.0, 1.0)
+    s.viewport = capi.Viewport(*vp)
+    for b, name in scene.vertex_buffers.items():
+        s.vertexBuffers[b] = m.addr[name]
+    if scene.index_buffer:
+        s.indexBuffer, s.indexStride = m.addr[scene.index_buffer], scene.index_stride
+    s.count, s.instanceCount, s.first = scene.count, scene.instances, scene.first
+    s.vertexOffset, s.firstInstance = scene.vertex_offset, scene.first_instance
+    nd = 0
+    for set_, binding, name in scene.uniforms:
+        ds = s.descriptors[nd]
+        ds.set, ds.binding, ds.type = set_, binding, capi.DESC_BUFFER
+        ds.address, ds.range = m.addr[name], scene.buffers[name].nbytes
+        nd += 1
+    for t in scene.textures:
+        ds = s.descriptors[nd]
+        img = t.image
+        addr = alloc("tex%d" % t.binding, img.nbytes, img.data)
+        m.addr["tex%d" % t.binding] = addr
+        ds.set, ds.binding, ds.type = t.set, t.binding, capi.DESC_IMAGE
+        ds.format, ds.dimensions, ds.levelCount = img.format, 2, 1
+        ds.levels[0] = capi.MipLevel(addr, img.width, img.height, 1, 0)
+        sm = ds.sampler
+        sm.magFilter = sm.minFilter = t.filter
+        sm.addressModeU = sm.addressModeV = sm.addressModeW = t.address
+        sm.minLod, sm.maxLod = 0.0, 0.0
+        nd += 1
+    s.descriptorCount = nd
+    pc = scene.push_constants
+    s.pushConstantSize = len(pc)
+    for i, byte in enumerate(pc):
+        s.pushConstants[i] = byte
+
+    caddr = alloc("color", scene.color.nbytes, scene.color.data)
+    m.addr["color"] = caddr
+    m.color_attachment = capi.Attachment(caddr, scene.color.width, scene.color.height, scene.color.pitch, scene.color.format)
+    s.color[0] = m.color_attachment
+    if scene.depth:
+        daddr = alloc("depth", scene.depth.nbytes, scene.depth.data)
+        m.addr["depth"] = daddr
+        m.depth_attachment = capi.Attachment(daddr, scene.depth.width, scene.depth.height, scene.depth.pitch, scene.depth.format)
+        s.depthStencil = m.depth_attachment
+    return m
+
+
+def clear_value(image):
+    cv = capi.ClearValue()
+    kind, val = image.clear
+    if kind == "depth":
+        cv.depthStencil.depth, cv.depthStencil.stencil = val
+    else:
+        for i in range(4):
+            cv.float32[i] = val[i]
+    return cv, (1 if kind == "depth" else 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# matrices (float32, column-major like the sample's glm matrices; Samples/utils/util_init.cpp:1050-1068)
+
+def _perspective(fovy, aspect, near, far):
+    t = np.float32(math.tan(fovy / 2.0))
+    m = np.zeros((4, 4), dtype=np.float32)  # m[col][row]
+    m[0][0] = np.float32(1.0) / (np.float32(aspect) * t)
+    m[1][1] = np.float32(1.0) / t
+    m[2][2] = -np.float32(far + near) / np.float32(far - near)
+    m[2][3] = -1.0
+    m[3][2] = -np.float32(2.0 * far * near) / np.float32(far - near)
+    return m
+
+
+def _look_at(eye, center, up):
+    eye, center, up = (np.array(v, dtype=np.float32) for v in (eye, center, up))
+    f = center - eye
+    f = f / np.float32(np.linalg.norm(f))
+    s = np.cross(f, up)
+    s = s / np.float32(np.linalg.norm(s))
+    u = np.cross(s, f)
+    m = np.identity(4, dtype=np.float32)
+    m[0][0], m[1][0], m[2][0] = s
+    m[0][1], m[1][1], m[2][1] = u
+    m[0][2], m[1][2], m[2][2] = -f
+    m[3][0], m[3][1], m[3][2] = -np.dot(s, eye), -np.dot(u, eye), np.dot(f, eye)
+    return m.astype(np.float32)
+
+
+def _mul(a, b):  # column-major product a*b with m[col][row] storage
+    return (b.astype(np.float32) @ a.astype(np.float32)).astype(np.float32)
+
+
+def cube_mvp(width, height):
+    fov = math.radians(45.0)
+    if width > height:
+        fov *= float(height) / float(width)
+    proj = _perspective(fov, float(width) / float(height), 0.1, 100.0)
+    view = _look_at((-5, 3, -10), (0, 0, 0), (0, -1, 0))
+    clip = np.array([[1, 0, 0, 0], [0, -1, 0, 0], [0, 0, 0.5, 0], [0, 0, 0.5, 1]], dtype=np.float32)
+    return _mul(_mul(clip, proj), view)
+
+
+_FACES = [  # (axis, sign): the face x/y/z = +-1; colour per face as in the sample's solid-colour cube
+    ((2, +1), (1, 0, 0)), ((2, -1), (0, 1, 0)), ((0, -1), (0, 0, 1)),
+    ((0, +1), (1, 1, 0)), ((1, +1), (1, 0, 1)), ((1, -1), (0, 1, 1)),
+]
+
+
+def _cube_faces():
+    """36 positions (two triangles per face, clockwise seen from outside in a right-handed frame) + face uv."""
+    pos, uv, face = [], [], []
+    for fi, ((axis, sign), _) in enumerate(_FACES):
+        a1, a2 = (axis + 1) % 3, (axis + 2) % 3
+        corners = []
+        for (u, v) in ((0, 0), (1, 0), (1, 1), (0, 1)):
+            p = [0.0, 0.0, 0.0]
+            p[axis] = float(sign)
+            p[a1] = 2.0 * u - 1.0
+            p[a2] = (2.0 * v - 1.0) * sign  # flip so every face has the same handedness seen from outside
+            corners.append((p, (float(u), float(v))))
+        for k in (0, 2, 1, 0, 3, 2):
+            pos.append(corners[k][0] + [1.0])
+            uv.append(corners[k][1])
+            face.append(fi)
+    return np.array(pos, dtype=np.float32), np.array(uv, dtype=np.float32), face
+
+
+def _render_targets(scene, width, height, color_fmt, depth_fmt, clear_color, clear_depth=1.0):
+    scene.color = Image(color_fmt, width, height, clear=("color", clear_color))
+    if depth_fmt:
+        scene.depth = Image(depth_fmt, width, height, clear=("depth", (clear_depth, 0)))
+
+
+def draw_cube(width=500, height=500):
+    """C1 = Samples/15-draw_cube: 36-vertex coloured cube, BGRA8 + D16, cull BACK, front CLOCKWISE, LESS_OR_EQUAL."""
+    s = Scene("draw_cube")
+    s.vs, s.fs = "cube.vert", "cube.frag"
+    pos, _, face = _cube_faces()
+    col = np.array([list(_FACES[f][1]) + [1.0] for f in face], dtype=np.float32)
+    vb = np.concatenate([pos, col], axis=1).astype(np.float32)  # Vertex{vec4 pos, vec4 rgba}, stride 32
+    s.buffers["vb"] = vb.view(np.uint8).reshape(-1)
+    s.buffers["ubo"] = cube_mvp(width, height).reshape(-1).view(np.uint8)
+    s.bindings = [(0, 32, 0)]
+    s.attributes = [(0, 0, R32G32B32A32_SFLOAT, 0), (1, 0, R32G32B32A32_SFLOAT, 16)]
+    s.vertex_buffers = {0: "vb"}
+    s.uniforms = [(0, 0, "ubo")]
+    s.cull, s.front_face = CULL_BACK, FRONT_CW
+    s.depth_test = s.depth_write = True
+    s.count = 36
+    _render_targets(s, width, height, B8G8R8A8_UNORM, D16_UNORM, (0.2, 0.2, 0.2, 0.2))
+    return s
+
+
+def checker_texture(size=256, seed=7):
+    """Stand-in for Samples/data/lunarg.ppm (256x256 RGBA8, alpha forced to 255 by read_ppm)."""
+    rng = np.random.RandomState(seed)
+    img = rng.randint(0, 256, size=(size, size, 4), dtype=np.uint8)
+    yy, xx = np.mgrid[0:size, 0:size]
+    img[((xx // 16 + yy // 16) % 2) == 0, :3] //= 3
+    img[..., 3] = 255
+    return img
+
+
+def draw_textured_cube(width=500, height=500, filt=NEAREST):
+    """C2 = Samples/draw_textured_cube: VertexUV{vec4 pos, vec2 uv} stride 24, 256^2 RGBA8 texture at binding 1."""
+    s = Scene("draw_textured_cube_%s" % ("linear" if filt == LINEAR else "nearest"))
+    s.vs, s.fs = "texcube.vert", "texcube.frag"
+    pos, uv, _ = _cube_faces()
+    vb = np.concatenate([pos, uv], axis=1).astype(np.float32)
+    s.buffers["vb"] = vb.view(np.uint8).reshape(-1)
+    s.buffers["ubo"] = cube_mvp(width, height).reshape(-1).view(np.uint8)
+    s.bindings = [(0, 24, 0)]
+    s.attributes = [(0, 0, R32G32B32A32_SFLOAT, 0), (1, 0, R32G32_SFLOAT, 16)]
+    s.vertex_buffers = {0: "vb"}
+    s.uniforms = [(0, 0, "ubo")]
+    tex = checker_texture()
+    s.textures = [Texture(1, Image(R8G8B8A8_UNORM, 256, 256, data=tex.reshape(-1)), filt, CLAMP_TO_EDGE)]
+    s.cull, s.front_face = CULL_BACK, FRONT_CW
+    s.depth_test = s.depth_write = True
+    s.count = 36
+    _render_targets(s, width, height, B8G8R8A8_UNORM, D16_UNORM, (0.2, 0.2, 0.2, 0.2))
+    return s
+
+
+def _grid_mesh(nx, ny, z_of, seed):
+    """(nx x ny)-quad grid over NDC [-1,1]^2: vertices {vec4 pos, vec4 rgba}, u32 indices, CCW in framebuffer space."""
+    ix, iy = np.meshgrid(np.arange(nx + 1, dtype=np.float32), np.arange(ny + 1, dtype=np.float32))
+    x = (np.float32(-1.0) + np.float32(2.0) * ix / np.float32(nx)).astype(np.float32)
+    y = (np.float32(-1.0) + np.float32(2.0) * iy / np.float32(ny)).astype(np.float32)
+    z = z_of(ix, iy).astype(np.float32)
+    pos = np.stack([x, y, z, np.ones_like(x)], axis=-1).reshape(-1, 4)
+    rng = np.random.RandomState(seed)
+    col = rng.random_sample((pos.shape[0], 4)).astype(np.float32)
+    vb = np.concatenate([pos, col], axis=1).astype(np.float32)
+    qx, qy = np.meshgrid(np.arange(nx, dtype=np.uint32), np.arange(ny, dtype=np.uint32))
+    v00 = (qy * (nx + 1) + qx).reshape(-1)
+    v10, v01, v11 = v00 + 1, v00 + (nx + 1), v00 + (nx + 2)
+    # framebuffer y grows downwards with NDC y: (v00, v01, v11) and (v00, v11, v10) have positive edge-function area
+    idx = np.stack([v00, v01, v11, v00, v11, v10], axis=-1).reshape(-1).astype(np.uint32)
+    return vb, idx
+
+
+def mesh_indexed(width=3840, height=2160, nx=1000, ny=500, layers=1, seed=1234):
+    """C3: synthetic indexed mesh, RGBA8 + D32, opaque, LESS_OR_EQUAL. layers=1 -> M1 (2*nx*ny triangles);
+    layers=4 with nx=500, ny=250 -> M4 (four stacked grids drawn far to near)."""
+    s = Scene("mesh_%dx%dx%d_%dx%d" % (nx, ny, layers, width, height))
+    s.vs, s.fs = "cube.vert", "cube.frag"
+    vbs, ibs, base = [], [], 0
+    for layer in range(layers):
+        if layers == 1:
+            z_of = lambda ix, iy: np.float32(0.25) + np.float32(0.5) * (ix + iy) / np.float32(nx + ny)
+        else:
+            zl = np.float32(0.8 - 0.2 * layer)
+            z_of = lambda ix, iy, zl=zl: np.full_like(ix, zl)
+        vb, idx = _grid_mesh(nx, ny, z_of, seed + layer)
+        vbs.append(vb)
+        ibs.append(idx + np.uint32(base))
+        base += vb.shape[0]
+    s.buffers["vb"] = np.concatenate(vbs).view(np.uint8).reshape(-1)
+    s.buffers["ib"] = np.concatenate(ibs).view(np.uint8).reshape(-1)
+    s.buffers["ubo"] = np.identity(4, dtype=np.float32).reshape(-1).view(np.uint8)
+    s.bindings = [(0, 32, 0)]
+    s.attributes = [(0, 0, R32G32B32A32_SFLOAT, 0), (1, 0, R32G32B32A32_SFLOAT, 16)]
+    s.vertex_buffers = {0: "vb"}
+    s.index_buffer, s.index_stride = "ib", 4
+    s.uniforms = [(0, 0, "ubo")]
+    s.cull, s.front_face = CULL_NONE, FRONT_CCW
+    s.depth_test = s.depth_write = True
+    s.count = 6 * nx * ny * layers
+    _render_targets(s, width, height, R8G8B8A8_UNORM, D32_SFLOAT, (0.0, 0.0, 0.0, 1.0))
+    return s
+
+
+def overdraw_quads(width=7680, height=4320, quads=2000, tex_size=1024, seed=42, blend=True,
+                   color_fmt=R16G16B16A16_SFLOAT):
+    """C4: alpha-blended full-screen textured quads, RGBA16F, no depth; texture RGBA8 random, LINEAR, REPEAT, uv x4."""
+    s = Scene("overdraw_%dq_%dx%d" % (quads, width, height))
+    s.vs, s.fs = "texcube.vert", "texcube.frag"
+    corner = np.array([[-1, -1, 0, 1, 0, 0], [-1, 1, 0, 1, 0, 4], [1, 1, 0, 1, 4, 4], [1, -1, 0, 1, 4, 0]], dtype=np.float32)
+    vb = np.tile(corner, (quads, 1)).astype(np.float32)
+    base = (np.arange(quads, dtype=np.uint32) * 4)[:, None]
+    idx = (base + np.array([0, 1, 2, 0, 2, 3], dtype=np.uint32)[None, :]).reshape(-1).astype(np.uint32)
+    s.buffers["vb"] = vb.view(np.uint8).reshape(-1)
+    s.buffers["ib"] = idx.view(np.uint8).reshape(-1)
+    s.buffers["ubo"] = np.identity(4, dtype=np.float32).reshape(-1).view(np.uint8)
+    s.bindings = [(0, 24, 0)]
+    s.attributes = [(0, 0, R32G32B32A32_SFLOAT, 0), (1, 0, R32G32_SFLOAT, 16)]
+    s.vertex_buffers = {0: "vb"}
+    s.index_buffer, s.index_stride = "ib", 4
+    s.uniforms = [(0, 0, "ubo")]
+    rng = np.random.RandomState(seed)
+    tex = rng.randint(0, 256, size=(tex_size, tex_size, 4), dtype=np.uint8)
+    s.textures = [Texture(1, Image(R8G8B8A8_UNORM, tex_size, tex_size, data=tex.reshape(-1)), LINEAR, REPEAT)]
+    s.cull, s.front_face = CULL_NONE, FRONT_CCW
+    if blend:
+        s.blend = dict(src=BF_SRC_ALPHA, dst=BF_ONE_MINUS_SRC_ALPHA, op=BO_ADD)
+    s.count = 6 * quads
+    _render_targets(s, width, height, color_fmt, None, (0.0, 0.0, 0.0, 0.0))
+    return s
+
+
+def random_triangles(width=256, height=192, tris=200, seed=1, depth_fmt=D32_SFLOAT, color_fmt=R8G8B8A8_UNORM,
+                     cull=CULL_NONE, front_face=FRONT_CCW, perspective=True, depth_op=LESS_OR_EQUAL,
+                     topology=TRIANGLE_LIST, indexed=None, snap=False):
+    """Parity fuzz: random, overlapping, mixed-winding triangles (optionally with varying w and vertices snapped to
+    pixel centres so edge-on-centre and shared-edge cases occur)."""
+    s = Scene("random_%d_%dx%d_s%d" % (tris, width, height, seed))
+    s.vs, s.fs = "cube.vert", "cube.frag"
+    rng = np.random.RandomState(seed)
+    n = tris * 3 if topology == TRIANGLE_LIST else tris + 2
+    xy = rng.uniform(-1.1, 1.1, size=(n, 2)).astype(np.float32)
+    if snap:  # put vertices exactly on pixel centres: ((x/W + 0.5/W) * 2 - 1)
+        px = rng.randint(0, width, size=n).astype(np.float32)
+        py = rng.randint(0, height, size=n).astype(np.float32)
+        W, H = np.float32(width), np.float32(height)
+        xy[:, 0] = (px / W + (np.float32(1.0) / W) * np.float32(0.5)) * np.float32(2) - np.float32(1)
+        xy[:, 1] = (py / H + (np.float32(1.0) / H) * np.float32(0.5)) * np.float32(2) - np.float32(1)
+    z = rng.uniform(0.0, 1.0, size=(n, 1)).astype(np.float32)
+    w = rng.uniform(0.5, 3.0, size=(n, 1)).astype(np.float32) if perspective else np.ones((n, 1), dtype=np.float32)
+    pos = np.concatenate([xy * w, z * w, w], axis=1).astype(np.float32)
+    col = rng.random_sample((n, 4)).astype(np.float32)
+    vb = np.concatenate([pos, col], axis=1).astype(np.float32)
+    s.buffers["vb"] = vb.view(np.uint8).reshape(-1)
+    s.buffers["ubo"] = np.identity(4, dtype=np.float32).reshape(-1).view(np.uint8)
+    s.bindings = [(0, 32, 0)]
+    s.attributes = [(0, 0, R32G32B32A32_SFLOAT, 0), (1, 0, R32G32B32A32_SFLOAT, 16)]
+    s.vertex_buffers = {0: "vb"}
+    s.uniforms = [(0, 0, "ubo")]
+    s.topology = topology
+    s.count = n
+    if indexed:
+        dtype = {1: np.uint8, 2: np.uint16, 4: np.uint32}[indexed]
+        perm = rng.permutation(n).astype(dtype) if n <= np.iinfo(dtype).max else np.arange(n, dtype=dtype)
+        s.buffers["ib"] = perm.view(np.uint8).reshape(-1)
+        s.index_buffer, s.index_stride = "ib", indexed
+    s.cull, s.front_face = cull, front_face
+    s.depth_test = s.depth_write = depth_fmt is not None
+    s.depth_op = depth_op
+    _render_targets(s, width, height, color_fmt, depth_fmt, (0.1, 0.2, 0.3, 1.0))
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-memory backend used with the CPU oracle (tests / bench cpu_baseline only)
+
+class HostMemory:
+    def __init__(self):
+        self.arrays = {}
+
+    def alloc(self, name, nbytes, init):
+        arr = np.zeros(max(nbytes, 1), dtype=np.uint8)
+        if init is not None:
+            arr[:nbytes] = np.frombuffer(np.ascontiguousarray(init).tobytes(), dtype=np.uint8)[:nbytes]
+        self.arrays[name] = arr
+        return arr.ctypes.data
+
+
+def run_oracle(scene, window=None):
+    """Render `scene` with the CPU oracle. Returns (color bytes, depth bytes or None, DrawStats)."""
+    lib = capi.load_oracle()
+    mem = HostMemory()
+    m = materialize(scene, mem.alloc)
+    for img, att in ((scene.color, m.color_attachment), (scene.depth, m.depth_attachment)):
+        if img is not None and img.clear is not None:
+            cv, is_ds = clear_value(img)
+            rc = lib.cpvk_oracle_clear(C.byref(att), C.byref(cv), is_ds)
+            assert rc == 0, lib.cpvk_oracle_last_error()
+    stats = capi.DrawStats()
+    if window is None:
+        rc = lib.cpvk_oracle_draw(C.byref(m.desc), C.byref(m.state), C.byref(stats))
+    else:
+        rc = lib.cpvk_oracle_draw_window(C.byref(m.desc), C.byref(m.state), *window, C.byref(stats))
+    if rc != 0:
+        raise RuntimeError("oracle draw failed: %s" % lib.cpvk_oracle_last_error().decode())
+    color = mem.arrays["color"][:scene.color.nbytes].copy()
+    depth = mem.arrays["depth"][:scene.depth.nbytes].copy() if scene.depth else None
+    return color, depth, stats
