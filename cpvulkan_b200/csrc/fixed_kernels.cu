@@ -1,0 +1,334 @@
+// fixed_kernels.cu — sm_100a kernels that do not depend on application shaders: triangle setup, API-order
+// preserving tile binning, clear, row copy and blit. Compiled straight to SASS into libcpvk_cuda.so.
+//
+//   k_setup      a2 + a5 (per-primitive part) + a6 (area, facing, cull, bbox) of SURVEY §8(a)
+//   k_bin_*      new: screen-tile lists that keep API primitive order (count -> scan -> fill -> per-tile sort)
+//   k_clear      a15 / f1: ClearImage (Draw.cpp:117-149) as vector stores of one packed texel
+//   k_copy_rows  f2: vkCmdCopyImage row memcpy (CommandBuffer.Copy.cpp:77-200)
+//   k_blit       f2: vkCmdBlitImage (CommandBuffer.cpp:57-232)
+#include <cstdint>
+
+#include "cpvk_device.cuh"
+#include "fixed_kernels.h"
+
+// x86 cvttss2si semantics for static_cast<int32_t>(float) as the reference binary executes it
+// (Draw.cpp:1548-1564): NaN and out-of-range inputs give INT_MIN ("integer indefinite").
+__device__ __forceinline__ int cpvk_cvtt(float v) {
+    return (v >= 2147483648.0f || v < -2147483648.0f || v != v) ? (int)0x80000000 : (int)v;
+}
+
+__global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
+    const cpvk_u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.primCount) return;
+    // CalculatePrimitives (Draw.cpp:614-661)
+    cpvk_u32 i0, i1, i2, prov;
+    if (a.topology == 3) { prov = p * 3; i0 = p * 3; i1 = p * 3 + 1; i2 = p * 3 + 2; }
+    else if (a.topology == 4) { prov = p; i0 = p; i1 = p + 1; i2 = p + 2; }
+    else { prov = p + 1; i0 = 0; i1 = p + 1; i2 = p + 2; }
+    if (a.frontFace == 1) { const cpvk_u32 t = i0; i0 = i2; i2 = t; } // Draw.cpp:1532-1535
+    const cpvk_u32 idx[3] = {i0, i1, i2};
+    float P[3][4];
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float pos[4];
+        #pragma unroll
+        for (int c = 0; c < 4; c++) pos[c] = __uint_as_float(__ldg(a.vsOut + (cpvk_u64)c * a.nVerts + idx[k]));
+        P[k][0] = pos[0] / pos[3]; P[k][1] = pos[1] / pos[3]; P[k][2] = pos[2] / pos[3]; // glm vec4 / scalar
+        P[k][3] = pos[3];                                                                 // Draw.cpp:1544-1546
+    }
+    const float W = a.vpWidth, H = a.vpHeight;
+    int sx[3], sy[3];
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        sx[k] = cpvk_cvtt((P[k][0] + 1.0f) * 0.5f * W);
+        sy[k] = cpvk_cvtt((P[k][1] + 1.0f) * 0.5f * H);
+    }
+    int startX = max(0, min(sx[0], min(sx[1], sx[2])));
+    int startY = max(0, min(sy[0], min(sy[1], sy[2])));
+    int endX = min(cpvk_cvtt(W), max(sx[0], max(sx[1], sx[2])) + 1);
+    int endY = min(cpvk_cvtt(H), max(sy[0], max(sy[1], sy[2])) + 1);
+    // render area: attachments and this GPU's band (the reference has neither clamp: writes past the attachment
+    // are undefined behaviour there)
+    startX = max(startX, a.clipX0); startY = max(startY, a.clipY0);
+    endX = min(endX, a.clipX1); endY = min(endY, a.clipY1);
+
+    // GetFragmentInput (Draw.cpp:879-903): area, facing, edge orientation, cull
+    float area = (P[2][0] - P[0][0]) * (P[1][1] - P[0][1]) - (P[2][1] - P[0][1]) * (P[1][0] - P[0][0]);
+    bool front;
+    int ea[3], eb[3];
+    if (area < 0.0f) { area = -area; front = false; ea[0] = 2; eb[0] = 1; ea[1] = 0; eb[1] = 2; ea[2] = 1; eb[2] = 0; }
+    else { front = true; ea[0] = 1; eb[0] = 2; ea[1] = 2; eb[1] = 0; ea[2] = 0; eb[2] = 1; }
+    const bool culled = ((a.cullMode & 2u) && !front) || ((a.cullMode & 1u) && front);
+
+    CpvkTriSetup s;
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float ax = 0, ay = 0, bx = 0, by = 0;
+        #pragma unroll
+        for (int j = 0; j < 3; j++) { if (ea[k] == j) { ax = P[j][0]; ay = P[j][1]; } if (eb[k] == j) { bx = P[j][0]; by = P[j][1]; } }
+        s.e[k][0] = ax; s.e[k][1] = ay; s.e[k][2] = by - ay; s.e[k][3] = bx - ax;
+        s.z[k] = P[k][2]; s.pw[k] = P[k][3]; s.idx[k] = idx[k];
+    }
+    s.area = area; s.flags = front ? 1u : 0u; s.provoking = prov;
+    a.setups[p] = s;
+    CpvkBBox bb;
+    if (culled || endX <= startX || endY <= startY) { bb.x0 = bb.y0 = bb.x1 = bb.y1 = 0; }
+    else { bb.x0 = (short)startX; bb.y0 = (short)startY; bb.x1 = (short)endX; bb.y1 = (short)endY; }
+    a.bboxes[p] = bb;
+}
+
+// ---- binning ----
+// Pass 0 counts (primitive, tile) pairs, pass 1 writes primitive ids at atomically claimed positions inside each
+// tile's segment; k_bin_sort then sorts every segment ascending, which restores API order exactly (ids are unique).
+// Primitives touching more than CPVK_BIN_SMALL tiles are deferred to k_bin_large, one CTA per primitive.
+__global__ void __launch_bounds__(256) k_bin(CpvkBinArgs a, int pass) {
+    const cpvk_u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.primCount) return;
+    const CpvkBBox bb = a.bboxes[p];
+    if (bb.x1 <= bb.x0) return;
+    const int tx0 = bb.x0 / CPVK_TILE_W, tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty0 = bb.y0 / CPVK_TILE_H, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
+    const int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+    if (n > CPVK_BIN_SMALL) {
+        if (pass == 0) { const cpvk_u32 slot = atomicAdd(a.meta + 2, 1u); a.largeList[slot] = p; }
+        return;
+    }
+    for (int ty = ty0; ty <= ty1; ty++)
+        for (int tx = tx0; tx <= tx1; tx++) {
+            const cpvk_u32 t = (cpvk_u32)ty * a.tilesX + (cpvk_u32)tx;
+            if (pass == 0) atomicAdd(a.counts + t, 1u);
+            else a.lists[atomicAdd(a.cursors + t, 1u)] = p;
+        }
+}
+__global__ void __launch_bounds__(256) k_bin_large(CpvkBinArgs a, int pass) {
+    const cpvk_u32 nLarge = a.meta[2];
+    for (cpvk_u32 li = blockIdx.x; li < nLarge; li += gridDim.x) {
+        const cpvk_u32 p = a.largeList[li];
+        const CpvkBBox bb = a.bboxes[p];
+        const int tx0 = bb.x0 / CPVK_TILE_W, tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty0 = bb.y0 / CPVK_TILE_H, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
+        const int tw = tx1 - tx0 + 1, n = tw * (ty1 - ty0 + 1);
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const int ty = ty0 + k / tw, tx = tx0 + k % tw;
+            const cpvk_u32 t = (cpvk_u32)ty * a.tilesX + (cpvk_u32)tx;
+            if (pass == 0) atomicAdd(a.counts + t, 1u);
+            else a.lists[atomicAdd(a.cursors + t, 1u)] = p;
+        }
+    }
+}
+// Single-CTA exclusive scan of the per-tile counts (<= a few 10^4 tiles). offsets[tiles] = total.
+// meta[0] = total entries, meta[1] = longest list.
+__global__ void __launch_bounds__(1024) k_bin_scan(CpvkBinArgs a) {
+    __shared__ cpvk_u32 warpSums[32];
+    __shared__ cpvk_u32 carry, maxShared;
+    const cpvk_u32 tiles = a.tilesX * a.tilesY;
+    if (threadIdx.x == 0) { carry = 0; maxShared = 0; }
+    __syncthreads();
+    cpvk_u32 localMax = 0;
+    for (cpvk_u32 base = 0; base < tiles; base += blockDim.x) {
+        const cpvk_u32 i = base + threadIdx.x;
+        const cpvk_u32 v = i < tiles ? a.counts[i] : 0u;
+        localMax = max(localMax, v);
+        cpvk_u32 x = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const cpvk_u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            cpvk_u32 w = warpSums[threadIdx.x];
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const cpvk_u32 y = __shfl_up_sync(0xFFFFFFFFu, w, d); if (threadIdx.x >= d) w += y; }
+            warpSums[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const cpvk_u32 warpBase = (threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u;
+        const cpvk_u32 excl = carry + warpBase + x - v;
+        if (i < tiles) { a.offsets[i] = excl; a.cursors[i] = excl; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warpSums[31];
+        __syncthreads();
+    }
+    atomicMax(&maxShared, localMax);
+    __syncthreads();
+    if (threadIdx.x == 0) { a.offsets[tiles] = carry; a.meta[0] = carry; a.meta[1] = maxShared; }
+}
+// Per-tile ascending sort. Lists that fit the dynamic shared buffer use a bitonic network; longer ones fall back
+// to an in-place stable LSD split sort through `scratch` (rare: > capacity primitives over one 32x32 tile).
+__global__ void __launch_bounds__(256) k_bin_sort(CpvkBinArgs a, cpvk_u32 capacity) {
+    extern __shared__ cpvk_u32 sKeys[];
+    const cpvk_u32 t = blockIdx.x;
+    const cpvk_u32 begin = a.offsets[t], n = a.offsets[t + 1] - begin;
+    if (n < 2) return;
+    cpvk_u32* list = a.lists + begin;
+    if (n <= capacity) {
+        cpvk_u32 m = 1; while (m < n) m <<= 1;
+        for (cpvk_u32 i = threadIdx.x; i < m; i += blockDim.x) sKeys[i] = i < n ? list[i] : 0xFFFFFFFFu;
+        __syncthreads();
+        for (cpvk_u32 k = 2; k <= m; k <<= 1)
+            for (cpvk_u32 j = k >> 1; j > 0; j >>= 1) {
+                for (cpvk_u32 i = threadIdx.x; i < m; i += blockDim.x) {
+                    const cpvk_u32 l = i ^ j;
+                    if (l > i) {
+                        const cpvk_u32 x = sKeys[i], y = sKeys[l];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { sKeys[i] = y; sKeys[l] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (cpvk_u32 i = threadIdx.x; i < n; i += blockDim.x) list[i] = sKeys[i];
+        return;
+    }
+    // fallback: one-bit stable splits, bit 0 .. highest set bit of primCount, ping-ponging list <-> scratch
+    __shared__ cpvk_u32 sWarp[8], sZeros, sBaseZ, sBaseO;
+    cpvk_u32* src = list; cpvk_u32* dst = a.scratch + begin;
+    int bitsNeeded = 0; while ((a.primCount >> bitsNeeded) != 0) bitsNeeded++;
+    for (int bit = 0; bit < bitsNeeded; bit++) {
+        if (threadIdx.x == 0) sZeros = 0;
+        __syncthreads();
+        cpvk_u32 z = 0;
+        for (cpvk_u32 i = threadIdx.x; i < n; i += blockDim.x) z += ((src[i] >> bit) & 1u) ^ 1u;
+        atomicAdd(&sZeros, z);
+        __syncthreads();
+        if (threadIdx.x == 0) { sBaseZ = 0; sBaseO = sZeros; }
+        __syncthreads();
+        for (cpvk_u32 base = 0; base < n; base += blockDim.x) {
+            const cpvk_u32 i = base + threadIdx.x;
+            const bool valid = i < n;
+            const cpvk_u32 key = valid ? src[i] : 0u;
+            const bool one = valid && ((key >> bit) & 1u);
+            const bool zero = valid && !one;
+            const cpvk_u32 zm = __ballot_sync(0xFFFFFFFFu, zero), om = __ballot_sync(0xFFFFFFFFu, one);
+            const cpvk_u32 lt = (1u << (threadIdx.x & 31)) - 1u;
+            const int w = threadIdx.x >> 5;
+            if ((threadIdx.x & 31) == 0) sWarp[w] = (__popc(zm) << 16) | __popc(om);
+            __syncthreads();
+            cpvk_u32 zBefore = 0, oBefore = 0, zAll = 0, oAll = 0;
+            for (int q = 0; q < 8; q++) { const cpvk_u32 v = sWarp[q]; if (q < w) { zBefore += v >> 16; oBefore += v & 0xFFFFu; } zAll += v >> 16; oAll += v & 0xFFFFu; }
+            if (zero) dst[sBaseZ + zBefore + __popc(zm & lt)] = key;
+            if (one) dst[sBaseO + oBefore + __popc(om & lt)] = key;
+            __syncthreads();
+            if (threadIdx.x == 0) { sBaseZ += zAll; sBaseO += oAll; }
+            __syncthreads();
+        }
+        cpvk_u32* tmp = src; src = dst; dst = tmp;
+    }
+    if (src != list) { for (cpvk_u32 i = threadIdx.x; i < n; i += blockDim.x) list[i] = src[i]; }
+}
+
+// ---- clear: every texel gets the same packed bytes, so pack once per thread and store 16 bytes at a time ----
+__global__ void __launch_bounds__(256) k_clear(CpvkDevAttachment img, CpvkClearArgs c) {
+    __shared__ __align__(16) cpvk_u8 pattern[48]; // lcm(texel, 16) bytes of repeated texel (texel in {1,2,3,4,8,16}); 48 covers 3-byte texels
+    const cpvk_u32 texel = cpvk_texel_size(img.format);
+    if (threadIdx.x == 0) {
+        __align__(16) cpvk_u8 one[16];
+        if (c.isDepthStencil) cpvk_set_depth_stencil(img.format, one, c.depth, c.stencil);
+        else if (cpvk_format_is_int(img.format)) cpvk_set_pixel_int(img.format, one, c.u);
+        else cpvk_set_pixel_f32_dyn(img.format, one, c.f);
+        for (cpvk_u32 i = 0; i < 48; i++) pattern[i] = one[i % texel];
+    }
+    __syncthreads();
+    const cpvk_u32 rowBytes = texel * img.width;
+    cpvk_u8* base = reinterpret_cast<cpvk_u8*>(img.address);
+    const bool vec = ((img.address | img.rowPitch | rowBytes) & 15) == 0 && (16 % texel) == 0;
+    if (vec) {
+        const uint4 v = *reinterpret_cast<const uint4*>(pattern);
+        const cpvk_u64 per = rowBytes >> 4, total = per * img.height;
+        for (cpvk_u64 i = (cpvk_u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (cpvk_u64)gridDim.x * blockDim.x) {
+            const cpvk_u64 r = i / per, q = i - r * per;
+            reinterpret_cast<uint4*>(base + r * img.rowPitch)[q] = v;
+        }
+    } else {
+        const cpvk_u64 total = (cpvk_u64)img.width * img.height;
+        for (cpvk_u64 i = (cpvk_u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (cpvk_u64)gridDim.x * blockDim.x) {
+            const cpvk_u64 r = i / img.width, x = i - r * img.width;
+            cpvk_u8* d = base + r * img.rowPitch + x * texel;
+            for (cpvk_u32 k = 0; k < texel; k++) d[k] = pattern[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_copy_rows(cpvk_u8* dst, cpvk_u32 dstPitch, const cpvk_u8* src, cpvk_u32 srcPitch, cpvk_u32 rowBytes, cpvk_u32 rows) {
+    const cpvk_u64 align = (cpvk_u64)dst | (cpvk_u64)src | dstPitch | srcPitch | rowBytes;
+    const cpvk_u64 stride = (cpvk_u64)gridDim.x * blockDim.x, start = (cpvk_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((align & 15) == 0) {
+        const cpvk_u64 per = rowBytes >> 4, total = per * rows;
+        for (cpvk_u64 i = start; i < total; i += stride) { const cpvk_u64 r = i / per, q = i - r * per;
+            reinterpret_cast<uint4*>(dst + r * dstPitch)[q] = __ldg(reinterpret_cast<const uint4*>(src + r * srcPitch) + q); }
+    } else {
+        const cpvk_u64 total = (cpvk_u64)rowBytes * rows;
+        for (cpvk_u64 i = start; i < total; i += stride) { const cpvk_u64 r = i / rowBytes, q = i - r * rowBytes; dst[r * dstPitch + q] = src[r * srcPitch + q]; }
+    }
+}
+
+// vkCmdBlitImage, one 2-D colour region: the reference samples the source as a 3-D image with lod 1 on a one-level
+// chain (-> level 0), clamp-to-edge, both z taps on slice 0 with weight 0, then SetPixel (CommandBuffer.cpp:75-226).
+__global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
+    const int dstW = abs(b.dstX1 - b.dstX0), dstH = abs(b.dstY1 - b.dstY0);
+    const bool negW = b.dstX1 < b.dstX0, negH = b.dstY1 < b.dstY0;
+    const cpvk_u64 total = (cpvk_u64)dstW * dstH;
+    const cpvk_u32 dtexel = cpvk_texel_size(b.dst.format);
+    CpvkDevDescriptor d; // register-resident view of the source
+    d.type = 2; d.format = b.src.format; d.dimensions = 3; d.levelCount = 1;
+    d.levels[0].address = b.src.address; d.levels[0].width = b.src.width; d.levels[0].height = b.src.height; d.levels[0].depth = 1;
+    d.sampler.addressModeU = d.sampler.addressModeV = d.sampler.addressModeW = 2; d.sampler.mipmapMode = 0; d.sampler.borderColor = 0;
+    for (cpvk_u64 i = (cpvk_u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (cpvk_u64)gridDim.x * blockDim.x) {
+        const int y = (int)(i / dstW), x = (int)(i - (cpvk_u64)y * dstW);
+        const int dstX = negW ? x + b.dstX1 : x + b.dstX0, dstY = negH ? y + b.dstY1 : y + b.dstY0;
+        const float u = ((float)dstX + 0.5f - (float)b.dstX0) * ((float)(b.srcX1 - b.srcX0) / (float)(b.dstX1 - b.dstX0)) + (float)b.srcX0;
+        const float v = ((float)dstY + 0.5f - (float)b.dstY0) * ((float)(b.srcY1 - b.srcY0) / (float)(b.dstY1 - b.dstY0)) + (float)b.srcY0;
+        const float w = (0.0f + 0.5f - 0.0f) * ((float)(1 - 0) / (float)(1 - 0)) + 0.0f;
+        const float coord[3] = {u / (float)b.src.width, v / (float)b.src.height, w / 1.0f};
+        const CpvkVec4 value = cpvk_sample_image(&d, 3, coord, 1.0f, b.filter, b.filter);
+        if (dstX < 0 || dstY < 0 || (cpvk_u32)dstX >= b.dst.width || (cpvk_u32)dstY >= b.dst.height) continue;
+        cpvk_set_pixel_f32_dyn(b.dst.format, reinterpret_cast<cpvk_u8*>(b.dst.address) + (cpvk_u64)dstY * b.dst.rowPitch + (cpvk_u64)dstX * dtexel, value.v);
+    }
+}
+
+// ---- host-callable launchers (cpvk_abi.cpp is plain C++) ----
+static inline unsigned cpvk_grid(unsigned long long n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" {
+cudaError_t cpvk_launch_setup(const CpvkSetupArgs* a, cudaStream_t s) {
+    if (a->primCount == 0) return cudaSuccess;
+    k_setup<<<cpvk_grid(a->primCount, 256), 256, 0, s>>>(*a);
+    return cudaGetLastError();
+}
+cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, cudaStream_t s) {
+    if (a->primCount == 0) return cudaSuccess;
+    k_bin<<<cpvk_grid(a->primCount, 256), 256, 0, s>>>(*a, pass);
+    k_bin_large<<<592, 256, 0, s>>>(*a, pass); // 148 SMs x 4 resident CTAs; loops over the deferred list
+    return cudaGetLastError();
+}
+cudaError_t cpvk_launch_bin_scan(const CpvkBinArgs* a, cudaStream_t s) {
+    k_bin_scan<<<1, 1024, 0, s>>>(*a);
+    return cudaGetLastError();
+}
+cudaError_t cpvk_launch_bin_sort(const CpvkBinArgs* a, unsigned capacity, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+    k_bin_sort<<<a->tilesX * a->tilesY, 256, capacity * 4, s>>>(*a, capacity);
+    return cudaGetLastError();
+}
+cudaError_t cpvk_launch_clear(const CpvkDevAttachment* img, const CpvkClearArgs* c, cudaStream_t s) {
+    const unsigned long long texels = (unsigned long long)img->width * img->height;
+    unsigned grid = cpvk_grid(texels, 256 * 4);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid == 0) return cudaSuccess;
+    k_clear<<<grid, 256, 0, s>>>(*img, *c);
+    return cudaGetLastError();
+}
+cudaError_t cpvk_launch_copy_rows(unsigned long long dst, unsigned dstPitch, unsigned long long src, unsigned srcPitch, unsigned rowBytes, unsigned rows, cudaStream_t s) {
+    if (!rowBytes || !rows) return cudaSuccess;
+    unsigned grid = cpvk_grid((unsigned long long)rowBytes * rows / 16 + 1, 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    k_copy_rows<<<grid, 256, 0, s>>>((cpvk_u8*)dst, dstPitch, (const cpvk_u8*)src, srcPitch, rowBytes, rows);
+    return cudaGetLastError();
+}
+cudaError_t cpvk_launch_blit(const CpvkBlitArgs* b, cudaStream_t s) {
+    const unsigned long long total = (unsigned long long)abs(b->dstX1 - b->dstX0) * (unsigned long long)abs(b->dstY1 - b->dstY0);
+    if (!total) return cudaSuccess;
+    unsigned grid = cpvk_grid(total, 256);
+    if (grid > 148 * 32) grid = 148 * 32;
+    k_blit<<<grid, 256, 0, s>>>(*b);
+    return cudaGetLastError();
+}
+}

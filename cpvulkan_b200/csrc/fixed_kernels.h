@@ -1,0 +1,54 @@
+// fixed_kernels.h — argument blocks and host launchers of the shader-independent kernels (fixed_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "cpvk_device.cuh"
+
+#define CPVK_BIN_SMALL 16 /* primitives touching more tiles than this are binned by a whole CTA */
+
+struct CpvkSetupArgs {
+    const cpvk_u32* vsOut;
+    cpvk_u32 nVerts, primCount;
+    cpvk_u32 topology, frontFace, cullMode;
+    float vpWidth, vpHeight;
+    cpvk_i32 clipX0, clipY0, clipX1, clipY1;
+    CpvkTriSetup* setups;
+    CpvkBBox* bboxes;
+};
+
+struct CpvkBinArgs {
+    const CpvkBBox* bboxes;
+    cpvk_u32 primCount, tilesX, tilesY;
+    cpvk_u32* counts;    // [tiles]
+    cpvk_u32* offsets;   // [tiles + 1]
+    cpvk_u32* cursors;   // [tiles]
+    cpvk_u32* lists;     // [total entries]
+    cpvk_u32* scratch;   // [total entries] or null (only needed by the long-list sort fallback)
+    cpvk_u32* largeList; // [primCount]
+    cpvk_u32* meta;      // [0] total entries, [1] longest list, [2] deferred-primitive count
+};
+
+struct CpvkClearArgs {
+    float f[4];
+    cpvk_u32 u[4];
+    float depth;
+    cpvk_u32 stencil;
+    int isDepthStencil;
+};
+
+struct CpvkBlitArgs {
+    CpvkDevAttachment src, dst;
+    int srcX0, srcY0, srcX1, srcY1;
+    int dstX0, dstY0, dstX1, dstY1;
+    cpvk_u32 filter;
+};
+
+extern "C" {
+cudaError_t cpvk_launch_setup(const CpvkSetupArgs* a, cudaStream_t s);
+cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, cudaStream_t s);
+cudaError_t cpvk_launch_bin_scan(const CpvkBinArgs* a, cudaStream_t s);
+cudaError_t cpvk_launch_bin_sort(const CpvkBinArgs* a, unsigned capacity, cudaStream_t s);
+cudaError_t cpvk_launch_clear(const CpvkDevAttachment* img, const CpvkClearArgs* c, cudaStream_t s);
+cudaError_t cpvk_launch_copy_rows(unsigned long long dst, unsigned dstPitch, unsigned long long src, unsigned srcPitch, unsigned rowBytes, unsigned rows, cudaStream_t s);
+cudaError_t cpvk_launch_blit(const CpvkBlitArgs* b, cudaStream_t s);
+}

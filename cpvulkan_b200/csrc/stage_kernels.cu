@@ -1,0 +1,389 @@
+// stage_kernels.cu — the two sm_100a pipeline stages that call into application shaders.
+// Compiled by nvcc to LTO-IR at build time; at vkCreateGraphicsPipelines time nvJitLink links this with the
+// NVRTC-compiled shader translation unit (cpvk_vs_main / cpvk_fs_main / cpvk_spec_*), so the shader bodies and
+// all baked pipeline state inline into these kernels — the GPU counterpart of the reference's per-pipeline
+// JIT'd vertex and fragment wrappers (LLVMRuntime/PipelineCompiler.cpp:499-982, :991-1799).
+//
+//   cpvk_k_vertex : a1 + a3 of SURVEY §8(a) — input assembly + vertex fetch + VS + record store, one thread/index
+//   cpvk_k_raster : a5 (pixel loop) a6 a7 a8 a9 a10 a11 a12 a13 — coverage, interpolation, FS, late depth/stencil,
+//                   blend and format pack on a shared-memory tile; one CTA per 32x32 screen tile, API order kept.
+#include "cpvk_device.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Vertex stage. ProcessInputAssembler[Indexed] (Draw.cpp:675-760): rawId = i,
+// vertexId = firstVertex + i  or  vertexOffset + index[firstIndex + i]; the VS runs once per index (no cache).
+extern "C" __global__ void __launch_bounds__(256) cpvk_k_vertex(const __grid_constant__ CpvkDrawParams p) {
+    const cpvk_u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.count) return;
+    cpvk_u32 vertexId;
+    if (p.indexStride == 0) {
+        vertexId = p.first + i;
+    } else {
+        const cpvk_u8* ib = reinterpret_cast<const cpvk_u8*>(p.indexBuffer);
+        const cpvk_u64 k = (cpvk_u64)p.first + i;
+        cpvk_u32 index;
+        if (p.indexStride == 4) index = __ldg(reinterpret_cast<const cpvk_u32*>(ib) + k);
+        else if (p.indexStride == 2) index = __ldg(reinterpret_cast<const cpvk_u16*>(ib) + k);
+        else index = __ldg(ib + k);
+        vertexId = (cpvk_u32)p.vertexOffset + index;
+    }
+    cpvk_vs_main(vertexId, p.instance, i, &p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fragment back end.
+
+__device__ __forceinline__ bool cpvk_fcompare(float reference, float value, cpvk_u32 op) {
+    // CompileFCompareTest (PipelineCompiler.cpp:1492-1508): ordered compares, NaN fails (NOT_EQUAL = ONE).
+    switch (op) {
+    case 0: return false;
+    case 1: return reference < value;
+    case 2: return reference == value;
+    case 3: return reference <= value;
+    case 4: return reference > value;
+    case 5: return reference < value || reference > value;
+    case 6: return reference >= value;
+    default: return true;
+    }
+}
+__device__ __forceinline__ bool cpvk_icompare(cpvk_u32 reference, cpvk_u32 value, cpvk_u32 op) {
+    switch (op) {
+    case 0: return false;
+    case 1: return reference < value;
+    case 2: return reference == value;
+    case 3: return reference <= value;
+    case 4: return reference > value;
+    case 5: return reference != value;
+    case 6: return reference >= value;
+    default: return true;
+    }
+}
+__device__ __forceinline__ cpvk_u32 cpvk_stencil_result(cpvk_u32 op, cpvk_u32 cur, cpvk_u32 ref) {
+    // CompileGetStencilResult (PipelineCompiler.cpp:1382-1413); INC/DEC_CLAMP are *signed* i8 saturation there.
+    switch (op) {
+    case 0: return cur;
+    case 1: return 0;
+    case 2: return ref;
+    case 3: { int v = (int)(signed char)cur + 1; if (v > 127) v = 127; return (cpvk_u32)v & 0xFFu; }
+    case 4: { int v = (int)(signed char)cur - 1; if (v < -128) v = -128; return (cpvk_u32)v & 0xFFu; }
+    case 5: return (~cur) & 0xFFu;
+    case 6: return (cur + 1) & 0xFFu;
+    default: return (cur - 1) & 0xFFu;
+    }
+}
+
+// ApplyBlendFactor (Draw.cpp:956-1103)
+__device__ __forceinline__ void cpvk_blend_factor(const float s[4], const float d[4], const float c[4], cpvk_u32 colourFactor,
+                                                  cpvk_u32 alphaFactor, float v[4]) {
+    v[0] = v[1] = v[2] = v[3] = 0.0f;
+    switch (colourFactor) {
+    case 0: break;
+    case 1: v[0] = v[1] = v[2] = v[3] = 1.0f; break;
+    case 2: for (int i = 0; i < 4; i++) v[i] = s[i]; break;
+    case 3: for (int i = 0; i < 4; i++) v[i] = 1.0f - s[i]; break;
+    case 4: for (int i = 0; i < 4; i++) v[i] = d[i]; break;
+    case 5: for (int i = 0; i < 4; i++) v[i] = 1.0f - d[i]; break;
+    case 6: v[0] = v[1] = v[2] = v[3] = s[3]; break;
+    case 7: v[0] = v[1] = v[2] = v[3] = 1.0f - s[3]; break;
+    case 8: v[0] = v[1] = v[2] = v[3] = d[3]; break;
+    case 9: v[0] = v[1] = v[2] = v[3] = 1.0f - d[3]; break;
+    case 10: for (int i = 0; i < 4; i++) v[i] = c[i]; break;
+    case 11: for (int i = 0; i < 4; i++) v[i] = 1.0f - c[i]; break;
+    case 12: v[0] = v[1] = v[2] = v[3] = c[3]; break;
+    case 13: v[0] = v[1] = v[2] = v[3] = 1.0f - c[3]; break;
+    case 14: { const float a = 1.0f - d[3]; const float f = a < s[3] ? a : s[3]; v[0] = v[1] = v[2] = f; v[3] = 1.0f; break; } // std::min(sa, 1-da)
+    default: break;
+    }
+    if (colourFactor != alphaFactor) {
+        switch (alphaFactor) {
+        case 0: v[3] = 0.0f; break;
+        case 1: case 14: v[3] = 1.0f; break;
+        case 2: case 6: v[3] = s[3]; break;
+        case 3: case 7: v[3] = 1.0f - s[3]; break;
+        case 4: case 8: v[3] = d[3]; break;
+        case 5: case 9: v[3] = 1.0f - d[3]; break;
+        case 10: case 12: v[3] = c[3]; break;
+        case 11: case 13: v[3] = 1.0f - c[3]; break;
+        default: break;
+        }
+    }
+}
+// ApplyBlend (Draw.cpp:1105-1262)
+__device__ __forceinline__ void cpvk_apply_blend(const float s[4], const float d[4], int a, float out[4]) {
+    const int base = CPVK_SPEC_BLEND0 + a * 8;
+    const cpvk_u32 srcC = cpvk_spec_u32(base + 1), dstC = cpvk_spec_u32(base + 2), opC = cpvk_spec_u32(base + 3);
+    const cpvk_u32 srcA = cpvk_spec_u32(base + 4), dstA = cpvk_spec_u32(base + 5), opA = cpvk_spec_u32(base + 6);
+    const float c[4] = {cpvk_spec_f32(0), cpvk_spec_f32(1), cpvk_spec_f32(2), cpvk_spec_f32(3)};
+    float sf[4], df[4];
+    cpvk_blend_factor(s, d, c, srcC, srcA, sf);
+    cpvk_blend_factor(s, d, c, dstC, dstA, df);
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        switch (opC) {
+        case 0: out[i] = s[i] * sf[i] + d[i] * df[i]; break;
+        case 1: out[i] = s[i] * sf[i] - d[i] * df[i]; break;
+        case 2: out[i] = d[i] * df[i] - s[i] * sf[i]; break;
+        case 3: out[i] = d[i] < s[i] ? d[i] : s[i]; break; // glm::min
+        default: out[i] = s[i] < d[i] ? d[i] : s[i]; break; // glm::max
+        }
+    }
+    if (opC != opA) {
+        switch (opA) {
+        case 0: out[3] = s[3] * sf[3] + d[3] * df[3]; break;
+        case 1: out[3] = s[3] * sf[3] - d[3] * df[3]; break;
+        case 2: out[3] = d[3] * df[3] - s[3] * sf[3]; break;
+        case 3: out[3] = d[3] < s[3] ? d[3] : s[3]; break; // std::min
+        default: out[3] = s[3] < d[3] ? d[3] : s[3]; break; // std::max
+        }
+    }
+}
+
+// Copy `bytes` (a multiple of the texel size) between a global row segment and shared memory, all threads of
+// the CTA cooperating over `rows` rows; 16-byte vectors when both sides allow, else 4-byte words, else bytes.
+__device__ __forceinline__ void cpvk_tile_copy(cpvk_u8* dst, cpvk_u32 dstPitch, const cpvk_u8* src, cpvk_u32 srcPitch, cpvk_u32 bytes, cpvk_u32 rows) {
+    const cpvk_u64 align = ((cpvk_u64)dst | (cpvk_u64)src | dstPitch | srcPitch | bytes);
+    if ((align & 15) == 0) {
+        const cpvk_u32 per = bytes >> 4;
+        for (cpvk_u32 i = threadIdx.x; i < per * rows; i += blockDim.x) {
+            const cpvk_u32 r = i / per, c = i - r * per;
+            reinterpret_cast<uint4*>(dst + (cpvk_u64)r * dstPitch)[c] = reinterpret_cast<const uint4*>(src + (cpvk_u64)r * srcPitch)[c];
+        }
+    } else if ((align & 3) == 0) {
+        const cpvk_u32 per = bytes >> 2;
+        for (cpvk_u32 i = threadIdx.x; i < per * rows; i += blockDim.x) {
+            const cpvk_u32 r = i / per, c = i - r * per;
+            reinterpret_cast<cpvk_u32*>(dst + (cpvk_u64)r * dstPitch)[c] = reinterpret_cast<const cpvk_u32*>(src + (cpvk_u64)r * srcPitch)[c];
+        }
+    } else {
+        for (cpvk_u32 i = threadIdx.x; i < bytes * rows; i += blockDim.x) {
+            const cpvk_u32 r = i / bytes, c = i - r * bytes;
+            dst[(cpvk_u64)r * dstPitch + c] = src[(cpvk_u64)r * srcPitch + c];
+        }
+    }
+}
+
+extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
+
+// One CTA per screen tile. Warp w owns the 16x8 sub-rectangle (w&1, w>>1) of the tile, so no two warps ever touch
+// the same pixel; inside a warp, triangles are taken strictly in list (= API) order and each triangle's candidate
+// pixels are spread over the lanes, one pixel per lane per step, so a pixel sees its fragments in API order —
+// the ordering the reference gets from its nested loops (Draw.cpp:1526-1593). Colour and depth live in shared
+// memory in their *storage* format for the whole tile lifetime: every ROP is the reference's get/set-pixel
+// round trip (GlslFunctions.cpp:842-928) on shared memory, and HBM sees one read and one write per tile byte.
+extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(const __grid_constant__ CpvkDrawParams p) {
+    const cpvk_u32 tile = blockIdx.x;
+    const cpvk_u32 listBegin = p.tileOffsets[tile], listEnd = p.tileOffsets[tile + 1];
+    if (listBegin == listEnd) return;
+    const cpvk_u32 ty = tile / p.tilesX, tx = tile - ty * p.tilesX;
+    const int tileX0 = (int)tx * CPVK_TILE_W, tileY0 = (int)ty * CPVK_TILE_H;
+
+    const cpvk_u32 dsFormat = cpvk_spec_u32(CPVK_SPEC_DS_FORMAT);
+    const bool depthTest = cpvk_spec_u32(CPVK_SPEC_DEPTH_TEST) != 0, depthWrite = cpvk_spec_u32(CPVK_SPEC_DEPTH_WRITE) != 0;
+    const bool boundsTest = cpvk_spec_u32(CPVK_SPEC_BOUNDS_TEST) != 0, stencilTest = cpvk_spec_u32(CPVK_SPEC_STENCIL_TEST) != 0;
+    const cpvk_u32 depthOp = cpvk_spec_u32(CPVK_SPEC_DEPTH_OP);
+    const int colorCount = (int)cpvk_spec_u32(CPVK_SPEC_COLOR_COUNT);
+    const bool fmtDepth = dsFormat != 0 && dsFormat != 127, fmtStencil = dsFormat >= 127 && dsFormat <= 130 && dsFormat != 0;
+    const bool stencilOn = stencilTest && fmtStencil;
+    const bool dsUsed = dsFormat != 0 && p.ds.address != 0 && (depthTest || boundsTest || stencilOn);
+
+    // ---- shared-memory layout: [xf 32][yf 32] | depth tile | colour tiles ----
+    float* sXf = reinterpret_cast<float*>(cpvk_smem);
+    float* sYf = sXf + CPVK_TILE_W;
+    cpvk_u32 smemOff = (CPVK_TILE_W + CPVK_TILE_H) * 4;
+    const cpvk_u32 dsTexel = dsFormat ? cpvk_texel_size(dsFormat) : 0;
+    cpvk_u8* sDepth = cpvk_smem + smemOff;
+    const cpvk_u32 dsPitch = dsTexel * CPVK_TILE_W;
+    if (dsUsed) smemOff += ((dsPitch * CPVK_TILE_H) + 15u) & ~15u;
+    cpvk_u8* sColor[CPVK_MAX_COLOR];
+    cpvk_u32 cTexel[CPVK_MAX_COLOR];
+    #pragma unroll
+    for (int a = 0; a < CPVK_MAX_COLOR; a++) {
+        sColor[a] = nullptr; cTexel[a] = 0;
+        if (a < colorCount) {
+            const cpvk_u32 cf = cpvk_spec_u32(CPVK_SPEC_COLOR_FORMAT0 + a);
+            if (cf != 0 && p.color[a].address != 0) {
+                cTexel[a] = cpvk_texel_size(cf);
+                sColor[a] = cpvk_smem + smemOff;
+                smemOff += (cTexel[a] * CPVK_TILE_W * CPVK_TILE_H + 15u) & ~15u;
+            }
+        }
+    }
+
+    // tile extent inside the render area
+    const int x1 = min(tileX0 + CPVK_TILE_W, p.clipX1), y1 = min(tileY0 + CPVK_TILE_H, p.clipY1);
+    const int tw = x1 - tileX0, th = y1 - tileY0;
+    if (tw <= 0 || th <= 0) return;
+
+    // pixel centres in NDC, exactly as Draw.cpp:1524,1573,1578: ((float)x / W + (1/W)*0.5) * 2 - 1
+    if (threadIdx.x < CPVK_TILE_W) {
+        const float W = p.vpWidth; const float hp = (1.0f / W) * 0.5f;
+        sXf[threadIdx.x] = ((float)(tileX0 + (int)threadIdx.x) / W + hp) * 2.0f - 1.0f;
+    } else if (threadIdx.x < CPVK_TILE_W + CPVK_TILE_H) {
+        const int j = (int)threadIdx.x - CPVK_TILE_W;
+        const float H = p.vpHeight; const float hp = (1.0f / H) * 0.5f;
+        sYf[j] = ((float)(tileY0 + j) / H + hp) * 2.0f - 1.0f;
+    }
+    // ---- stage the tile: HBM -> shared ----
+    if (dsUsed)
+        cpvk_tile_copy(sDepth, dsPitch, reinterpret_cast<const cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel,
+                       p.ds.rowPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th);
+    #pragma unroll
+    for (int a = 0; a < CPVK_MAX_COLOR; a++)
+        if (sColor[a])
+            cpvk_tile_copy(sColor[a], cTexel[a] * CPVK_TILE_W, reinterpret_cast<const cpvk_u8*>(p.color[a].address) + (cpvk_u64)tileY0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a],
+                           p.color[a].rowPitch, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp region (16 wide, 8 tall) clipped to the tile extent
+    const int rx0 = tileX0 + (warp & 1) * 16, ry0 = tileY0 + (warp >> 1) * 8;
+    const int rx1 = min(rx0 + 16, x1), ry1 = min(ry0 + 8, y1);
+    cpvk_u32 nCov = 0, nPass = 0;
+
+    if (rx0 < rx1 && ry0 < ry1) {
+        for (cpvk_u32 base = listBegin; base < listEnd; base += 32) {
+            // 32 list entries at a time: lane-parallel bbox test against this warp's region
+            const cpvk_u32 li = base + lane;
+            cpvk_u32 prim = 0; bool hit = false;
+            if (li < listEnd) {
+                prim = __ldg(p.tileLists + li);
+                const CpvkBBox bb = p.bboxes[prim];
+                hit = bb.x0 < rx1 && bb.x1 > rx0 && bb.y0 < ry1 && bb.y1 > ry0;
+            }
+            cpvk_u32 mask = __ballot_sync(0xFFFFFFFFu, hit);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const cpvk_u32 pr = __shfl_sync(0xFFFFFFFFu, prim, src);
+                // warp-uniform loads of the setup record (L1 broadcast)
+                const uint4* sp = reinterpret_cast<const uint4*>(p.setups + pr);
+                const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1), q2 = __ldg(sp + 2), q3 = __ldg(sp + 3), q4 = __ldg(sp + 4), q5 = __ldg(sp + 5);
+                const CpvkBBox bb = p.bboxes[pr];
+                const float e0ax = __uint_as_float(q0.x), e0ay = __uint_as_float(q0.y), e0dy = __uint_as_float(q0.z), e0dx = __uint_as_float(q0.w);
+                const float e1ax = __uint_as_float(q1.x), e1ay = __uint_as_float(q1.y), e1dy = __uint_as_float(q1.z), e1dx = __uint_as_float(q1.w);
+                const float e2ax = __uint_as_float(q2.x), e2ay = __uint_as_float(q2.y), e2dy = __uint_as_float(q2.z), e2dx = __uint_as_float(q2.w);
+                const float z0 = __uint_as_float(q3.x), z1 = __uint_as_float(q3.y), z2 = __uint_as_float(q3.z), area = __uint_as_float(q3.w);
+                const bool front = (q4.w & 1u) != 0;
+
+                const int cx0 = max((int)bb.x0, rx0), cx1 = min((int)bb.x1, rx1);
+                const int cy0 = max((int)bb.y0, ry0), cy1 = min((int)bb.y1, ry1);
+                const int cw = cx1 - cx0;
+                const int lg = cw <= 4 ? 2 : (cw <= 8 ? 3 : 4); // lanes form a (1<<lg) x (32>>lg) block of candidates
+                const int lx = lane & ((1 << lg) - 1), ly = lane >> lg, rowsPer = 32 >> lg;
+                for (int row0 = cy0; row0 < cy1; row0 += rowsPer) {
+                    const int x = cx0 + lx, y = row0 + ly;
+                    bool covered = x < cx1 && y < cy1;
+                    float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
+                    if (covered) {
+                        // EdgeFunction (Draw.cpp:415-418) at the pixel centre; inside = none of the three is < 0
+                        // (no fill rule; NaN compares false, so NaN weights are accepted: Draw.cpp:900).
+                        const float xf = sXf[x - tileX0], yf = sYf[y - tileY0];
+                        w0 = (xf - e0ax) * e0dy - (yf - e0ay) * e0dx;
+                        w1 = (xf - e1ax) * e1dy - (yf - e1ay) * e1dx;
+                        w2 = (xf - e2ax) * e2dy - (yf - e2ay) * e2dx;
+                        covered = !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
+                    }
+                    const cpvk_u32 cm = __ballot_sync(0xFFFFFFFFu, covered);
+                    if (cm == 0) continue;
+                    nCov += __popc(cm);
+                    bool written = false;
+                    if (covered) {
+                        CpvkFragCtx ctx;
+                        w0 /= area; w1 /= area; w2 /= area;                  // Draw.cpp:905-907
+                        const float depth = z0 * w0 + z1 * w1 + z2 * w2;      // Draw.cpp:909
+                        ctx.w[0] = w0; ctx.w[1] = w1; ctx.w[2] = w2;
+                        ctx.pw[0] = __uint_as_float(q4.x); ctx.pw[1] = __uint_as_float(q4.y); ctx.pw[2] = __uint_as_float(q4.z);
+                        ctx.idx[0] = q5.x; ctx.idx[1] = q5.y; ctx.idx[2] = q5.z; ctx.provoking = q5.w;
+                        ctx.fragCoord[0] = cpvk_spec_u32(CPVK_SPEC_ORIGIN_UPPER) ? (float)x : p.vpWidth - (float)x - 1.0f; // Draw.cpp:1579
+                        ctx.fragCoord[1] = (float)y; ctx.fragCoord[2] = depth; ctx.fragCoord[3] = 1.0f;
+                        ctx.vsOut = p.vsOut; ctx.nVerts = p.nVerts; ctx.dp = &p;
+                        const float fragDepth = (p.vpMaxDepth - p.vpMinDepth) * depth + p.vpMinDepth; // DrawPixel, Draw.cpp:1310
+                        CpvkFragOut out;
+                        const bool discarded = cpvk_fs_main(&ctx, &out);
+                        if (!discarded) {
+                            // ---- fragment wrapper epilogue (PipelineCompiler.cpp:1061-1080) on the shared tile ----
+                            const int px = x - tileX0, py = y - tileY0;
+                            cpvk_u8* dsp = sDepth + (cpvk_u32)py * dsPitch + (cpvk_u32)px * dsTexel;
+                            float currentDepth = 0.0f; cpvk_u32 currentStencil = 0;
+                            if ((boundsTest || depthTest) && fmtDepth && dsUsed) currentDepth = cpvk_get_depth(dsFormat, dsp);
+                            if (stencilOn && dsUsed) currentStencil = cpvk_get_stencil(dsFormat, dsp);
+                            bool alive = true;
+                            if (boundsTest && dsFormat != 0) // FCmpULT / FCmpUGT: unordered counts as out of bounds
+                                alive = (currentDepth >= cpvk_spec_f32(4)) && (currentDepth <= cpvk_spec_f32(5));
+                            if (alive) {
+                                bool stencilResult = true, depthResult = true;
+                                cpvk_u32 sref = 0;
+                                if (stencilOn) {
+                                    const int sb = front ? CPVK_SPEC_STENCIL_FRONT : CPVK_SPEC_STENCIL_BACK;
+                                    sref = cpvk_spec_u32(sb + 6) & 0xFFu;
+                                    const cpvk_u32 cmask = cpvk_spec_u32(sb + 4) & 0xFFu;
+                                    stencilResult = cpvk_icompare(sref & cmask, currentStencil & cmask, cpvk_spec_u32(sb + 3));
+                                }
+                                if (depthTest && dsFormat != 0 && dsFormat != 127) depthResult = cpvk_fcompare(fragDepth, currentDepth, depthOp);
+                                if (stencilOn) {
+                                    // write ops always come from the FRONT state: both arms call depthFunctions(true)
+                                    // (PipelineCompiler.cpp:1175-1185, reference defect kept for parity)
+                                    const int wb = CPVK_SPEC_STENCIL_FRONT;
+                                    const cpvk_u32 failR = cpvk_stencil_result(cpvk_spec_u32(wb + 0), currentStencil, sref);
+                                    const cpvk_u32 passR = cpvk_stencil_result(cpvk_spec_u32(wb + 1), currentStencil, sref);
+                                    const cpvk_u32 dfailR = cpvk_stencil_result(cpvk_spec_u32(wb + 2), currentStencil, sref);
+                                    cpvk_u32 wv = stencilResult ? (depthResult ? passR : dfailR) : failR;
+                                    const cpvk_u32 wmask = cpvk_spec_u32(wb + 5) & 0xFFu;
+                                    wv = (wv & wmask) | (currentStencil & (~wmask & 0xFFu));
+                                    if (dsUsed) {
+                                        if (depthResult && depthTest && depthWrite && dsFormat != 127) cpvk_set_depth_stencil(dsFormat, dsp, fragDepth, wv);
+                                        else cpvk_set_depth_stencil(dsFormat, dsp, fmtDepth ? cpvk_get_depth(dsFormat, dsp) : 0.0f, wv); // GlslFunctions.cpp:898-914
+                                    }
+                                } else if (depthTest && depthWrite && dsFormat != 0 && dsFormat != 127) {
+                                    if (depthResult && dsUsed) // SetDepthPixelXXX keeps the stencil byte (GlslFunctions.cpp:880-896)
+                                        cpvk_set_depth_stencil(dsFormat, dsp, fragDepth, fmtStencil ? cpvk_get_stencil(dsFormat, dsp) : 0u);
+                                }
+                                if (stencilResult && depthResult) {
+                                    written = true;
+                                    #pragma unroll
+                                    for (int a = 0; a < CPVK_MAX_COLOR; a++) {
+                                        if (!sColor[a]) continue;
+                                        const cpvk_u32 cf = cpvk_spec_u32(CPVK_SPEC_COLOR_FORMAT0 + a);
+                                        cpvk_u8* cp = sColor[a] + ((cpvk_u32)py * CPVK_TILE_W + (cpvk_u32)px) * cTexel[a];
+                                        const int bb8 = CPVK_SPEC_BLEND0 + a * 8;
+                                        const bool blendOn = cpvk_spec_u32(bb8) != 0;
+                                        const cpvk_u32 wm = cpvk_spec_u32(bb8 + 7);
+                                        if (cpvk_format_is_int(cf)) {
+                                            cpvk_u32 v[4] = {out.color[a][0], out.color[a][1], out.color[a][2], out.color[a][3]};
+                                            if (wm != 0xFu) { cpvk_u32 d[4]; cpvk_get_pixel_int(cf, cp, d); for (int k = 0; k < 4; k++) if (!(wm & (1u << k))) v[k] = d[k]; }
+                                            cpvk_set_pixel_int(cf, cp, v);
+                                        } else {
+                                            float v[4] = {__uint_as_float(out.color[a][0]), __uint_as_float(out.color[a][1]), __uint_as_float(out.color[a][2]), __uint_as_float(out.color[a][3])};
+                                            if (blendOn || wm != 0xFu) {
+                                                float d[4]; cpvk_get_pixel_f32(cf, cp, d); // ImageFetch of the destination (Draw.cpp:1283-1298)
+                                                if (blendOn) { float r[4]; cpvk_apply_blend(v, d, a, r); v[0] = r[0]; v[1] = r[1]; v[2] = r[2]; v[3] = r[3]; }
+                                                for (int k = 0; k < 4; k++) if (!(wm & (1u << k))) v[k] = d[k]; // PipelineCompiler.cpp:1695-1698
+                                            }
+                                            cpvk_set_pixel_f32(cf, cp, v);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    nPass += __popc(__ballot_sync(0xFFFFFFFFu, written));
+                    __syncwarp(); // order this triangle's shared-memory ROP before the next triangle's reads
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- write the tile back: shared -> HBM, row segments are contiguous in the linear image ----
+    if (dsUsed && depthTest && depthWrite || (dsUsed && stencilOn))
+        cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel, p.ds.rowPitch,
+                       sDepth, dsPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th);
+    #pragma unroll
+    for (int a = 0; a < CPVK_MAX_COLOR; a++)
+        if (sColor[a])
+            cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.color[a].address) + (cpvk_u64)tileY0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a], p.color[a].rowPitch,
+                           sColor[a], cTexel[a] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th);
+    if (p.stats && lane == 0 && (nCov | nPass)) {
+        atomicAdd(p.stats + 0, (cpvk_u64)nCov);
+        atomicAdd(p.stats + 1, (cpvk_u64)nPass);
+    }
+}

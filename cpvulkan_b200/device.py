@@ -1,0 +1,166 @@
+"""Thin Python driver over the C ABI (libcpvk_cuda.so) — what tests, smoke() and bench.py call.
+
+No fallback: constructing a Device without the built library or without a CUDA device raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi, scenes
+
+
+class CpvkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cpvk_cuda error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise CpvkError(rc, (lib.cpvk_cuda_last_error() or b"").decode(errors="replace"))
+
+
+class Device:
+    def __init__(self, ordinal=0, stream=None, stats=True, timing=False):
+        self.lib = capi.load_cuda()
+        self.handle = C.c_void_p()
+        _check(self.lib, self.lib.cpvk_cuda_device_create(ordinal, C.byref(self.handle)))
+        if stream is not None:
+            _check(self.lib, self.lib.cpvk_cuda_device_set_stream(self.handle, C.c_void_p(stream)))
+        _check(self.lib, self.lib.cpvk_cuda_device_set_stats(self.handle, int(stats)))
+        _check(self.lib, self.lib.cpvk_cuda_device_set_timing(self.handle, int(timing)))
+        self.allocs = {}
+
+    def close(self):
+        if self.handle:
+            self.lib.cpvk_cuda_device_destroy(self.handle)
+            self.handle = None
+
+    def set_timing(self, on):
+        _check(self.lib, self.lib.cpvk_cuda_device_set_timing(self.handle, int(on)))
+
+    def set_stats(self, on):
+        _check(self.lib, self.lib.cpvk_cuda_device_set_stats(self.handle, int(on)))
+
+    # memory ------------------------------------------------------------------------------------
+    def alloc(self, nbytes, host_shadow=False):
+        dev = C.c_uint64()
+        host = C.c_void_p()
+        _check(self.lib, self.lib.cpvk_cuda_mem_alloc(self.handle, max(nbytes, 1), C.byref(dev), C.byref(host) if host_shadow else None))
+        self.allocs[dev.value] = (nbytes, host.value)
+        return dev.value
+
+    def shadow(self, addr):
+        """numpy view of the pinned host shadow of an allocation made with host_shadow=True."""
+        nbytes, host = self.allocs[addr]
+        return np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_uint8)), shape=(max(nbytes, 1),))
+
+    def free(self, addr):
+        _check(self.lib, self.lib.cpvk_cuda_mem_free(self.handle, addr))
+        self.allocs.pop(addr, None)
+
+    def upload(self, addr, data):
+        data = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        _check(self.lib, self.lib.cpvk_cuda_mem_upload(self.handle, addr, data.ctypes.data_as(C.c_void_p), data.nbytes))
+        self.sync()  # `data` may be pageable and short-lived
+
+    def upload_async(self, addr, host_ptr, nbytes):
+        _check(self.lib, self.lib.cpvk_cuda_mem_upload(self.handle, addr, C.c_void_p(host_ptr), nbytes))
+
+    def download(self, addr, nbytes):
+        out = np.empty(max(nbytes, 1), dtype=np.uint8)
+        _check(self.lib, self.lib.cpvk_cuda_mem_download(self.handle, out.ctypes.data_as(C.c_void_p), addr, nbytes))
+        return out[:nbytes]
+
+    def download_into(self, host_ptr, addr, nbytes):
+        _check(self.lib, self.lib.cpvk_cuda_mem_download(self.handle, C.c_void_p(host_ptr), addr, nbytes))
+
+    def sync(self):
+        _check(self.lib, self.lib.cpvk_cuda_sync(self.handle))
+
+    # pipeline / commands -------------------------------------------------------------------------
+    def create_pipeline(self, desc):
+        p = C.c_void_p()
+        _check(self.lib, self.lib.cpvk_cuda_pipeline_create(self.handle, C.byref(desc), C.byref(p)))
+        return p
+
+    def destroy_pipeline(self, p):
+        self.lib.cpvk_cuda_pipeline_destroy(self.handle, p)
+
+    def draw(self, state):
+        _check(self.lib, self.lib.cpvk_cuda_draw(self.handle, C.byref(state)))
+
+    def stats(self):
+        st = capi.DrawStats()
+        _check(self.lib, self.lib.cpvk_cuda_last_draw_stats(self.handle, C.byref(st)))
+        return st
+
+    def clear(self, attachment, value, is_depth_stencil):
+        _check(self.lib, self.lib.cpvk_cuda_clear(self.handle, C.byref(attachment), C.byref(value), int(is_depth_stencil)))
+
+    def copy_rows(self, dst, dst_pitch, src, src_pitch, row_bytes, rows):
+        _check(self.lib, self.lib.cpvk_cuda_copy_rows(self.handle, dst, dst_pitch, src, src_pitch, row_bytes, rows))
+
+    def blit(self, blit):
+        _check(self.lib, self.lib.cpvk_cuda_blit(self.handle, C.byref(blit)))
+
+    def launch_count(self):
+        return int(self.lib.cpvk_cuda_launch_count(self.handle))
+
+
+class SceneOnDevice:
+    """A scenes.Scene resident in HBM: buffers uploaded once, pipeline linked once, re-drawable."""
+
+    def __init__(self, dev, scene, band=None):
+        self.dev, self.scene = dev, scene
+        self.owned = []
+
+        def alloc(name, nbytes, init):
+            a = dev.alloc(nbytes)
+            self.owned.append(a)
+            if init is not None:
+                dev.upload(a, np.ascontiguousarray(init).view(np.uint8).reshape(-1)[:nbytes])
+            return a
+
+        self.m = scenes.materialize(scene, alloc)
+        self.pipeline = dev.create_pipeline(self.m.desc)
+        self.m.state.pipeline = self.pipeline.value
+        if band is not None:
+            self.m.state.bandY0, self.m.state.bandY1 = band
+
+    def clear(self):
+        for img, att in ((self.scene.color, self.m.color_attachment), (self.scene.depth, self.m.depth_attachment)):
+            if img is not None and img.clear is not None:
+                cv, is_ds = scenes.clear_value(img)
+                self.dev.clear(att, cv, is_ds)
+
+    def draw(self):
+        self.dev.draw(self.m.state)
+
+    def render(self):
+        self.clear()
+        self.draw()
+
+    def read_color(self):
+        return self.dev.download(self.m.addr["color"], self.scene.color.nbytes)
+
+    def read_depth(self):
+        return self.dev.download(self.m.addr["depth"], self.scene.depth.nbytes) if self.scene.depth else None
+
+    def close(self):
+        self.dev.sync()
+        self.dev.destroy_pipeline(self.pipeline)
+        for a in self.owned:
+            self.dev.free(a)
+        self.owned = []
+
+
+def run_cuda(dev, scene, band=None):
+    """Render `scene` once on the GPU. Returns (color bytes, depth bytes or None, DrawStats)."""
+    s = SceneOnDevice(dev, scene, band)
+    try:
+        s.render()
+        st = dev.stats()
+        return s.read_color(), s.read_depth(), st
+    finally:
+        s.close()

@@ -1,0 +1,94 @@
+"""GPU parity: the sm_100a draw path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): coverage, depth results and UNORM / integer attachments bit-exact; float attachments
+within 2 ULP (RGBA16F here is produced by one IEEE float->half rounding of identical float values, so it is
+compared bit-exact as well).
+"""
+import numpy as np
+import pytest
+
+from cpvulkan_b200 import scenes
+from cpvulkan_b200.device import run_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def compare(dev, scene, check_depth=True):
+    oc, od, ost = scenes.run_oracle(scene)
+    gc, gd, gst = run_cuda(dev, scene)
+    assert gst.primitives == ost.primitives
+    assert gst.fragmentsCovered == ost.fragmentsCovered, "coverage differs"
+    assert gst.fragmentsWritten == ost.fragmentsWritten, "depth/stencil pass count differs"
+    texel = scenes.TEXEL_SIZE[scene.color.format]
+    if not np.array_equal(oc, gc):
+        a = oc.reshape(scene.color.height, scene.color.width, texel)
+        b = gc.reshape(scene.color.height, scene.color.width, texel)
+        bad = np.argwhere((a != b).any(axis=2))
+        y, x = bad[0]
+        raise AssertionError("colour differs at %d pixels, first (x=%d,y=%d): oracle %s gpu %s" % (len(bad), x, y, a[y, x], b[y, x]))
+    if check_depth and scene.depth is not None:
+        assert np.array_equal(od, gd), "depth attachment differs"
+    return ost
+
+
+def test_draw_cube(dev):
+    st = compare(dev, scenes.draw_cube())
+    assert st.primitives == 12 and st.fragmentsCovered > 10000
+
+
+@pytest.mark.parametrize("filt", [scenes.NEAREST, scenes.LINEAR])
+def test_draw_textured_cube(dev, filt):
+    compare(dev, scenes.draw_textured_cube(filt=filt))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("cull,front", [(scenes.CULL_NONE, scenes.FRONT_CCW), (scenes.CULL_BACK, scenes.FRONT_CW), (scenes.CULL_FRONT, scenes.FRONT_CCW)])
+def test_random_triangles(dev, seed, cull, front):
+    compare(dev, scenes.random_triangles(tris=300, seed=seed, cull=cull, front_face=front))
+
+
+def test_random_triangles_snapped_shared_edges(dev):
+    # vertices exactly on pixel centres: edge-on-centre, double hits on shared edges, zero-area triangles
+    compare(dev, scenes.random_triangles(width=64, height=48, tris=400, seed=11, snap=True, perspective=False))
+
+
+@pytest.mark.parametrize("depth_fmt", [scenes.D16_UNORM, scenes.D32_SFLOAT, scenes.D24_UNORM_S8_UINT, None])
+def test_depth_formats(dev, depth_fmt):
+    compare(dev, scenes.random_triangles(tris=200, seed=5, depth_fmt=depth_fmt))
+
+
+@pytest.mark.parametrize("op", [scenes.LESS, scenes.GREATER, scenes.EQUAL, scenes.ALWAYS, scenes.NOT_EQUAL, scenes.NEVER])
+def test_depth_ops(dev, op):
+    compare(dev, scenes.random_triangles(tris=150, seed=6, depth_op=op))
+
+
+@pytest.mark.parametrize("topology", [scenes.TRIANGLE_STRIP, scenes.TRIANGLE_FAN])
+def test_strip_and_fan(dev, topology):
+    compare(dev, scenes.random_triangles(tris=60, seed=7, topology=topology))
+
+
+@pytest.mark.parametrize("stride", [1, 2, 4])
+def test_indexed(dev, stride):
+    compare(dev, scenes.random_triangles(tris=80 if stride > 1 else 60, seed=8, indexed=stride))
+
+
+@pytest.mark.parametrize("size", [(33, 17), (500, 500), (1, 1), (257, 3)])
+def test_odd_sizes(dev, size):
+    compare(dev, scenes.random_triangles(width=size[0], height=size[1], tris=50, seed=9))
+
+
+def test_mesh_small(dev):
+    compare(dev, scenes.mesh_indexed(width=640, height=360, nx=160, ny=90))
+
+
+def test_mesh_layers(dev):
+    compare(dev, scenes.mesh_indexed(width=320, height=200, nx=40, ny=25, layers=4))
+
+
+@pytest.mark.parametrize("fmt", [scenes.R16G16B16A16_SFLOAT, scenes.R8G8B8A8_UNORM])
+def test_overdraw_blend(dev, fmt):
+    compare(dev, scenes.overdraw_quads(width=96, height=64, quads=12, tex_size=32, color_fmt=fmt))
+
+
+def test_overdraw_opaque(dev):
+    compare(dev, scenes.overdraw_quads(width=96, height=64, quads=3, tex_size=32, blend=False))
