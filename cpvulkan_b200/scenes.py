@@ -439,6 +439,74 @@ def random_triangles(width=256, height=192, tris=200, seed=1, depth_fmt=D32_SFLO
 
 
 # ---------------------------------------------------------------------------------------------------
+# export for the Vulkan loader-harness (cpvulkan_b200/icd/cpvk_harness.cpp)
+
+def export_scene(scene, directory):
+    """Write `scene` as scene.txt + raw blobs so the harness can replay it through the Vulkan API of the ICD."""
+    os.makedirs(directory, exist_ok=True)
+    lines = []
+    for tag, name in (("vs", scene.vs), ("fs", scene.fs)):
+        fn = name + ".spv"
+        shader(name).tofile(os.path.join(directory, fn))
+        lines.append("%s %s" % (tag, fn))
+    for b in scene.bindings:
+        lines.append("binding %d %d %d" % b)
+    for a in scene.attributes:
+        lines.append("attribute %d %d %d %d" % a)
+    lines += ["topology %d" % scene.topology, "cull %d" % scene.cull, "front %d" % scene.front_face,
+              "depth_test %d" % int(scene.depth_test), "depth_write %d" % int(scene.depth_write), "depth_op %d" % scene.depth_op,
+              "write_mask %d" % scene.write_mask]
+    if scene.blend:
+        bl = scene.blend
+        lines.append("blend %d %d %d %d %d %d" % (bl["src"], bl["dst"], bl["op"], bl.get("srcA", bl["src"]), bl.get("dstA", bl["dst"]), bl.get("opA", bl["op"])))
+    for name, data in scene.buffers.items():
+        fn = "buf_%s.bin" % name
+        np.ascontiguousarray(data).tofile(os.path.join(directory, fn))
+        lines.append("buffer %s %s %d" % (name, fn, data.nbytes))
+    for b, name in scene.vertex_buffers.items():
+        lines.append("vertex_buffer %d %s" % (b, name))
+    if scene.index_buffer:
+        lines.append("index_buffer %s %d" % (scene.index_buffer, scene.index_stride))
+    for set_, binding, name in scene.uniforms:
+        lines.append("uniform %d %d %s" % (set_, binding, name))
+    for t in scene.textures:
+        fn = "tex_%d.bin" % t.binding
+        np.ascontiguousarray(t.image.data).tofile(os.path.join(directory, fn))
+        lines.append("texture %d %d %d %d %d %d %d %s" % (t.set, t.binding, t.image.format, t.image.width, t.image.height, t.filter, t.address, fn))
+    cc = scene.color.clear[1] if scene.color.clear else (0, 0, 0, 0)
+    lines.append("color %d %d %d %r %r %r %r" % ((scene.color.format, scene.color.width, scene.color.height) + tuple(float(np.float32(c)) for c in cc)))
+    if scene.depth:
+        d, s = scene.depth.clear[1] if scene.depth.clear else (1.0, 0)
+        lines.append("depth %d %r %d" % (scene.depth.format, float(d), int(s)))
+    vp = scene.viewport or (0.0, 0.0, float(scene.color.width), float(scene.color.height), 0.0, 1.0)
+    lines.append("viewport " + " ".join(repr(float(v)) for v in vp))
+    lines.append("draw %d %d %d %d %d" % (scene.count, scene.instances, scene.first, scene.vertex_offset, scene.first_instance))
+    with open(os.path.join(directory, "scene.txt"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def run_icd(scene, workdir, frames=1, env=None):
+    """Render `scene` through the Vulkan ICD (manifest -> vk_icd* -> vkCmdDraw* -> vkQueueSubmit) with the
+    loader-harness. Returns (color bytes, depth bytes or None, harness JSON dict)."""
+    import json
+    import subprocess
+    icd_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "icd", "build")
+    scene_dir, out_dir = os.path.join(workdir, "scene"), os.path.join(workdir, "out")
+    export_scene(scene, scene_dir)
+    os.makedirs(out_dir, exist_ok=True)
+    e = dict(os.environ)
+    e["VK_ICD_FILENAMES"] = os.path.join(icd_dir, "CPVulkan_b200.json")
+    if env:
+        e.update(env)
+    out = subprocess.run([os.path.join(icd_dir, "cpvk_harness"), scene_dir, out_dir, "--frames", str(frames)], env=e, check=True,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    info = json.loads(out.stdout.strip().splitlines()[-1])
+    color = np.fromfile(os.path.join(out_dir, "color.bin"), dtype=np.uint8)
+    depth = np.fromfile(os.path.join(out_dir, "depth.bin"), dtype=np.uint8) if scene.depth else None
+    return color, depth, info
+
+
+# ---------------------------------------------------------------------------------------------------
 # host-memory backend used with the CPU oracle (tests / bench cpu_baseline only)
 
 class HostMemory:
