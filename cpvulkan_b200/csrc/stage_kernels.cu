@@ -240,6 +240,128 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
     const int rx1 = min(rx0 + 16, x1), ry1 = min(ry0 + 8, y1);
     cpvk_u32 nCov = 0, nPass = 0;
 
+    // Per-warp fragment queue (ring of 64) in shared memory. Coverage (cheap, sparse) appends the covered pixels of
+    // successive triangles in API order; shading + ROP (expensive) always runs on 32 queued fragments at a time, so
+    // its lanes are full even when triangles cover a handful of pixels each. Order per pixel is preserved: the queue
+    // is FIFO, and inside a batch of 32 the ROP of fragments that hit the same pixel is serialised lowest lane first.
+    cpvk_u32* qPrim = reinterpret_cast<cpvk_u32*>(cpvk_smem + smemOff) + warp * 64;
+    cpvk_u32* qXY = reinterpret_cast<cpvk_u32*>(cpvk_smem + smemOff + 8 * 64 * 4) + warp * 64;
+    float* qW0 = reinterpret_cast<float*>(cpvk_smem + smemOff + 2 * 8 * 64 * 4) + warp * 64;
+    float* qW1 = reinterpret_cast<float*>(cpvk_smem + smemOff + 3 * 8 * 64 * 4) + warp * 64;
+    float* qW2 = reinterpret_cast<float*>(cpvk_smem + smemOff + 4 * 8 * 64 * 4) + warp * 64;
+    int qHead = 0, qCount = 0; // warp-uniform
+
+    // ---- the fragment wrapper epilogue (PipelineCompiler.cpp:1061-1080) on the shared tile; returns "colour written" ----
+    auto rop = [&](int px, int py, float fragDepth, bool front, const CpvkFragOut& out) -> bool {
+        cpvk_u8* dsp = sDepth + (cpvk_u32)py * dsPitch + (cpvk_u32)px * dsTexel;
+        float currentDepth = 0.0f; cpvk_u32 currentStencil = 0;
+        if ((boundsTest || depthTest) && fmtDepth && dsUsed) currentDepth = cpvk_get_depth(dsFormat, dsp);
+        if (stencilOn && dsUsed) currentStencil = cpvk_get_stencil(dsFormat, dsp);
+        if (boundsTest && dsFormat != 0) // FCmpULT / FCmpUGT: unordered counts as out of bounds
+            if (!((currentDepth >= cpvk_spec_f32(4)) && (currentDepth <= cpvk_spec_f32(5)))) return false;
+        bool stencilResult = true, depthResult = true;
+        cpvk_u32 sref = 0;
+        if (stencilOn) {
+            const int sb = front ? CPVK_SPEC_STENCIL_FRONT : CPVK_SPEC_STENCIL_BACK;
+            sref = cpvk_spec_u32(sb + 6) & 0xFFu;
+            const cpvk_u32 cmask = cpvk_spec_u32(sb + 4) & 0xFFu;
+            stencilResult = cpvk_icompare(sref & cmask, currentStencil & cmask, cpvk_spec_u32(sb + 3));
+        }
+        if (depthTest && dsFormat != 0 && dsFormat != 127) depthResult = cpvk_fcompare(fragDepth, currentDepth, depthOp);
+        if (stencilOn) {
+            // write ops always come from the FRONT state: both arms call depthFunctions(true)
+            // (PipelineCompiler.cpp:1175-1185, reference defect kept for parity)
+            const int wb = CPVK_SPEC_STENCIL_FRONT;
+            const cpvk_u32 failR = cpvk_stencil_result(cpvk_spec_u32(wb + 0), currentStencil, sref);
+            const cpvk_u32 passR = cpvk_stencil_result(cpvk_spec_u32(wb + 1), currentStencil, sref);
+            const cpvk_u32 dfailR = cpvk_stencil_result(cpvk_spec_u32(wb + 2), currentStencil, sref);
+            cpvk_u32 wv = stencilResult ? (depthResult ? passR : dfailR) : failR;
+            const cpvk_u32 wmask = cpvk_spec_u32(wb + 5) & 0xFFu;
+            wv = (wv & wmask) | (currentStencil & (~wmask & 0xFFu));
+            if (dsUsed) {
+                if (depthResult && depthTest && depthWrite && dsFormat != 127) cpvk_set_depth_stencil(dsFormat, dsp, fragDepth, wv);
+                else cpvk_set_depth_stencil(dsFormat, dsp, fmtDepth ? cpvk_get_depth(dsFormat, dsp) : 0.0f, wv); // GlslFunctions.cpp:898-914
+            }
+        } else if (depthTest && depthWrite && dsFormat != 0 && dsFormat != 127) {
+            if (depthResult && dsUsed) // SetDepthPixelXXX keeps the stencil byte (GlslFunctions.cpp:880-896)
+                cpvk_set_depth_stencil(dsFormat, dsp, fragDepth, fmtStencil ? cpvk_get_stencil(dsFormat, dsp) : 0u);
+        }
+        if (!(stencilResult && depthResult)) return false;
+        #pragma unroll
+        for (int a = 0; a < CPVK_MAX_COLOR; a++) {
+            if (!sColor[a]) continue;
+            const cpvk_u32 cf = cpvk_spec_u32(CPVK_SPEC_COLOR_FORMAT0 + a);
+            cpvk_u8* cp = sColor[a] + ((cpvk_u32)py * CPVK_TILE_W + (cpvk_u32)px) * cTexel[a];
+            const int bb8 = CPVK_SPEC_BLEND0 + a * 8;
+            const bool blendOn = cpvk_spec_u32(bb8) != 0;
+            const cpvk_u32 wm = cpvk_spec_u32(bb8 + 7);
+            if (cpvk_format_is_int(cf)) {
+                cpvk_u32 v[4] = {out.color[a][0], out.color[a][1], out.color[a][2], out.color[a][3]};
+                if (wm != 0xFu) { cpvk_u32 d[4]; cpvk_get_pixel_int(cf, cp, d); for (int k = 0; k < 4; k++) if (!(wm & (1u << k))) v[k] = d[k]; }
+                cpvk_set_pixel_int(cf, cp, v);
+            } else {
+                float v[4] = {__uint_as_float(out.color[a][0]), __uint_as_float(out.color[a][1]), __uint_as_float(out.color[a][2]), __uint_as_float(out.color[a][3])};
+                if (blendOn || wm != 0xFu) {
+                    float d[4]; cpvk_get_pixel_f32(cf, cp, d); // ImageFetch of the destination (Draw.cpp:1283-1298)
+                    if (blendOn) { float r[4]; cpvk_apply_blend(v, d, a, r); v[0] = r[0]; v[1] = r[1]; v[2] = r[2]; v[3] = r[3]; }
+                    for (int k = 0; k < 4; k++) if (!(wm & (1u << k))) v[k] = d[k]; // PipelineCompiler.cpp:1695-1698
+                }
+                cpvk_set_pixel_f32(cf, cp, v);
+            }
+        }
+        return true;
+    };
+
+    // ---- shade + ROP the oldest `take` (<= 32) queued fragments ----
+    auto flush = [&](int take) {
+        const bool active = lane < take;
+        const int slot = (qHead + lane) & 63;
+        CpvkFragOut out;
+        bool survive = false, front = true;
+        float fragDepth = 0.0f;
+        int px = 0, py = 0;
+        cpvk_u32 key = 0x80000000u | (cpvk_u32)lane; // unique for idle lanes
+        if (active) {
+            const cpvk_u32 pr = qPrim[slot], xy = qXY[slot];
+            float w0 = qW0[slot], w1 = qW1[slot], w2 = qW2[slot];
+            px = (int)(xy & 0xFFFFu); py = (int)(xy >> 16);
+            const uint4* sp = reinterpret_cast<const uint4*>(p.setups + pr);
+            const uint4 q3 = __ldg(sp + 3), q4 = __ldg(sp + 4), q5 = __ldg(sp + 5);
+            const float area = __uint_as_float(q3.w);
+            CpvkFragCtx ctx;
+            w0 /= area; w1 /= area; w2 /= area;                                                   // Draw.cpp:905-907
+            const float depth = __uint_as_float(q3.x) * w0 + __uint_as_float(q3.y) * w1 + __uint_as_float(q3.z) * w2; // Draw.cpp:909
+            ctx.w[0] = w0; ctx.w[1] = w1; ctx.w[2] = w2;
+            ctx.pw[0] = __uint_as_float(q4.x); ctx.pw[1] = __uint_as_float(q4.y); ctx.pw[2] = __uint_as_float(q4.z);
+            ctx.unitW = ctx.pw[0] == 1.0f && ctx.pw[1] == 1.0f && ctx.pw[2] == 1.0f;
+            front = (q4.w & 1u) != 0;
+            ctx.idx[0] = q5.x; ctx.idx[1] = q5.y; ctx.idx[2] = q5.z; ctx.provoking = q5.w;
+            const int x = tileX0 + px, y = tileY0 + py;
+            ctx.fragCoord[0] = cpvk_spec_u32(CPVK_SPEC_ORIGIN_UPPER) ? (float)x : p.vpWidth - (float)x - 1.0f; // Draw.cpp:1579
+            ctx.fragCoord[1] = (float)y; ctx.fragCoord[2] = depth; ctx.fragCoord[3] = 1.0f;
+            ctx.vsOut = p.vsOut; ctx.nVerts = p.nVerts; ctx.dp = &p;
+            fragDepth = (p.vpMaxDepth - p.vpMinDepth) * depth + p.vpMinDepth;                       // DrawPixel, Draw.cpp:1310
+            survive = !cpvk_fs_main(&ctx, &out);
+            key = (cpvk_u32)(py * CPVK_TILE_W + px);
+        }
+        // ROP in API order: a fragment waits for every earlier (lower-lane) fragment of the same pixel
+        const cpvk_u32 same = __match_any_sync(0xFFFFFFFFu, key);
+        cpvk_u32 pending = __ballot_sync(0xFFFFFFFFu, survive);
+        const cpvk_u32 lowerMask = (1u << lane) - 1u;
+        cpvk_u32 writtenMask = 0;
+        while (pending) {
+            const bool go = ((pending >> lane) & 1u) && ((same & pending & lowerMask) == 0u);
+            bool wrote = false;
+            if (go) wrote = rop(px, py, fragDepth, front, out);
+            pending &= ~__ballot_sync(0xFFFFFFFFu, go);
+            writtenMask |= __ballot_sync(0xFFFFFFFFu, wrote);
+            __syncwarp();
+        }
+        nPass += __popc(writtenMask);
+        qHead = (qHead + take) & 63; qCount -= take;
+        __syncwarp();
+    };
+
     if (rx0 < rx1 && ry0 < ry1) {
         for (cpvk_u32 base = listBegin; base < listEnd; base += 32) {
             // 32 list entries at a time: lane-parallel bbox test against this warp's region
@@ -255,16 +377,13 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
                 const int src = __ffs(mask) - 1;
                 mask &= mask - 1;
                 const cpvk_u32 pr = __shfl_sync(0xFFFFFFFFu, prim, src);
-                // warp-uniform loads of the setup record (L1 broadcast)
+                // warp-uniform loads of the edge part of the setup record (L1 broadcast)
                 const uint4* sp = reinterpret_cast<const uint4*>(p.setups + pr);
-                const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1), q2 = __ldg(sp + 2), q3 = __ldg(sp + 3), q4 = __ldg(sp + 4), q5 = __ldg(sp + 5);
+                const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1), q2 = __ldg(sp + 2);
                 const CpvkBBox bb = p.bboxes[pr];
                 const float e0ax = __uint_as_float(q0.x), e0ay = __uint_as_float(q0.y), e0dy = __uint_as_float(q0.z), e0dx = __uint_as_float(q0.w);
                 const float e1ax = __uint_as_float(q1.x), e1ay = __uint_as_float(q1.y), e1dy = __uint_as_float(q1.z), e1dx = __uint_as_float(q1.w);
                 const float e2ax = __uint_as_float(q2.x), e2ay = __uint_as_float(q2.y), e2dy = __uint_as_float(q2.z), e2dx = __uint_as_float(q2.w);
-                const float z0 = __uint_as_float(q3.x), z1 = __uint_as_float(q3.y), z2 = __uint_as_float(q3.z), area = __uint_as_float(q3.w);
-                const bool front = (q4.w & 1u) != 0;
-
                 const int cx0 = max((int)bb.x0, rx0), cx1 = min((int)bb.x1, rx1);
                 const int cy0 = max((int)bb.y0, ry0), cy1 = min((int)bb.y1, ry1);
                 const int cw = cx1 - cx0;
@@ -285,92 +404,19 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
                     }
                     const cpvk_u32 cm = __ballot_sync(0xFFFFFFFFu, covered);
                     if (cm == 0) continue;
-                    nCov += __popc(cm);
-                    bool written = false;
                     if (covered) {
-                        CpvkFragCtx ctx;
-                        w0 /= area; w1 /= area; w2 /= area;                  // Draw.cpp:905-907
-                        const float depth = z0 * w0 + z1 * w1 + z2 * w2;      // Draw.cpp:909
-                        ctx.w[0] = w0; ctx.w[1] = w1; ctx.w[2] = w2;
-                        ctx.pw[0] = __uint_as_float(q4.x); ctx.pw[1] = __uint_as_float(q4.y); ctx.pw[2] = __uint_as_float(q4.z);
-                        ctx.idx[0] = q5.x; ctx.idx[1] = q5.y; ctx.idx[2] = q5.z; ctx.provoking = q5.w;
-                        ctx.fragCoord[0] = cpvk_spec_u32(CPVK_SPEC_ORIGIN_UPPER) ? (float)x : p.vpWidth - (float)x - 1.0f; // Draw.cpp:1579
-                        ctx.fragCoord[1] = (float)y; ctx.fragCoord[2] = depth; ctx.fragCoord[3] = 1.0f;
-                        ctx.vsOut = p.vsOut; ctx.nVerts = p.nVerts; ctx.dp = &p;
-                        const float fragDepth = (p.vpMaxDepth - p.vpMinDepth) * depth + p.vpMinDepth; // DrawPixel, Draw.cpp:1310
-                        CpvkFragOut out;
-                        const bool discarded = cpvk_fs_main(&ctx, &out);
-                        if (!discarded) {
-                            // ---- fragment wrapper epilogue (PipelineCompiler.cpp:1061-1080) on the shared tile ----
-                            const int px = x - tileX0, py = y - tileY0;
-                            cpvk_u8* dsp = sDepth + (cpvk_u32)py * dsPitch + (cpvk_u32)px * dsTexel;
-                            float currentDepth = 0.0f; cpvk_u32 currentStencil = 0;
-                            if ((boundsTest || depthTest) && fmtDepth && dsUsed) currentDepth = cpvk_get_depth(dsFormat, dsp);
-                            if (stencilOn && dsUsed) currentStencil = cpvk_get_stencil(dsFormat, dsp);
-                            bool alive = true;
-                            if (boundsTest && dsFormat != 0) // FCmpULT / FCmpUGT: unordered counts as out of bounds
-                                alive = (currentDepth >= cpvk_spec_f32(4)) && (currentDepth <= cpvk_spec_f32(5));
-                            if (alive) {
-                                bool stencilResult = true, depthResult = true;
-                                cpvk_u32 sref = 0;
-                                if (stencilOn) {
-                                    const int sb = front ? CPVK_SPEC_STENCIL_FRONT : CPVK_SPEC_STENCIL_BACK;
-                                    sref = cpvk_spec_u32(sb + 6) & 0xFFu;
-                                    const cpvk_u32 cmask = cpvk_spec_u32(sb + 4) & 0xFFu;
-                                    stencilResult = cpvk_icompare(sref & cmask, currentStencil & cmask, cpvk_spec_u32(sb + 3));
-                                }
-                                if (depthTest && dsFormat != 0 && dsFormat != 127) depthResult = cpvk_fcompare(fragDepth, currentDepth, depthOp);
-                                if (stencilOn) {
-                                    // write ops always come from the FRONT state: both arms call depthFunctions(true)
-                                    // (PipelineCompiler.cpp:1175-1185, reference defect kept for parity)
-                                    const int wb = CPVK_SPEC_STENCIL_FRONT;
-                                    const cpvk_u32 failR = cpvk_stencil_result(cpvk_spec_u32(wb + 0), currentStencil, sref);
-                                    const cpvk_u32 passR = cpvk_stencil_result(cpvk_spec_u32(wb + 1), currentStencil, sref);
-                                    const cpvk_u32 dfailR = cpvk_stencil_result(cpvk_spec_u32(wb + 2), currentStencil, sref);
-                                    cpvk_u32 wv = stencilResult ? (depthResult ? passR : dfailR) : failR;
-                                    const cpvk_u32 wmask = cpvk_spec_u32(wb + 5) & 0xFFu;
-                                    wv = (wv & wmask) | (currentStencil & (~wmask & 0xFFu));
-                                    if (dsUsed) {
-                                        if (depthResult && depthTest && depthWrite && dsFormat != 127) cpvk_set_depth_stencil(dsFormat, dsp, fragDepth, wv);
-                                        else cpvk_set_depth_stencil(dsFormat, dsp, fmtDepth ? cpvk_get_depth(dsFormat, dsp) : 0.0f, wv); // GlslFunctions.cpp:898-914
-                                    }
-                                } else if (depthTest && depthWrite && dsFormat != 0 && dsFormat != 127) {
-                                    if (depthResult && dsUsed) // SetDepthPixelXXX keeps the stencil byte (GlslFunctions.cpp:880-896)
-                                        cpvk_set_depth_stencil(dsFormat, dsp, fragDepth, fmtStencil ? cpvk_get_stencil(dsFormat, dsp) : 0u);
-                                }
-                                if (stencilResult && depthResult) {
-                                    written = true;
-                                    #pragma unroll
-                                    for (int a = 0; a < CPVK_MAX_COLOR; a++) {
-                                        if (!sColor[a]) continue;
-                                        const cpvk_u32 cf = cpvk_spec_u32(CPVK_SPEC_COLOR_FORMAT0 + a);
-                                        cpvk_u8* cp = sColor[a] + ((cpvk_u32)py * CPVK_TILE_W + (cpvk_u32)px) * cTexel[a];
-                                        const int bb8 = CPVK_SPEC_BLEND0 + a * 8;
-                                        const bool blendOn = cpvk_spec_u32(bb8) != 0;
-                                        const cpvk_u32 wm = cpvk_spec_u32(bb8 + 7);
-                                        if (cpvk_format_is_int(cf)) {
-                                            cpvk_u32 v[4] = {out.color[a][0], out.color[a][1], out.color[a][2], out.color[a][3]};
-                                            if (wm != 0xFu) { cpvk_u32 d[4]; cpvk_get_pixel_int(cf, cp, d); for (int k = 0; k < 4; k++) if (!(wm & (1u << k))) v[k] = d[k]; }
-                                            cpvk_set_pixel_int(cf, cp, v);
-                                        } else {
-                                            float v[4] = {__uint_as_float(out.color[a][0]), __uint_as_float(out.color[a][1]), __uint_as_float(out.color[a][2]), __uint_as_float(out.color[a][3])};
-                                            if (blendOn || wm != 0xFu) {
-                                                float d[4]; cpvk_get_pixel_f32(cf, cp, d); // ImageFetch of the destination (Draw.cpp:1283-1298)
-                                                if (blendOn) { float r[4]; cpvk_apply_blend(v, d, a, r); v[0] = r[0]; v[1] = r[1]; v[2] = r[2]; v[3] = r[3]; }
-                                                for (int k = 0; k < 4; k++) if (!(wm & (1u << k))) v[k] = d[k]; // PipelineCompiler.cpp:1695-1698
-                                            }
-                                            cpvk_set_pixel_f32(cf, cp, v);
-                                        }
-                                    }
-                                }
-                            }
-                        }
+                        const int slot = (qHead + qCount + __popc(cm & ((1u << lane) - 1u))) & 63;
+                        qPrim[slot] = pr; qXY[slot] = (cpvk_u32)(x - tileX0) | ((cpvk_u32)(y - tileY0) << 16);
+                        qW0[slot] = w0; qW1[slot] = w1; qW2[slot] = w2;
                     }
-                    nPass += __popc(__ballot_sync(0xFFFFFFFFu, written));
-                    __syncwarp(); // order this triangle's shared-memory ROP before the next triangle's reads
+                    const int added = __popc(cm);
+                    nCov += added; qCount += added;
+                    __syncwarp();
+                    if (qCount >= 32) flush(32);
                 }
             }
         }
+        while (qCount > 0) flush(qCount < 32 ? qCount : 32);
     }
     __syncthreads();
     // ---- write the tile back: shared -> HBM, row segments are contiguous in the linear image ----
