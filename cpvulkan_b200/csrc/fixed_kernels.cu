@@ -75,6 +75,12 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
     if (culled || endX <= startX || endY <= startY) { bb.x0 = bb.y0 = bb.x1 = bb.y1 = 0; }
     else { bb.x0 = (short)startX; bb.y0 = (short)startY; bb.x1 = (short)endX; bb.y1 = (short)endY; }
     a.bboxes[p] = bb;
+    // binning pass 0, fused: count the (primitive, tile) pairs while the bbox is in registers
+    if (bb.x1 > bb.x0) {
+        const int tx0 = bb.x0 / CPVK_TILE_W, tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty0 = bb.y0 / CPVK_TILE_H, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
+        if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > CPVK_BIN_SMALL) { a.largeList[atomicAdd(a.meta + 2, 1u)] = p; }
+        else for (int ty = ty0; ty <= ty1; ty++) for (int tx = tx0; tx <= tx1; tx++) atomicAdd(a.counts + (cpvk_u32)ty * a.tilesX + (cpvk_u32)tx, 1u);
+    }
 }
 
 // ---- binning ----
@@ -88,10 +94,7 @@ __global__ void __launch_bounds__(256) k_bin(CpvkBinArgs a, int pass) {
     if (bb.x1 <= bb.x0) return;
     const int tx0 = bb.x0 / CPVK_TILE_W, tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty0 = bb.y0 / CPVK_TILE_H, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
     const int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-    if (n > CPVK_BIN_SMALL) {
-        if (pass == 0) { const cpvk_u32 slot = atomicAdd(a.meta + 2, 1u); a.largeList[slot] = p; }
-        return;
-    }
+    if (n > CPVK_BIN_SMALL) return; // deferred to k_bin_large (listed by k_setup)
     for (int ty = ty0; ty <= ty1; ty++)
         for (int tx = tx0; tx <= tx1; tx++) {
             const cpvk_u32 t = (cpvk_u32)ty * a.tilesX + (cpvk_u32)tx;
@@ -294,7 +297,7 @@ cudaError_t cpvk_launch_setup(const CpvkSetupArgs* a, cudaStream_t s) {
 }
 cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, cudaStream_t s) {
     if (a->primCount == 0) return cudaSuccess;
-    k_bin<<<cpvk_grid(a->primCount, 256), 256, 0, s>>>(*a, pass);
+    if (pass != 0) k_bin<<<cpvk_grid(a->primCount, 256), 256, 0, s>>>(*a, pass); // pass 0 of the small primitives is fused into k_setup
     k_bin_large<<<592, 256, 0, s>>>(*a, pass); // 148 SMs x 4 resident CTAs; loops over the deferred list
     return cudaGetLastError();
 }

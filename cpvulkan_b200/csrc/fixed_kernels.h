@@ -14,6 +14,11 @@ struct CpvkSetupArgs {
     cpvk_i32 clipX0, clipY0, clipX1, clipY1;
     CpvkTriSetup* setups;
     CpvkBBox* bboxes;
+    // binning pass 0 (count) is fused into setup: the bbox is in registers right here
+    cpvk_u32 tilesX;
+    cpvk_u32* counts;    // [tiles], zeroed by the host
+    cpvk_u32* largeList; // [primCount]
+    cpvk_u32* meta;      // [2] = number of deferred (large) primitives, zeroed by the host
 };
 
 struct CpvkBinArgs {
@@ -45,7 +50,7 @@ struct CpvkBlitArgs {
 
 extern "C" {
 cudaError_t cpvk_launch_setup(const CpvkSetupArgs* a, cudaStream_t s);
-cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, cudaStream_t s);
+cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, cudaStream_t s); /* pass 0: only the deferred large primitives (small ones are counted by k_setup) */
 cudaError_t cpvk_launch_bin_scan(const CpvkBinArgs* a, cudaStream_t s);
 cudaError_t cpvk_launch_bin_sort(const CpvkBinArgs* a, unsigned capacity, cudaStream_t s);
 cudaError_t cpvk_launch_clear(const CpvkDevAttachment* img, const CpvkClearArgs* c, cudaStream_t s);

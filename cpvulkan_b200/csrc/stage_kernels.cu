@@ -244,11 +244,14 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
     // successive triangles in API order; shading + ROP (expensive) always runs on 32 queued fragments at a time, so
     // its lanes are full even when triangles cover a handful of pixels each. Order per pixel is preserved: the queue
     // is FIFO, and inside a batch of 32 the ROP of fragments that hit the same pixel is serialised lowest lane first.
-    cpvk_u32* qPrim = reinterpret_cast<cpvk_u32*>(cpvk_smem + smemOff) + warp * 64;
-    cpvk_u32* qXY = reinterpret_cast<cpvk_u32*>(cpvk_smem + smemOff + 8 * 64 * 4) + warp * 64;
-    float* qW0 = reinterpret_cast<float*>(cpvk_smem + smemOff + 2 * 8 * 64 * 4) + warp * 64;
-    float* qW1 = reinterpret_cast<float*>(cpvk_smem + smemOff + 3 * 8 * 64 * 4) + warp * 64;
-    float* qW2 = reinterpret_cast<float*>(cpvk_smem + smemOff + 4 * 8 * 64 * 4) + warp * 64;
+    cpvk_u32* qXY = reinterpret_cast<cpvk_u32*>(cpvk_smem + smemOff) + warp * 64;          // px | py << 8 | chunk-local triangle << 16
+    float* qW0 = reinterpret_cast<float*>(cpvk_smem + smemOff + 1 * 8 * 64 * 4) + warp * 64;
+    float* qW1 = reinterpret_cast<float*>(cpvk_smem + smemOff + 2 * 8 * 64 * 4) + warp * 64;
+    float* qW2 = reinterpret_cast<float*>(cpvk_smem + smemOff + 3 * 8 * 64 * 4) + warp * 64;
+    // Triangle chunk staged by the whole CTA: CPVK_CHUNK setup records as six uint4 planes + bboxes. Every warp of the
+    // tile scans the same list, so one coalesced global read per record replaces eight latency-bound ones.
+    uint4* sQ = reinterpret_cast<uint4*>(cpvk_smem + smemOff + 4 * 8 * 64 * 4);                 // [6][CPVK_CHUNK]
+    uint2* sBB = reinterpret_cast<uint2*>(cpvk_smem + smemOff + 4 * 8 * 64 * 4 + 6 * CPVK_CHUNK * 16); // [CPVK_CHUNK]
     int qHead = 0, qCount = 0; // warp-uniform
 
     // ---- the fragment wrapper epilogue (PipelineCompiler.cpp:1061-1080) on the shared tile; returns "colour written" ----
@@ -322,11 +325,11 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
         int px = 0, py = 0;
         cpvk_u32 key = 0x80000000u | (cpvk_u32)lane; // unique for idle lanes
         if (active) {
-            const cpvk_u32 pr = qPrim[slot], xy = qXY[slot];
+            const cpvk_u32 xy = qXY[slot];
+            const cpvk_u32 kt = xy >> 16;
             float w0 = qW0[slot], w1 = qW1[slot], w2 = qW2[slot];
-            px = (int)(xy & 0xFFFFu); py = (int)(xy >> 16);
-            const uint4* sp = reinterpret_cast<const uint4*>(p.setups + pr);
-            const uint4 q3 = __ldg(sp + 3), q4 = __ldg(sp + 4), q5 = __ldg(sp + 5);
+            px = (int)(xy & 0xFFu); py = (int)((xy >> 8) & 0xFFu);
+            const uint4 q3 = sQ[3 * CPVK_CHUNK + kt], q4 = sQ[4 * CPVK_CHUNK + kt], q5 = sQ[5 * CPVK_CHUNK + kt];
             const float area = __uint_as_float(q3.w);
             CpvkFragCtx ctx;
             w0 /= area; w1 /= area; w2 /= area;                                                   // Draw.cpp:905-907
@@ -362,61 +365,93 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
         __syncwarp();
     };
 
-    if (rx0 < rx1 && ry0 < ry1) {
-        for (cpvk_u32 base = listBegin; base < listEnd; base += 32) {
-            // 32 list entries at a time: lane-parallel bbox test against this warp's region
-            const cpvk_u32 li = base + lane;
-            cpvk_u32 prim = 0; bool hit = false;
-            if (li < listEnd) {
-                prim = __ldg(p.tileLists + li);
-                const CpvkBBox bb = p.bboxes[prim];
-                hit = bb.x0 < rx1 && bb.x1 > rx0 && bb.y0 < ry1 && bb.y1 > ry0;
+    const bool regionLive = rx0 < rx1 && ry0 < ry1;
+    for (cpvk_u32 chunkBase = listBegin; chunkBase < listEnd; chunkBase += CPVK_CHUNK) {
+        const int n = (int)min((cpvk_u32)CPVK_CHUNK, listEnd - chunkBase);
+        if (!p.listsSorted) {
+            // Binning claims list slots with atomics, so a tile's ids arrive in arbitrary order. When every list fits
+            // one chunk the host skips k_bin_sort and the tile orders its own list here: ids are unique, so each id's
+            // rank (number of smaller ids) is its position in API order. Broadcast shared-memory reads, no barriers
+            // inside the loop.
+            cpvk_u32* sKeys = reinterpret_cast<cpvk_u32*>(sBB);          // reused before the bboxes are staged
+            cpvk_u32* sSorted = reinterpret_cast<cpvk_u32*>(sQ);         // reused before the records are staged
+            const cpvk_u32 key = (int)threadIdx.x < n ? __ldg(p.tileLists + chunkBase + threadIdx.x) : 0xFFFFFFFFu;
+            sKeys[threadIdx.x] = key;
+            __syncthreads();
+            if ((int)threadIdx.x < n) {
+                cpvk_u32 rank = 0;
+                const uint4* k4 = reinterpret_cast<const uint4*>(sKeys);
+                for (int j = 0; j < (n + 3) / 4; j++) { const uint4 v = k4[j]; rank += (v.x < key) + (v.y < key) + (v.z < key) + (v.w < key); }
+                sSorted[rank] = key;
             }
-            cpvk_u32 mask = __ballot_sync(0xFFFFFFFFu, hit);
-            while (mask) {
-                const int src = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const cpvk_u32 pr = __shfl_sync(0xFFFFFFFFu, prim, src);
-                // warp-uniform loads of the edge part of the setup record (L1 broadcast)
-                const uint4* sp = reinterpret_cast<const uint4*>(p.setups + pr);
-                const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1), q2 = __ldg(sp + 2);
-                const CpvkBBox bb = p.bboxes[pr];
-                const float e0ax = __uint_as_float(q0.x), e0ay = __uint_as_float(q0.y), e0dy = __uint_as_float(q0.z), e0dx = __uint_as_float(q0.w);
-                const float e1ax = __uint_as_float(q1.x), e1ay = __uint_as_float(q1.y), e1dy = __uint_as_float(q1.z), e1dx = __uint_as_float(q1.w);
-                const float e2ax = __uint_as_float(q2.x), e2ay = __uint_as_float(q2.y), e2dy = __uint_as_float(q2.z), e2dx = __uint_as_float(q2.w);
-                const int cx0 = max((int)bb.x0, rx0), cx1 = min((int)bb.x1, rx1);
-                const int cy0 = max((int)bb.y0, ry0), cy1 = min((int)bb.y1, ry1);
-                const int cw = cx1 - cx0;
-                const int lg = cw <= 4 ? 2 : (cw <= 8 ? 3 : 4); // lanes form a (1<<lg) x (32>>lg) block of candidates
-                const int lx = lane & ((1 << lg) - 1), ly = lane >> lg, rowsPer = 32 >> lg;
-                for (int row0 = cy0; row0 < cy1; row0 += rowsPer) {
-                    const int x = cx0 + lx, y = row0 + ly;
-                    bool covered = x < cx1 && y < cy1;
-                    float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
-                    if (covered) {
-                        // EdgeFunction (Draw.cpp:415-418) at the pixel centre; inside = none of the three is < 0
-                        // (no fill rule; NaN compares false, so NaN weights are accepted: Draw.cpp:900).
-                        const float xf = sXf[x - tileX0], yf = sYf[y - tileY0];
-                        w0 = (xf - e0ax) * e0dy - (yf - e0ay) * e0dx;
-                        w1 = (xf - e1ax) * e1dy - (yf - e1ay) * e1dx;
-                        w2 = (xf - e2ax) * e2dy - (yf - e2ay) * e2dx;
-                        covered = !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
+            __syncthreads();
+        }
+        cpvk_u32 stagedPrim = 0;
+        if ((int)threadIdx.x < n) stagedPrim = p.listsSorted ? __ldg(p.tileLists + chunkBase + threadIdx.x) : reinterpret_cast<const cpvk_u32*>(sQ)[threadIdx.x];
+        if (!p.listsSorted) __syncthreads(); // every thread has read its sorted id before the planes are overwritten
+        if ((int)threadIdx.x < n) { // CPVK_CHUNK == blockDim.x: one record per thread, 16-byte coalesced pieces
+            const cpvk_u32 prim = stagedPrim;
+            const uint4* sp = reinterpret_cast<const uint4*>(p.setups + prim);
+            #pragma unroll
+            for (int j = 0; j < 6; j++) sQ[j * CPVK_CHUNK + threadIdx.x] = __ldg(sp + j);
+            sBB[threadIdx.x] = __ldg(reinterpret_cast<const uint2*>(p.bboxes + prim));
+        }
+        __syncthreads();
+        if (regionLive) {
+            for (int base = 0; base < n; base += 32) {
+                // 32 staged triangles at a time: lane-parallel bbox test against this warp's region
+                const int li = base + lane;
+                bool hit = false;
+                if (li < n) {
+                    const uint2 b = sBB[li];
+                    const int bx0 = (short)(b.x & 0xFFFFu), by0 = (short)(b.x >> 16), bx1 = (short)(b.y & 0xFFFFu), by1 = (short)(b.y >> 16);
+                    hit = bx0 < rx1 && bx1 > rx0 && by0 < ry1 && by1 > ry0;
+                }
+                cpvk_u32 mask = __ballot_sync(0xFFFFFFFFu, hit);
+                while (mask) {
+                    const int kt = base + __ffs(mask) - 1; // chunk-local triangle, warp-uniform
+                    mask &= mask - 1;
+                    const uint4 q0 = sQ[kt], q1 = sQ[CPVK_CHUNK + kt], q2 = sQ[2 * CPVK_CHUNK + kt]; // broadcast reads
+                    const uint2 b = sBB[kt];
+                    const int bx0 = (short)(b.x & 0xFFFFu), by0 = (short)(b.x >> 16), bx1 = (short)(b.y & 0xFFFFu), by1 = (short)(b.y >> 16);
+                    const float e0ax = __uint_as_float(q0.x), e0ay = __uint_as_float(q0.y), e0dy = __uint_as_float(q0.z), e0dx = __uint_as_float(q0.w);
+                    const float e1ax = __uint_as_float(q1.x), e1ay = __uint_as_float(q1.y), e1dy = __uint_as_float(q1.z), e1dx = __uint_as_float(q1.w);
+                    const float e2ax = __uint_as_float(q2.x), e2ay = __uint_as_float(q2.y), e2dy = __uint_as_float(q2.z), e2dx = __uint_as_float(q2.w);
+                    const int cx0 = max(bx0, rx0), cx1 = min(bx1, rx1);
+                    const int cy0 = max(by0, ry0), cy1 = min(by1, ry1);
+                    const int cw = cx1 - cx0;
+                    const int lg = cw <= 4 ? 2 : (cw <= 8 ? 3 : 4); // lanes form a (1<<lg) x (32>>lg) block of candidates
+                    const int lx = lane & ((1 << lg) - 1), ly = lane >> lg, rowsPer = 32 >> lg;
+                    for (int row0 = cy0; row0 < cy1; row0 += rowsPer) {
+                        const int x = cx0 + lx, y = row0 + ly;
+                        bool covered = x < cx1 && y < cy1;
+                        float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
+                        if (covered) {
+                            // EdgeFunction (Draw.cpp:415-418) at the pixel centre; inside = none of the three is < 0
+                            // (no fill rule; NaN compares false, so NaN weights are accepted: Draw.cpp:900).
+                            const float xf = sXf[x - tileX0], yf = sYf[y - tileY0];
+                            w0 = (xf - e0ax) * e0dy - (yf - e0ay) * e0dx;
+                            w1 = (xf - e1ax) * e1dy - (yf - e1ay) * e1dx;
+                            w2 = (xf - e2ax) * e2dy - (yf - e2ay) * e2dx;
+                            covered = !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
+                        }
+                        const cpvk_u32 cm = __ballot_sync(0xFFFFFFFFu, covered);
+                        if (cm == 0) continue;
+                        if (covered) {
+                            const int slot = (qHead + qCount + __popc(cm & ((1u << lane) - 1u))) & 63;
+                            qXY[slot] = (cpvk_u32)(x - tileX0) | ((cpvk_u32)(y - tileY0) << 8) | ((cpvk_u32)kt << 16);
+                            qW0[slot] = w0; qW1[slot] = w1; qW2[slot] = w2;
+                        }
+                        const int added = __popc(cm);
+                        nCov += added; qCount += added;
+                        __syncwarp();
+                        if (qCount >= 32) flush(32);
                     }
-                    const cpvk_u32 cm = __ballot_sync(0xFFFFFFFFu, covered);
-                    if (cm == 0) continue;
-                    if (covered) {
-                        const int slot = (qHead + qCount + __popc(cm & ((1u << lane) - 1u))) & 63;
-                        qPrim[slot] = pr; qXY[slot] = (cpvk_u32)(x - tileX0) | ((cpvk_u32)(y - tileY0) << 16);
-                        qW0[slot] = w0; qW1[slot] = w1; qW2[slot] = w2;
-                    }
-                    const int added = __popc(cm);
-                    nCov += added; qCount += added;
-                    __syncwarp();
-                    if (qCount >= 32) flush(32);
                 }
             }
+            while (qCount > 0) flush(qCount < 32 ? qCount : 32); // queue entries name chunk-local triangles: drain before restaging
         }
-        while (qCount > 0) flush(qCount < 32 ? qCount : 32);
+        __syncthreads();
     }
     __syncthreads();
     // ---- write the tile back: shared -> HBM, row segments are contiguous in the linear image ----

@@ -92,3 +92,13 @@ def test_overdraw_blend(dev, fmt):
 
 def test_overdraw_opaque(dev):
     compare(dev, scenes.overdraw_quads(width=96, height=64, quads=3, tex_size=32, blend=False))
+
+
+def test_long_tile_lists_multi_chunk(dev):
+    # > 256 primitives over one tile: k_bin_sort path + several staged chunks per tile in k_raster
+    compare(dev, scenes.random_triangles(width=64, height=64, tris=1500, seed=12))
+
+
+def test_very_long_tile_lists_sort_fallback(dev):
+    # > 16384 primitives over one tile: the in-HBM stable split-sort fallback of k_bin_sort
+    compare(dev, scenes.random_triangles(width=40, height=40, tris=17000, seed=13, perspective=False))
