@@ -265,6 +265,9 @@ __global__ void __launch_bounds__(256) k_copy_rows(cpvk_u8* dst, cpvk_u32 dstPit
 // vkCmdBlitImage, one 2-D colour region: the reference samples the source as a 3-D image with lod 1 on a one-level
 // chain (-> level 0), clamp-to-edge, both z taps on slice 0 with weight 0, then SetPixel (CommandBuffer.cpp:75-226).
 __global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
+    __shared__ float lut[256]; // (float)k / 255.0f by the IEEE divide itself: exact UNORM8 decode without a divide per channel
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
     const int dstW = abs(b.dstX1 - b.dstX0), dstH = abs(b.dstY1 - b.dstY0);
     const bool negW = b.dstX1 < b.dstX0, negH = b.dstY1 < b.dstY0;
     const cpvk_u64 total = (cpvk_u64)dstW * dstH;
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
         const float v = ((float)dstY + 0.5f - (float)b.dstY0) * ((float)(b.srcY1 - b.srcY0) / (float)(b.dstY1 - b.dstY0)) + (float)b.srcY0;
         const float w = (0.0f + 0.5f - 0.0f) * ((float)(1 - 0) / (float)(1 - 0)) + 0.0f;
         const float coord[3] = {u / (float)b.src.width, v / (float)b.src.height, w / 1.0f};
-        const CpvkVec4 value = cpvk_sample_image(&d, 3, coord, 1.0f, b.filter, b.filter);
+        const CpvkVec4 value = cpvk_sample_image(&d, 3, coord, 1.0f, b.filter, b.filter, lut);
         if (dstX < 0 || dstY < 0 || (cpvk_u32)dstX >= b.dst.width || (cpvk_u32)dstY >= b.dst.height) continue;
         cpvk_set_pixel_f32_dyn(b.dst.format, reinterpret_cast<cpvk_u8*>(b.dst.address) + (cpvk_u64)dstY * b.dst.rowPitch + (cpvk_u64)dstX * dtexel, value.v);
     }

@@ -246,6 +246,7 @@ public:
         if (vs) out << "extern \"C\" __device__ void cpvk_vs_main(cpvk_u32 vertexId, cpvk_u32 instanceId, cpvk_u32 rawId, const CpvkDrawParams* dp) {\n";
         else out << "extern \"C\" __device__ bool cpvk_fs_main(const CpvkFragCtx* ctx, CpvkFragOut* out) {\n  const CpvkDrawParams* dp = ctx->dp; (void)dp;\n";
         out << "  bool discard_ = false; (void)discard_;\n";
+        out << (vs ? "  const float* lut_ = nullptr; (void)lut_;\n" : "  const float* lut_ = ctx->unorm8; __builtin_assume(lut_ != nullptr);\n");
         for (auto& a : arrays) out << "  " << a << "\n";
         EmitDecls(out, "float", declF); EmitDecls(out, "unsigned", declU); EmitDecls(out, "bool", declB); EmitDecls(out, "CpvkVec4", declV);
         out << pre.str() << body.str();
@@ -856,7 +857,7 @@ private:
             const std::string t = "s" + std::to_string(tmpCounter++);
             declV.insert(t);
             body << "  " << t << " = cpvk_image_sample(" << h->second << ", " << W(ctx, in.ops[1], 0) << ", " << (cn > 1 ? W(ctx, in.ops[1], 1) : "0.0f") << ", "
-                 << (cn > 2 ? W(ctx, in.ops[1], 2) : "0.0f") << ", " << lod << ");\n";
+                 << (cn > 2 ? W(ctx, in.ops[1], 2) : "0.0f") << ", " << lod << ", lut_);\n";
             if (T(T(in.type).kind == Type::Vector ? T(in.type).elem : in.type).kind != Type::Float) throw Unsupported("integer image sampling");
             Comp(ctx, in, [&](uint32_t k) { return t + ".v[" + std::to_string(k) + "]"; });
             break; }
@@ -867,7 +868,7 @@ private:
             const std::string t = "s" + std::to_string(tmpCounter++);
             declV.insert(t);
             body << "  " << t << " = cpvk_image_fetch(" << h->second << ", (int)" << W(ctx, in.ops[1], 0) << ", " << (cn > 1 ? "(int)" + W(ctx, in.ops[1], 1) : "0") << ", "
-                 << (cn > 2 ? "(int)" + W(ctx, in.ops[1], 2) : "0") << ");\n";
+                 << (cn > 2 ? "(int)" + W(ctx, in.ops[1], 2) : "0") << ", lut_);\n";
             if (T(T(in.type).kind == Type::Vector ? T(in.type).elem : in.type).kind != Type::Float) throw Unsupported("integer image fetch");
             Comp(ctx, in, [&](uint32_t k) { return t + ".v[" + std::to_string(k) + "]"; });
             break; }

@@ -189,7 +189,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
     // ---- shared-memory layout: [xf 32][yf 32] | depth tile | colour tiles ----
     float* sXf = reinterpret_cast<float*>(cpvk_smem);
     float* sYf = sXf + CPVK_TILE_W;
-    cpvk_u32 smemOff = (CPVK_TILE_W + CPVK_TILE_H) * 4;
+    float* sLut = sYf + CPVK_TILE_H; // [256] (float)k / 255.0f, see cpvk_get_pixel_f32_dyn
+    cpvk_u32 smemOff = (CPVK_TILE_W + CPVK_TILE_H + 256) * 4;
     const cpvk_u32 dsTexel = dsFormat ? cpvk_texel_size(dsFormat) : 0;
     cpvk_u8* sDepth = cpvk_smem + smemOff;
     const cpvk_u32 dsPitch = dsTexel * CPVK_TILE_W;
@@ -223,6 +224,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
         const float H = p.vpHeight; const float hp = (1.0f / H) * 0.5f;
         sYf[j] = ((float)(tileY0 + j) / H + hp) * 2.0f - 1.0f;
     }
+    sLut[threadIdx.x] = (float)threadIdx.x / 255.0f; // CPVK_RASTER_THREADS == 256
     // ---- stage the tile: HBM -> shared ----
     if (dsUsed)
         cpvk_tile_copy(sDepth, dsPitch, reinterpret_cast<const cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel,
@@ -305,7 +307,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
             } else {
                 float v[4] = {__uint_as_float(out.color[a][0]), __uint_as_float(out.color[a][1]), __uint_as_float(out.color[a][2]), __uint_as_float(out.color[a][3])};
                 if (blendOn || wm != 0xFu) {
-                    float d[4]; cpvk_get_pixel_f32(cf, cp, d); // ImageFetch of the destination (Draw.cpp:1283-1298)
+                    float d[4]; // ImageFetch of the destination (Draw.cpp:1283-1298)
+                    if (cf == 37 || cf == 44) cpvk_get_pixel_f32_dyn(cf, cp, d, sLut); else cpvk_get_pixel_f32(cf, cp, d);
                     if (blendOn) { float r[4]; cpvk_apply_blend(v, d, a, r); v[0] = r[0]; v[1] = r[1]; v[2] = r[2]; v[3] = r[3]; }
                     for (int k = 0; k < 4; k++) if (!(wm & (1u << k))) v[k] = d[k]; // PipelineCompiler.cpp:1695-1698
                 }
@@ -342,7 +345,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
             const int x = tileX0 + px, y = tileY0 + py;
             ctx.fragCoord[0] = cpvk_spec_u32(CPVK_SPEC_ORIGIN_UPPER) ? (float)x : p.vpWidth - (float)x - 1.0f; // Draw.cpp:1579
             ctx.fragCoord[1] = (float)y; ctx.fragCoord[2] = depth; ctx.fragCoord[3] = 1.0f;
-            ctx.vsOut = p.vsOut; ctx.nVerts = p.nVerts; ctx.dp = &p;
+            ctx.vsOut = p.vsOut; ctx.nVerts = p.nVerts; ctx.dp = &p; ctx.unorm8 = sLut;
             fragDepth = (p.vpMaxDepth - p.vpMinDepth) * depth + p.vpMinDepth;                       // DrawPixel, Draw.cpp:1310
             survive = !cpvk_fs_main(&ctx, &out);
             key = (cpvk_u32)(py * CPVK_TILE_W + px);
@@ -352,6 +355,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
         cpvk_u32 pending = __ballot_sync(0xFFFFFFFFu, survive);
         const cpvk_u32 lowerMask = (1u << lane) - 1u;
         cpvk_u32 writtenMask = 0;
+        #pragma unroll 1
         while (pending) {
             const bool go = ((pending >> lane) & 1u) && ((same & pending & lowerMask) == 0u);
             bool wrote = false;
@@ -366,6 +370,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
     };
 
     const bool regionLive = rx0 < rx1 && ry0 < ry1;
+    #pragma unroll 1
     for (cpvk_u32 chunkBase = listBegin; chunkBase < listEnd; chunkBase += CPVK_CHUNK) {
         const int n = (int)min((cpvk_u32)CPVK_CHUNK, listEnd - chunkBase);
         if (!p.listsSorted) {
@@ -398,6 +403,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
         }
         __syncthreads();
         if (regionLive) {
+            #pragma unroll 1
             for (int base = 0; base < n; base += 32) {
                 // 32 staged triangles at a time: lane-parallel bbox test against this warp's region
                 const int li = base + lane;
@@ -408,6 +414,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
                     hit = bx0 < rx1 && bx1 > rx0 && by0 < ry1 && by1 > ry0;
                 }
                 cpvk_u32 mask = __ballot_sync(0xFFFFFFFFu, hit);
+                #pragma unroll 1
                 while (mask) {
                     const int kt = base + __ffs(mask) - 1; // chunk-local triangle, warp-uniform
                     mask &= mask - 1;
@@ -422,6 +429,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
                     const int cw = cx1 - cx0;
                     const int lg = cw <= 4 ? 2 : (cw <= 8 ? 3 : 4); // lanes form a (1<<lg) x (32>>lg) block of candidates
                     const int lx = lane & ((1 << lg) - 1), ly = lane >> lg, rowsPer = 32 >> lg;
+                    #pragma unroll 1
                     for (int row0 = cy0; row0 < cy1; row0 += rowsPer) {
                         const int x = cx0 + lx, y = row0 + ly;
                         bool covered = x < cx1 && y < cy1;
@@ -449,6 +457,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(
                     }
                 }
             }
+            #pragma unroll 1
             while (qCount > 0) flush(qCount < 32 ? qCount : 32); // queue entries name chunk-local triangles: drain before restaging
         }
         __syncthreads();
