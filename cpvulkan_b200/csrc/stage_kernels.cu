@@ -170,7 +170,7 @@ extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 // the ordering the reference gets from its nested loops (Draw.cpp:1526-1593). Colour and depth live in shared
 // memory in their *storage* format for the whole tile lifetime: every ROP is the reference's get/set-pixel
 // round trip (GlslFunctions.cpp:842-928) on shared memory, and HBM sees one read and one write per tile byte.
-extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS) cpvk_k_raster(const __grid_constant__ CpvkDrawParams p) {
+extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_raster(const __grid_constant__ CpvkDrawParams p) {
     const cpvk_u32 tile = blockIdx.x;
     const cpvk_u32 listBegin = p.tileOffsets[tile], listEnd = p.tileOffsets[tile + 1];
     if (listBegin == listEnd) return;
