@@ -242,19 +242,11 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
     const int rx1 = min(rx0 + 16, x1), ry1 = min(ry0 + 8, y1);
     cpvk_u32 nCov = 0, nPass = 0;
 
-    // Per-warp fragment queue (ring of 64) in shared memory. Coverage (cheap, sparse) appends the covered pixels of
-    // successive triangles in API order; shading + ROP (expensive) always runs on 32 queued fragments at a time, so
-    // its lanes are full even when triangles cover a handful of pixels each. Order per pixel is preserved: the queue
-    // is FIFO, and inside a batch of 32 the ROP of fragments that hit the same pixel is serialised lowest lane first.
-    cpvk_u32* qXY = reinterpret_cast<cpvk_u32*>(cpvk_smem + smemOff) + warp * 64;          // px | py << 8 | chunk-local triangle << 16
-    float* qW0 = reinterpret_cast<float*>(cpvk_smem + smemOff + 1 * 8 * 64 * 4) + warp * 64;
-    float* qW1 = reinterpret_cast<float*>(cpvk_smem + smemOff + 2 * 8 * 64 * 4) + warp * 64;
-    float* qW2 = reinterpret_cast<float*>(cpvk_smem + smemOff + 3 * 8 * 64 * 4) + warp * 64;
-    // Triangle chunk staged by the whole CTA: CPVK_CHUNK setup records as six uint4 planes + bboxes. Every warp of the
-    // tile scans the same list, so one coalesced global read per record replaces eight latency-bound ones.
-    uint4* sQ = reinterpret_cast<uint4*>(cpvk_smem + smemOff + 4 * 8 * 64 * 4);                 // [6][CPVK_CHUNK]
-    uint2* sBB = reinterpret_cast<uint2*>(cpvk_smem + smemOff + 4 * 8 * 64 * 4 + 6 * CPVK_CHUNK * 16); // [CPVK_CHUNK]
-    int qHead = 0, qCount = 0; // warp-uniform
+    // Shared-memory scratch after the tiles: the staged triangle chunk (six uint4 planes of the setup records + bboxes,
+    // read by every warp of the tile) and one compacted hit list per warp.
+    uint4* sQ = reinterpret_cast<uint4*>(cpvk_smem + smemOff);                                   // [6][CPVK_CHUNK]
+    uint2* sBB = reinterpret_cast<uint2*>(cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16);            // [CPVK_CHUNK]
+    cpvk_u8* sHit = cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + warp * CPVK_CHUNK; // [warps][CPVK_CHUNK] chunk-local ids
 
     // ---- the fragment wrapper epilogue (PipelineCompiler.cpp:1061-1080) on the shared tile; returns "colour written" ----
     auto rop = [&](int px, int py, float fragDepth, bool front, const CpvkFragOut& out) -> bool {
@@ -318,21 +310,24 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
         return true;
     };
 
-    // ---- shade + ROP the oldest `take` (<= 32) queued fragments ----
-    auto flush = [&](int take) {
-        const bool active = lane < take;
-        const int slot = (qHead + lane) & 63;
+
+    // ---- shade + ROP one batch: lane = one fragment (active, chunk-local triangle kt, tile-local pixel px,py) ----
+    // Weights are recomputed from the staged edges (EdgeFunction, Draw.cpp:415-418 — same expression as the coverage
+    // test, so the same bits), then GetFragmentInput's normalisation/depth, DrawPixel's viewport depth, the fragment
+    // shader, and the epilogue. Fragments of one batch are in API order by lane; the ROP of fragments that share a
+    // pixel is serialised lowest lane first (a pixel belongs to exactly one warp, so that is the only hazard).
+    auto shadeBatch = [&](bool active, cpvk_u32 kt, int px, int py) {
         CpvkFragOut out;
         bool survive = false, front = true;
         float fragDepth = 0.0f;
-        int px = 0, py = 0;
         cpvk_u32 key = 0x80000000u | (cpvk_u32)lane; // unique for idle lanes
         if (active) {
-            const cpvk_u32 xy = qXY[slot];
-            const cpvk_u32 kt = xy >> 16;
-            float w0 = qW0[slot], w1 = qW1[slot], w2 = qW2[slot];
-            px = (int)(xy & 0xFFu); py = (int)((xy >> 8) & 0xFFu);
+            const uint4 q0 = sQ[kt], q1 = sQ[CPVK_CHUNK + kt], q2 = sQ[2 * CPVK_CHUNK + kt];
             const uint4 q3 = sQ[3 * CPVK_CHUNK + kt], q4 = sQ[4 * CPVK_CHUNK + kt], q5 = sQ[5 * CPVK_CHUNK + kt];
+            const float xf = sXf[px], yf = sYf[py];
+            float w0 = (xf - __uint_as_float(q0.x)) * __uint_as_float(q0.z) - (yf - __uint_as_float(q0.y)) * __uint_as_float(q0.w);
+            float w1 = (xf - __uint_as_float(q1.x)) * __uint_as_float(q1.z) - (yf - __uint_as_float(q1.y)) * __uint_as_float(q1.w);
+            float w2 = (xf - __uint_as_float(q2.x)) * __uint_as_float(q2.z) - (yf - __uint_as_float(q2.y)) * __uint_as_float(q2.w);
             const float area = __uint_as_float(q3.w);
             CpvkFragCtx ctx;
             w0 /= area; w1 /= area; w2 /= area;                                                   // Draw.cpp:905-907
@@ -350,7 +345,6 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
             survive = !cpvk_fs_main(&ctx, &out);
             key = (cpvk_u32)(py * CPVK_TILE_W + px);
         }
-        // ROP in API order: a fragment waits for every earlier (lower-lane) fragment of the same pixel
         const cpvk_u32 same = __match_any_sync(0xFFFFFFFFu, key);
         cpvk_u32 pending = __ballot_sync(0xFFFFFFFFu, survive);
         const cpvk_u32 lowerMask = (1u << lane) - 1u;
@@ -365,8 +359,6 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
             __syncwarp();
         }
         nPass += __popc(writtenMask);
-        qHead = (qHead + take) & 63; qCount -= take;
-        __syncwarp();
     };
 
     const bool regionLive = rx0 < rx1 && ry0 < ry1;
@@ -395,17 +387,17 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
         if ((int)threadIdx.x < n) stagedPrim = p.listsSorted ? __ldg(p.tileLists + chunkBase + threadIdx.x) : reinterpret_cast<const cpvk_u32*>(sQ)[threadIdx.x];
         if (!p.listsSorted) __syncthreads(); // every thread has read its sorted id before the planes are overwritten
         if ((int)threadIdx.x < n) { // CPVK_CHUNK == blockDim.x: one record per thread, 16-byte coalesced pieces
-            const cpvk_u32 prim = stagedPrim;
-            const uint4* sp = reinterpret_cast<const uint4*>(p.setups + prim);
+            const uint4* sp = reinterpret_cast<const uint4*>(p.setups + stagedPrim);
             #pragma unroll
             for (int j = 0; j < 6; j++) sQ[j * CPVK_CHUNK + threadIdx.x] = __ldg(sp + j);
-            sBB[threadIdx.x] = __ldg(reinterpret_cast<const uint2*>(p.bboxes + prim));
+            sBB[threadIdx.x] = __ldg(reinterpret_cast<const uint2*>(p.bboxes + stagedPrim));
         }
         __syncthreads();
         if (regionLive) {
+            // ---- step 1: compact the triangles whose bbox meets this warp's region (order kept) ----
+            int nHits = 0;
             #pragma unroll 1
             for (int base = 0; base < n; base += 32) {
-                // 32 staged triangles at a time: lane-parallel bbox test against this warp's region
                 const int li = base + lane;
                 bool hit = false;
                 if (li < n) {
@@ -413,52 +405,124 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
                     const int bx0 = (short)(b.x & 0xFFFFu), by0 = (short)(b.x >> 16), bx1 = (short)(b.y & 0xFFFFu), by1 = (short)(b.y >> 16);
                     hit = bx0 < rx1 && bx1 > rx0 && by0 < ry1 && by1 > ry0;
                 }
-                cpvk_u32 mask = __ballot_sync(0xFFFFFFFFu, hit);
-                #pragma unroll 1
-                while (mask) {
-                    const int kt = base + __ffs(mask) - 1; // chunk-local triangle, warp-uniform
-                    mask &= mask - 1;
-                    const uint4 q0 = sQ[kt], q1 = sQ[CPVK_CHUNK + kt], q2 = sQ[2 * CPVK_CHUNK + kt]; // broadcast reads
+                const cpvk_u32 m = __ballot_sync(0xFFFFFFFFu, hit);
+                if (hit) sHit[nHits + __popc(m & ((1u << lane) - 1u))] = (cpvk_u8)li;
+                nHits += __popc(m);
+            }
+            __syncwarp();
+            // ---- step 2: 32 hit triangles at a time, one per lane ----
+            // Small triangles (<= 32 candidate pixels in this region) get their coverage mask computed by their own lane;
+            // their covered pixels are then packed densely, 32 fragments per shading batch, in triangle order. A large
+            // triangle is rasterised by the whole warp, one pixel per lane, and splits the packing at its position so
+            // that fragments still reach the ROP in API order.
+            #pragma unroll 1
+            for (int hb = 0; hb < nHits; hb += 32) {
+                const bool valid = hb + lane < nHits;
+                const cpvk_u32 kt = valid ? sHit[hb + lane] : 0u;
+                int cx0 = 0, cy0 = 0, cw = 0, ch = 0;
+                if (valid) {
                     const uint2 b = sBB[kt];
                     const int bx0 = (short)(b.x & 0xFFFFu), by0 = (short)(b.x >> 16), bx1 = (short)(b.y & 0xFFFFu), by1 = (short)(b.y >> 16);
-                    const float e0ax = __uint_as_float(q0.x), e0ay = __uint_as_float(q0.y), e0dy = __uint_as_float(q0.z), e0dx = __uint_as_float(q0.w);
-                    const float e1ax = __uint_as_float(q1.x), e1ay = __uint_as_float(q1.y), e1dy = __uint_as_float(q1.z), e1dx = __uint_as_float(q1.w);
-                    const float e2ax = __uint_as_float(q2.x), e2ay = __uint_as_float(q2.y), e2dy = __uint_as_float(q2.z), e2dx = __uint_as_float(q2.w);
-                    const int cx0 = max(bx0, rx0), cx1 = min(bx1, rx1);
-                    const int cy0 = max(by0, ry0), cy1 = min(by1, ry1);
-                    const int cw = cx1 - cx0;
-                    const int lg = cw <= 4 ? 2 : (cw <= 8 ? 3 : 4); // lanes form a (1<<lg) x (32>>lg) block of candidates
-                    const int lx = lane & ((1 << lg) - 1), ly = lane >> lg, rowsPer = 32 >> lg;
+                    cx0 = max(bx0, rx0); cy0 = max(by0, ry0);
+                    cw = min(bx1, rx1) - cx0; ch = min(by1, ry1) - cy0;
+                }
+                const int cand = cw * ch; // 1 .. 128
+                const bool small = valid && cand <= 32;
+                cpvk_u32 cov = 0; // bit c = candidate c (row-major inside the candidate rectangle) is covered
+                {
+                    float e0ax = 0, e0ay = 0, e0dy = 0, e0dx = 0, e1ax = 0, e1ay = 0, e1dy = 0, e1dx = 0, e2ax = 0, e2ay = 0, e2dy = 0, e2dx = 0;
+                    if (small) {
+                        const uint4 q0 = sQ[kt], q1 = sQ[CPVK_CHUNK + kt], q2 = sQ[2 * CPVK_CHUNK + kt];
+                        e0ax = __uint_as_float(q0.x); e0ay = __uint_as_float(q0.y); e0dy = __uint_as_float(q0.z); e0dx = __uint_as_float(q0.w);
+                        e1ax = __uint_as_float(q1.x); e1ay = __uint_as_float(q1.y); e1dy = __uint_as_float(q1.z); e1dx = __uint_as_float(q1.w);
+                        e2ax = __uint_as_float(q2.x); e2ay = __uint_as_float(q2.y); e2dy = __uint_as_float(q2.z); e2dx = __uint_as_float(q2.w);
+                    }
+                    const int maxCand = __reduce_max_sync(0xFFFFFFFFu, small ? cand : 0);
+                    int xx = 0, yy = 0;
                     #pragma unroll 1
-                    for (int row0 = cy0; row0 < cy1; row0 += rowsPer) {
-                        const int x = cx0 + lx, y = row0 + ly;
-                        bool covered = x < cx1 && y < cy1;
-                        float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
-                        if (covered) {
-                            // EdgeFunction (Draw.cpp:415-418) at the pixel centre; inside = none of the three is < 0
-                            // (no fill rule; NaN compares false, so NaN weights are accepted: Draw.cpp:900).
-                            const float xf = sXf[x - tileX0], yf = sYf[y - tileY0];
-                            w0 = (xf - e0ax) * e0dy - (yf - e0ay) * e0dx;
-                            w1 = (xf - e1ax) * e1dy - (yf - e1ay) * e1dx;
-                            w2 = (xf - e2ax) * e2dy - (yf - e2ay) * e2dx;
-                            covered = !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
+                    for (int c = 0; c < maxCand; c++) {
+                        if (small && c < cand) {
+                            // EdgeFunction at the pixel centre; inside = none of the three is < 0 (no fill rule; NaN accepted)
+                            const float xf = sXf[cx0 + xx - tileX0], yf = sYf[cy0 + yy - tileY0];
+                            const float w0 = (xf - e0ax) * e0dy - (yf - e0ay) * e0dx;
+                            const float w1 = (xf - e1ax) * e1dy - (yf - e1ay) * e1dx;
+                            const float w2 = (xf - e2ax) * e2dy - (yf - e2ay) * e2dx;
+                            if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) cov |= 1u << c;
+                            if (++xx == cw) { xx = 0; yy++; }
                         }
-                        const cpvk_u32 cm = __ballot_sync(0xFFFFFFFFu, covered);
-                        if (cm == 0) continue;
-                        if (covered) {
-                            const int slot = (qHead + qCount + __popc(cm & ((1u << lane) - 1u))) & 63;
-                            qXY[slot] = (cpvk_u32)(x - tileX0) | ((cpvk_u32)(y - tileY0) << 8) | ((cpvk_u32)kt << 16);
-                            qW0[slot] = w0; qW1[slot] = w1; qW2[slot] = w2;
-                        }
-                        const int added = __popc(cm);
-                        nCov += added; qCount += added;
-                        __syncwarp();
-                        if (qCount >= 32) flush(32);
                     }
                 }
+                const cpvk_u32 largeMask = __ballot_sync(0xFFFFFFFFu, valid && !small);
+                cpvk_u32 todo = __ballot_sync(0xFFFFFFFFu, valid);
+                // packed candidate rectangle for shuffles: cx0, cy0 tile-local (5 bits each), cw (6 bits)
+                const cpvk_u32 rectPacked = (cpvk_u32)((cx0 - tileX0) & 31) | ((cpvk_u32)((cy0 - tileY0) & 31) << 5) | ((cpvk_u32)cw << 10);
+                #pragma unroll 1
+                while (todo) {
+                    const cpvk_u32 lt = largeMask & todo;
+                    const int firstLarge = lt ? __ffs(lt) - 1 : 32;
+                    const cpvk_u32 seg = firstLarge == 32 ? todo : (todo & ((1u << firstLarge) - 1u));
+                    // state of the unified batch loop below: first the packed small segment, then the large triangle's rows
+                    const int cnt = ((seg >> lane) & 1u) ? __popc(cov) : 0;
+                    int incl = cnt;
+                    #pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
+                    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    nCov += total;
+                    // large triangle (warp-uniform)
+                    int lcx0 = 0, lcy0 = 0, lcx1 = 0, lcy1 = 0, lg = 4; cpvk_u32 lkt = 0;
+                    if (firstLarge < 32) {
+                        lkt = __shfl_sync(0xFFFFFFFFu, kt, firstLarge);
+                        lcx0 = __shfl_sync(0xFFFFFFFFu, cx0, firstLarge); lcy0 = __shfl_sync(0xFFFFFFFFu, cy0, firstLarge);
+                        lcx1 = lcx0 + __shfl_sync(0xFFFFFFFFu, cw, firstLarge); lcy1 = lcy0 + __shfl_sync(0xFFFFFFFFu, ch, firstLarge);
+                        const int lw = lcx1 - lcx0;
+                        lg = lw <= 4 ? 2 : (lw <= 8 ? 3 : 4); // lanes form a (1<<lg) x (32>>lg) block of candidates
+                    }
+                    int o = 0, row0 = lcy0;
+                    #pragma unroll 1
+                    for (;;) {
+                        bool active = false; cpvk_u32 bkt = 0; int px = 0, py = 0;
+                        if (o < total) {
+                            // next 32 fragments of the packed segment: fragment f belongs to the first lane s with incl[s] > f
+                            const int f = o + lane;
+                            int s = 0;
+                            #pragma unroll
+                            for (int step = 16; step > 0; step >>= 1) { const int v = __shfl_sync(0xFFFFFFFFu, incl, s + step - 1); if (v <= f) s += step; }
+                            s = min(s, 31);
+                            const int sIncl = __shfl_sync(0xFFFFFFFFu, incl, s), sCnt = __shfl_sync(0xFFFFFFFFu, cnt, s);
+                            const cpvk_u32 sCov = __shfl_sync(0xFFFFFFFFu, cov, s), sRect = __shfl_sync(0xFFFFFFFFu, rectPacked, s);
+                            bkt = __shfl_sync(0xFFFFFFFFu, kt, s);
+                            active = f < total;
+                            if (active) {
+                                const int k = f - (sIncl - sCnt);             // k-th covered candidate of triangle s
+                                const int c = (int)__fns(sCov, 0, k + 1);     // its candidate number
+                                const int w = (int)(sRect >> 10);
+                                const int row = c / w;                        // c < 32, w <= 32
+                                px = (int)(sRect & 31u) + (c - row * w); py = (int)((sRect >> 5) & 31u) + row;
+                            }
+                            o += 32;
+                        } else if (firstLarge < 32 && row0 < lcy1) {
+                            const int x = lcx0 + (lane & ((1 << lg) - 1)), y = row0 + (lane >> lg);
+                            bool covered = x < lcx1 && y < lcy1;
+                            if (covered) {
+                                const uint4 q0 = sQ[lkt], q1 = sQ[CPVK_CHUNK + lkt], q2 = sQ[2 * CPVK_CHUNK + lkt];
+                                const float xf = sXf[x - tileX0], yf = sYf[y - tileY0];
+                                const float w0 = (xf - __uint_as_float(q0.x)) * __uint_as_float(q0.z) - (yf - __uint_as_float(q0.y)) * __uint_as_float(q0.w);
+                                const float w1 = (xf - __uint_as_float(q1.x)) * __uint_as_float(q1.z) - (yf - __uint_as_float(q1.y)) * __uint_as_float(q1.w);
+                                const float w2 = (xf - __uint_as_float(q2.x)) * __uint_as_float(q2.z) - (yf - __uint_as_float(q2.y)) * __uint_as_float(q2.w);
+                                covered = !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
+                            }
+                            row0 += 32 >> lg;
+                            const cpvk_u32 cm = __ballot_sync(0xFFFFFFFFu, covered);
+                            if (cm == 0) continue;
+                            nCov += __popc(cm);
+                            active = covered; bkt = lkt; px = x - tileX0; py = y - tileY0;
+                        } else break;
+                        shadeBatch(active, bkt, px, py); // the only call site: one copy of the fragment shader per kernel
+                    }
+                    todo &= ~seg;
+                    if (firstLarge < 32) todo &= ~(1u << firstLarge);
+                }
             }
-            #pragma unroll 1
-            while (qCount > 0) flush(qCount < 32 ? qCount : 32); // queue entries name chunk-local triangles: drain before restaging
         }
         __syncthreads();
     }
