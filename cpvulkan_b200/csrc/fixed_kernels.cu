@@ -30,9 +30,8 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
     float P[3][4];
     #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float pos[4];
-        #pragma unroll
-        for (int c = 0; c < 4; c++) pos[c] = __uint_as_float(__ldg(a.vsOut + (cpvk_u64)c * a.nVerts + idx[k]));
+        const uint4 pv = __ldg(a.vsPos + idx[k]);
+        const float pos[4] = {__uint_as_float(pv.x), __uint_as_float(pv.y), __uint_as_float(pv.z), __uint_as_float(pv.w)};
         P[k][0] = pos[0] / pos[3]; P[k][1] = pos[1] / pos[3]; P[k][2] = pos[2] / pos[3]; // glm vec4 / scalar
         P[k][3] = pos[3];                                                                 // Draw.cpp:1544-1546
     }

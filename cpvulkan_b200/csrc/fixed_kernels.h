@@ -7,7 +7,7 @@
 #define CPVK_BIN_SMALL 16 /* primitives touching more tiles than this are binned by a whole CTA */
 
 struct CpvkSetupArgs {
-    const cpvk_u32* vsOut;
+    const uint4* vsPos;
     cpvk_u32 nVerts, primCount;
     cpvk_u32 topology, frontFace, cullMode;
     float vpWidth, vpHeight;

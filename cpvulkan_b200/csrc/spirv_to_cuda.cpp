@@ -517,7 +517,8 @@ private:
 
     void Epilogue(bool vs) {
         if (vs) {
-            auto outw = [&](uint32_t word, const std::string& val) { body << "  dp->vsOut[(cpvk_u64)" << word << "u * dp->nVerts + rawId] = " << val << ";\n"; };
+            body << "  cpvk_u32* rec_ = (cpvk_u32*)__builtin_assume_aligned(dp->vsOut + (cpvk_u64)rawId * dp->vsStride, 16);\n";
+            auto outw = [&](uint32_t word, const std::string& val) { if (word >= 6) body << "  rec_[cpvk_vs_slot(" << word << "u)] = " << val << ";\n"; };
             // builtin block {vec4 position, float pointSize, float clip[1]} = words 0..5 (PipelineCompiler.cpp:532-538, :957-960)
             std::string pos[4] = {"0u", "0u", "0u", "0u"}, psz = "0u", clip = "0u";
             if (perVertexVar) {
@@ -533,8 +534,8 @@ private:
             }
             if (positionVar) for (int q = 0; q < 4; q++) pos[q] = "g" + std::to_string(positionVar) + "[" + std::to_string(q) + "]";
             if (pointSizeVar) psz = "g" + std::to_string(pointSizeVar) + "[0]";
-            for (int q = 0; q < 4; q++) outw(q, pos[q]);
-            outw(4, psz); outw(5, clip);
+            body << "  dp->vsPos[rawId] = make_uint4(" << pos[0] << ", " << pos[1] << ", " << pos[2] << ", " << pos[3] << ");\n";
+            (void)psz; (void)clip; // words 4..5 of the record have no consumer on the triangle path
             uint32_t byteOff = 24;
             std::function<void(uint32_t, const std::string&, uint32_t&, uint32_t)> store = [&](uint32_t ty, const std::string& g, uint32_t& srcWord, uint32_t dstByte) {
                 const Type& t = T(ty);

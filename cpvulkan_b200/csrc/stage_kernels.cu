@@ -247,6 +247,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
     uint4* sQ = reinterpret_cast<uint4*>(cpvk_smem + smemOff);                                   // [6][CPVK_CHUNK]
     uint2* sBB = reinterpret_cast<uint2*>(cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16);            // [CPVK_CHUNK]
     cpvk_u8* sHit = cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + warp * CPVK_CHUNK; // [warps][CPVK_CHUNK] chunk-local ids
+    unsigned short* sFrag = reinterpret_cast<unsigned short*>(cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * CPVK_CHUNK)
+                            + warp * CPVK_FRAG_CAP;                                                  // [warps][CPVK_FRAG_CAP]
 
     // ---- the fragment wrapper epilogue (PipelineCompiler.cpp:1061-1080) on the shared tile; returns "colour written" ----
     auto rop = [&](int px, int py, float fragDepth, bool front, const CpvkFragOut& out) -> bool {
@@ -321,13 +323,22 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
         bool survive = false, front = true;
         float fragDepth = 0.0f;
         cpvk_u32 key = 0x80000000u | (cpvk_u32)lane; // unique for idle lanes
+        float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
         if (active) {
+            // EdgeFunction at the pixel centre; inside = none of the three is < 0 (no fill rule; NaN accepted). Packed
+            // fragments were already found covered by the same expression, so for them this is a no-op.
             const uint4 q0 = sQ[kt], q1 = sQ[CPVK_CHUNK + kt], q2 = sQ[2 * CPVK_CHUNK + kt];
-            const uint4 q3 = sQ[3 * CPVK_CHUNK + kt], q4 = sQ[4 * CPVK_CHUNK + kt], q5 = sQ[5 * CPVK_CHUNK + kt];
             const float xf = sXf[px], yf = sYf[py];
-            float w0 = (xf - __uint_as_float(q0.x)) * __uint_as_float(q0.z) - (yf - __uint_as_float(q0.y)) * __uint_as_float(q0.w);
-            float w1 = (xf - __uint_as_float(q1.x)) * __uint_as_float(q1.z) - (yf - __uint_as_float(q1.y)) * __uint_as_float(q1.w);
-            float w2 = (xf - __uint_as_float(q2.x)) * __uint_as_float(q2.z) - (yf - __uint_as_float(q2.y)) * __uint_as_float(q2.w);
+            w0 = (xf - __uint_as_float(q0.x)) * __uint_as_float(q0.z) - (yf - __uint_as_float(q0.y)) * __uint_as_float(q0.w);
+            w1 = (xf - __uint_as_float(q1.x)) * __uint_as_float(q1.z) - (yf - __uint_as_float(q1.y)) * __uint_as_float(q1.w);
+            w2 = (xf - __uint_as_float(q2.x)) * __uint_as_float(q2.z) - (yf - __uint_as_float(q2.y)) * __uint_as_float(q2.w);
+            active = !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
+        }
+        const cpvk_u32 covMask = __ballot_sync(0xFFFFFFFFu, active);
+        if (covMask == 0) return;
+        nCov += __popc(covMask);
+        if (active) {
+            const uint4 q3 = sQ[3 * CPVK_CHUNK + kt], q4 = sQ[4 * CPVK_CHUNK + kt], q5 = sQ[5 * CPVK_CHUNK + kt];
             const float area = __uint_as_float(q3.w);
             CpvkFragCtx ctx;
             w0 /= area; w1 /= area; w2 /= area;                                                   // Draw.cpp:905-907
@@ -335,12 +346,20 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
             ctx.w[0] = w0; ctx.w[1] = w1; ctx.w[2] = w2;
             ctx.pw[0] = __uint_as_float(q4.x); ctx.pw[1] = __uint_as_float(q4.y); ctx.pw[2] = __uint_as_float(q4.z);
             ctx.unitW = ctx.pw[0] == 1.0f && ctx.pw[1] == 1.0f && ctx.pw[2] == 1.0f;
+            {
+                float den = 0.0f; // dead code unless the shader has a perspective-interpolated input
+                if (ctx.unitW) { den += w0; den += w1; den += w2; }
+                else { den += w0 / ctx.pw[0]; den += w1 / ctx.pw[1]; den += w2 / ctx.pw[2]; }
+                ctx.persDen = den;
+            }
             front = (q4.w & 1u) != 0;
             ctx.idx[0] = q5.x; ctx.idx[1] = q5.y; ctx.idx[2] = q5.z; ctx.provoking = q5.w;
             const int x = tileX0 + px, y = tileY0 + py;
             ctx.fragCoord[0] = cpvk_spec_u32(CPVK_SPEC_ORIGIN_UPPER) ? (float)x : p.vpWidth - (float)x - 1.0f; // Draw.cpp:1579
             ctx.fragCoord[1] = (float)y; ctx.fragCoord[2] = depth; ctx.fragCoord[3] = 1.0f;
-            ctx.vsOut = p.vsOut; ctx.nVerts = p.nVerts; ctx.dp = &p; ctx.unorm8 = sLut;
+            ctx.v[0] = p.vsOut + (cpvk_u64)q5.x * p.vsStride; ctx.v[1] = p.vsOut + (cpvk_u64)q5.y * p.vsStride;
+            ctx.v[2] = p.vsOut + (cpvk_u64)q5.z * p.vsStride; ctx.vProv = p.vsOut + (cpvk_u64)q5.w * p.vsStride;
+            ctx.dp = &p; ctx.unorm8 = sLut;
             fragDepth = (p.vpMaxDepth - p.vpMinDepth) * depth + p.vpMinDepth;                       // DrawPixel, Draw.cpp:1310
             survive = !cpvk_fs_main(&ctx, &out);
             key = (cpvk_u32)(py * CPVK_TILE_W + px);
@@ -454,20 +473,40 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
                 }
                 const cpvk_u32 largeMask = __ballot_sync(0xFFFFFFFFu, valid && !small);
                 cpvk_u32 todo = __ballot_sync(0xFFFFFFFFu, valid);
-                // packed candidate rectangle for shuffles: cx0, cy0 tile-local (5 bits each), cw (6 bits)
-                const cpvk_u32 rectPacked = (cpvk_u32)((cx0 - tileX0) & 31) | ((cpvk_u32)((cy0 - tileY0) & 31) << 5) | ((cpvk_u32)cw << 10);
+                // Covered candidates of the small triangles are written, triangle after triangle (= API order), to this
+                // warp's fragment list in shared memory: 16 bits each = chunk-local triangle | x, y inside the warp region.
+                // The list is then shaded 32 fragments at a time. A large triangle ends the segment and is rasterised by
+                // the whole warp right after it, so fragments still reach the ROP in API order.
+                const cpvk_u32 divMagic = 1024u / (cpvk_u32)max(cw, 1) + 1u; // (c * divMagic) >> 10 == c / cw for c < 32, cw <= 16
+                const cpvk_u32 fragBase = kt | ((cpvk_u32)(cx0 - rx0) << 8) | ((cpvk_u32)(cy0 - ry0) << 12);
                 #pragma unroll 1
                 while (todo) {
                     const cpvk_u32 lt = largeMask & todo;
-                    const int firstLarge = lt ? __ffs(lt) - 1 : 32;
-                    const cpvk_u32 seg = firstLarge == 32 ? todo : (todo & ((1u << firstLarge) - 1u));
-                    // state of the unified batch loop below: first the packed small segment, then the large triangle's rows
-                    const int cnt = ((seg >> lane) & 1u) ? __popc(cov) : 0;
+                    int firstLarge = lt ? __ffs(lt) - 1 : 32;
+                    cpvk_u32 seg = firstLarge == 32 ? todo : (todo & ((1u << firstLarge) - 1u));
+                    int cnt = ((seg >> lane) & 1u) ? __popc(cov) : 0;
                     int incl = cnt;
                     #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
-                    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                    nCov += total;
+                    if (__shfl_sync(0xFFFFFFFFu, incl, 31) > CPVK_FRAG_CAP) {
+                        // more fragments than the list holds: keep the longest prefix that fits, the rest (and the large
+                        // triangle, which must come after them) waits for the next round
+                        seg &= __ballot_sync(0xFFFFFFFFu, incl <= CPVK_FRAG_CAP);
+                        if (!((seg >> lane) & 1u)) cnt = 0;
+                        firstLarge = 32;
+                    }
+                    const int total = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(cnt ? incl : 0));
+                    {
+                        int pos = incl - cnt;
+                        cpvk_u32 m = cnt ? cov : 0u;
+                        while (m) {
+                            const cpvk_u32 c = (cpvk_u32)__ffs((int)m) - 1u;
+                            m &= m - 1u;
+                            const cpvk_u32 row = (c * divMagic) >> 10;
+                            sFrag[pos++] = (unsigned short)(fragBase + ((c - row * (cpvk_u32)cw) << 8) + (row << 12));
+                        }
+                    }
+                    __syncwarp();
                     // large triangle (warp-uniform)
                     int lcx0 = 0, lcy0 = 0, lcx1 = 0, lcy1 = 0, lg = 4; cpvk_u32 lkt = 0;
                     if (firstLarge < 32) {
@@ -482,43 +521,20 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
                     for (;;) {
                         bool active = false; cpvk_u32 bkt = 0; int px = 0, py = 0;
                         if (o < total) {
-                            // next 32 fragments of the packed segment: fragment f belongs to the first lane s with incl[s] > f
-                            const int f = o + lane;
-                            int s = 0;
-                            #pragma unroll
-                            for (int step = 16; step > 0; step >>= 1) { const int v = __shfl_sync(0xFFFFFFFFu, incl, s + step - 1); if (v <= f) s += step; }
-                            s = min(s, 31);
-                            const int sIncl = __shfl_sync(0xFFFFFFFFu, incl, s), sCnt = __shfl_sync(0xFFFFFFFFu, cnt, s);
-                            const cpvk_u32 sCov = __shfl_sync(0xFFFFFFFFu, cov, s), sRect = __shfl_sync(0xFFFFFFFFu, rectPacked, s);
-                            bkt = __shfl_sync(0xFFFFFFFFu, kt, s);
-                            active = f < total;
+                            active = o + lane < total;
                             if (active) {
-                                const int k = f - (sIncl - sCnt);             // k-th covered candidate of triangle s
-                                const int c = (int)__fns(sCov, 0, k + 1);     // its candidate number
-                                const int w = (int)(sRect >> 10);
-                                const int row = c / w;                        // c < 32, w <= 32
-                                px = (int)(sRect & 31u) + (c - row * w); py = (int)((sRect >> 5) & 31u) + row;
+                                const cpvk_u32 rec = sFrag[o + lane];
+                                bkt = rec & 255u; px = rx0 - tileX0 + (int)((rec >> 8) & 15u); py = ry0 - tileY0 + (int)(rec >> 12);
                             }
                             o += 32;
                         } else if (firstLarge < 32 && row0 < lcy1) {
                             const int x = lcx0 + (lane & ((1 << lg) - 1)), y = row0 + (lane >> lg);
-                            bool covered = x < lcx1 && y < lcy1;
-                            if (covered) {
-                                const uint4 q0 = sQ[lkt], q1 = sQ[CPVK_CHUNK + lkt], q2 = sQ[2 * CPVK_CHUNK + lkt];
-                                const float xf = sXf[x - tileX0], yf = sYf[y - tileY0];
-                                const float w0 = (xf - __uint_as_float(q0.x)) * __uint_as_float(q0.z) - (yf - __uint_as_float(q0.y)) * __uint_as_float(q0.w);
-                                const float w1 = (xf - __uint_as_float(q1.x)) * __uint_as_float(q1.z) - (yf - __uint_as_float(q1.y)) * __uint_as_float(q1.w);
-                                const float w2 = (xf - __uint_as_float(q2.x)) * __uint_as_float(q2.z) - (yf - __uint_as_float(q2.y)) * __uint_as_float(q2.w);
-                                covered = !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
-                            }
                             row0 += 32 >> lg;
-                            const cpvk_u32 cm = __ballot_sync(0xFFFFFFFFu, covered);
-                            if (cm == 0) continue;
-                            nCov += __popc(cm);
-                            active = covered; bkt = lkt; px = x - tileX0; py = y - tileY0;
+                            active = x < lcx1 && y < lcy1; bkt = lkt; px = x - tileX0; py = y - tileY0; // coverage is tested by shadeBatch
                         } else break;
                         shadeBatch(active, bkt, px, py); // the only call site: one copy of the fragment shader per kernel
                     }
+                    __syncwarp();
                     todo &= ~seg;
                     if (firstLarge < 32) todo &= ~(1u << firstLarge);
                 }
