@@ -17,9 +17,27 @@ __device__ __forceinline__ int cpvk_cvtt(float v) {
     return (v >= 2147483648.0f || v < -2147483648.0f || v != v) ? (int)0x80000000 : (int)v;
 }
 
+// Warp-aggregated walk over the (at most CPVK_BIN_SMALL) tiles of each lane's bbox: lanes that name the same tile in
+// the same step are served by one atomic. Consecutive primitives mostly land in the same few tiles, so this cuts
+// the same-address atomics by an order of magnitude. fn(tile, leader, lanesOnThisTile, rankAmongThem).
+template <typename F> __device__ __forceinline__ void cpvk_for_each_tile_aggregated(bool has, int tx0, int ty0, int tw, int n, cpvk_u32 tilesX, F fn) {
+    const int lane = threadIdx.x & 31;
+    const int maxN = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(has ? n : 0));
+    int cx = 0, cy = 0;
+    for (int j = 0; j < maxN; j++) {
+        const bool live = has && j < n;
+        const cpvk_u32 t = live ? (cpvk_u32)(ty0 + cy) * tilesX + (cpvk_u32)(tx0 + cx) : 0xFFFFFFFFu;
+        const cpvk_u32 m = __match_any_sync(0xFFFFFFFFu, t);
+        fn(t, live, m, lane);
+        if (++cx == tw) { cx = 0; cy++; }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
-    const cpvk_u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.primCount) return;
+    __shared__ uint4 sRec[256 / 32][32 * 6]; // one warp's 32 records, staged so that the HBM stores are contiguous 512-byte rows
+    const cpvk_u32 pRaw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = pRaw < a.primCount;
+    const cpvk_u32 p = valid ? pRaw : a.primCount - 1; // idle lanes of the last warp redo the last primitive, results dropped
     // CalculatePrimitives (Draw.cpp:614-661)
     cpvk_u32 i0, i1, i2, prov;
     if (a.topology == 3) { prov = p * 3; i0 = p * 3; i1 = p * 3 + 1; i2 = p * 3 + 2; }
@@ -69,17 +87,34 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
         s.z[k] = P[k][2]; s.pw[k] = P[k][3]; s.idx[k] = idx[k];
     }
     s.area = area; s.flags = front ? 1u : 0u; s.provoking = prov;
-    a.setups[p] = s;
-    CpvkBBox bb;
-    if (culled || endX <= startX || endY <= startY) { bb.x0 = bb.y0 = bb.x1 = bb.y1 = 0; }
-    else { bb.x0 = (short)startX; bb.y0 = (short)startY; bb.x1 = (short)endX; bb.y1 = (short)endY; }
-    a.bboxes[p] = bb;
-    // binning pass 0, fused: count the (primitive, tile) pairs while the bbox is in registers
-    if (bb.x1 > bb.x0) {
-        const int tx0 = bb.x0 / CPVK_TILE_W, tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty0 = bb.y0 / CPVK_TILE_H, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
-        if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > CPVK_BIN_SMALL) { a.largeList[atomicAdd(a.meta + 2, 1u)] = p; }
-        else for (int ty = ty0; ty <= ty1; ty++) for (int tx = tx0; tx <= tx1; tx++) atomicAdd(a.counts + (cpvk_u32)ty * a.tilesX + (cpvk_u32)tx, 1u);
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint4* sv = reinterpret_cast<const uint4*>(&s);
+        #pragma unroll
+        for (int j = 0; j < 6; j++) sRec[warp][lane * 6 + j] = sv[j];
+        __syncwarp();
+        const cpvk_u32 warpFirst = pRaw - (cpvk_u32)lane;
+        const cpvk_u32 nRec = warpFirst < a.primCount ? min(32u, a.primCount - warpFirst) : 0u;
+        uint4* dst = reinterpret_cast<uint4*>(a.setups + warpFirst);
+        #pragma unroll
+        for (int j = 0; j < 6; j++) if ((cpvk_u32)(j * 32 + lane) < nRec * 6u) dst[j * 32 + lane] = sRec[warp][j * 32 + lane];
     }
+    CpvkBBox bb;
+    if (!valid || culled || endX <= startX || endY <= startY) { bb.x0 = bb.y0 = bb.x1 = bb.y1 = 0; }
+    else { bb.x0 = (short)startX; bb.y0 = (short)startY; bb.x1 = (short)endX; bb.y1 = (short)endY; }
+    if (valid) a.bboxes[p] = bb;
+    // binning pass 0, fused: count the (primitive, tile) pairs while the bbox is in registers
+    bool small = false; int tx0 = 0, ty0 = 0, tw = 1, n = 0;
+    if (bb.x1 > bb.x0) {
+        tx0 = bb.x0 / CPVK_TILE_W; ty0 = bb.y0 / CPVK_TILE_H;
+        const int tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
+        tw = tx1 - tx0 + 1; n = tw * (ty1 - ty0 + 1);
+        if (n > CPVK_BIN_SMALL) a.largeList[atomicAdd(a.meta + 2, 1u)] = p;
+        else small = true;
+    }
+    cpvk_for_each_tile_aggregated(small, tx0, ty0, tw, n, a.tilesX, [&](cpvk_u32 t, bool live, cpvk_u32 m, int lane) {
+        if (live && (int)__ffs((int)m) - 1 == lane) atomicAdd(a.counts + t, (cpvk_u32)__popc(m));
+    });
 }
 
 // ---- binning ----
@@ -88,18 +123,24 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
 // Primitives touching more than CPVK_BIN_SMALL tiles are deferred to k_bin_large, one CTA per primitive.
 __global__ void __launch_bounds__(256) k_bin(CpvkBinArgs a, int pass) {
     const cpvk_u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.primCount) return;
-    const CpvkBBox bb = a.bboxes[p];
-    if (bb.x1 <= bb.x0) return;
-    const int tx0 = bb.x0 / CPVK_TILE_W, tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty0 = bb.y0 / CPVK_TILE_H, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
-    const int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-    if (n > CPVK_BIN_SMALL) return; // deferred to k_bin_large (listed by k_setup)
-    for (int ty = ty0; ty <= ty1; ty++)
-        for (int tx = tx0; tx <= tx1; tx++) {
-            const cpvk_u32 t = (cpvk_u32)ty * a.tilesX + (cpvk_u32)tx;
-            if (pass == 0) atomicAdd(a.counts + t, 1u);
-            else a.lists[atomicAdd(a.cursors + t, 1u)] = p;
+    bool small = false; int tx0 = 0, ty0 = 0, tw = 1, n = 0;
+    if (p < a.primCount) {
+        const CpvkBBox bb = a.bboxes[p];
+        if (bb.x1 > bb.x0) {
+            tx0 = bb.x0 / CPVK_TILE_W; ty0 = bb.y0 / CPVK_TILE_H;
+            const int tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
+            tw = tx1 - tx0 + 1; n = tw * (ty1 - ty0 + 1);
+            small = n <= CPVK_BIN_SMALL; // larger ones are deferred to k_bin_large (listed by k_setup)
         }
+    }
+    cpvk_for_each_tile_aggregated(small, tx0, ty0, tw, n, a.tilesX, [&](cpvk_u32 t, bool live, cpvk_u32 m, int lane) {
+        const int leader = (int)__ffs((int)m) - 1;
+        if (pass == 0) { if (live && leader == lane) atomicAdd(a.counts + t, (cpvk_u32)__popc(m)); return; }
+        cpvk_u32 base = 0;
+        if (live && leader == lane) base = atomicAdd(a.cursors + t, (cpvk_u32)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (live) a.lists[base + (cpvk_u32)__popc(m & ((1u << lane) - 1u))] = p; // ascending primitive id inside the claim
+    });
 }
 __global__ void __launch_bounds__(256) k_bin_large(CpvkBinArgs a, int pass) {
     const cpvk_u32 nLarge = a.meta[2];
@@ -233,10 +274,16 @@ __global__ void __launch_bounds__(256) k_clear(CpvkDevAttachment img, CpvkClearA
     const bool vec = ((img.address | img.rowPitch | rowBytes) & 15) == 0 && (16 % texel) == 0;
     if (vec) {
         const uint4 v = *reinterpret_cast<const uint4*>(pattern);
-        const cpvk_u64 per = rowBytes >> 4, total = per * img.height;
-        for (cpvk_u64 i = (cpvk_u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (cpvk_u64)gridDim.x * blockDim.x) {
-            const cpvk_u64 r = i / per, q = i - r * per;
-            reinterpret_cast<uint4*>(base + r * img.rowPitch)[q] = v;
+        if (img.rowPitch == rowBytes) { // one contiguous block
+            uint4* d = reinterpret_cast<uint4*>(base);
+            const cpvk_u64 total = ((cpvk_u64)rowBytes * img.height) >> 4, stride = (cpvk_u64)gridDim.x * blockDim.x;
+            for (cpvk_u64 i = (cpvk_u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) d[i] = v;
+        } else {
+            const cpvk_u32 per = rowBytes >> 4;
+            for (cpvk_u32 r = blockIdx.x; r < img.height; r += gridDim.x) {
+                uint4* d = reinterpret_cast<uint4*>(base + (cpvk_u64)r * img.rowPitch);
+                for (cpvk_u32 q = threadIdx.x; q < per; q += blockDim.x) d[q] = v;
+            }
         }
     } else {
         const cpvk_u64 total = (cpvk_u64)img.width * img.height;
@@ -252,9 +299,15 @@ __global__ void __launch_bounds__(256) k_copy_rows(cpvk_u8* dst, cpvk_u32 dstPit
     const cpvk_u64 align = (cpvk_u64)dst | (cpvk_u64)src | dstPitch | srcPitch | rowBytes;
     const cpvk_u64 stride = (cpvk_u64)gridDim.x * blockDim.x, start = (cpvk_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if ((align & 15) == 0) {
-        const cpvk_u64 per = rowBytes >> 4, total = per * rows;
-        for (cpvk_u64 i = start; i < total; i += stride) { const cpvk_u64 r = i / per, q = i - r * per;
-            reinterpret_cast<uint4*>(dst + r * dstPitch)[q] = __ldg(reinterpret_cast<const uint4*>(src + r * srcPitch) + q); }
+        if (dstPitch == rowBytes && srcPitch == rowBytes) { // one contiguous block
+            const cpvk_u64 total = ((cpvk_u64)rowBytes * rows) >> 4;
+            for (cpvk_u64 i = start; i < total; i += stride) reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        } else {
+            const cpvk_u32 per = rowBytes >> 4;
+            for (cpvk_u32 r = blockIdx.x; r < rows; r += gridDim.x)
+                for (cpvk_u32 q = threadIdx.x; q < per; q += blockDim.x)
+                    reinterpret_cast<uint4*>(dst + (cpvk_u64)r * dstPitch)[q] = __ldg(reinterpret_cast<const uint4*>(src + (cpvk_u64)r * srcPitch) + q);
+        }
     } else {
         const cpvk_u64 total = (cpvk_u64)rowBytes * rows;
         for (cpvk_u64 i = start; i < total; i += stride) { const cpvk_u64 r = i / rowBytes, q = i - r * rowBytes; dst[r * dstPitch + q] = src[r * srcPitch + q]; }
