@@ -395,9 +395,13 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
             sKeys[threadIdx.x] = key;
             __syncthreads();
             if ((int)threadIdx.x < n) {
-                cpvk_u32 rank = 0;
+                cpvk_u32 rank = 0xFFFFFFFFu;
                 const uint4* k4 = reinterpret_cast<const uint4*>(sKeys);
-                for (int j = 0; j < (n + 3) / 4; j++) { const uint4 v = k4[j]; rank += (v.x < key) + (v.y < key) + (v.z < key) + (v.w < key); }
+                // rank += (v <= key): the carry of key - v (set when there is no borrow, i.e. v <= key) is added straight
+                // into the rank, 1.5 instructions per key. The key itself is counted once, hence the start value -1.
+                #define CPVK_RANK_STEP(v) asm("{ .reg .u32 t; sub.cc.u32 t, %2, %1; addc.u32 %0, %0, 0; }" : "+r"(rank) : "r"(v), "r"(key))
+                for (int j = 0; j < (n + 3) / 4; j++) { const uint4 v = k4[j]; CPVK_RANK_STEP(v.x); CPVK_RANK_STEP(v.y); CPVK_RANK_STEP(v.z); CPVK_RANK_STEP(v.w); }
+                #undef CPVK_RANK_STEP
                 sSorted[rank] = key;
             }
             __syncthreads();
@@ -456,18 +460,39 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
                         e1ax = __uint_as_float(q1.x); e1ay = __uint_as_float(q1.y); e1dy = __uint_as_float(q1.z); e1dx = __uint_as_float(q1.w);
                         e2ax = __uint_as_float(q2.x); e2ay = __uint_as_float(q2.y); e2dy = __uint_as_float(q2.z); e2dx = __uint_as_float(q2.w);
                     }
+                    // EdgeFunction at the pixel centre (Draw.cpp:415-418); inside = none of the three is < 0 (no fill rule,
+                    // NaN accepted). w = A - B with A = (x - ax) * dy, B = (y - ay) * dx, and fl(A - B) < 0 exactly when
+                    // A < B, so the coverage test compares the two products and skips the subtraction.
                     const int maxCand = __reduce_max_sync(0xFFFFFFFFu, small ? cand : 0);
-                    int xx = 0, yy = 0;
-                    #pragma unroll 1
-                    for (int c = 0; c < maxCand; c++) {
-                        if (small && c < cand) {
-                            // EdgeFunction at the pixel centre; inside = none of the three is < 0 (no fill rule; NaN accepted)
-                            const float xf = sXf[cx0 + xx - tileX0], yf = sYf[cy0 + yy - tileY0];
-                            const float w0 = (xf - e0ax) * e0dy - (yf - e0ay) * e0dx;
-                            const float w1 = (xf - e1ax) * e1dy - (yf - e1ay) * e1dx;
-                            const float w2 = (xf - e2ax) * e2dy - (yf - e2ay) * e2dx;
-                            if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) cov |= 1u << c;
-                            if (++xx == cw) { xx = 0; yy++; }
+                    const int maxW = __reduce_max_sync(0xFFFFFFFFu, small ? cw : 0), maxH = __reduce_max_sync(0xFFFFFFFFu, small ? ch : 0);
+                    const int bx = small ? cx0 - tileX0 : 0, by = small ? cy0 - tileY0 : 0;
+                    if (maxW * maxH * 5 <= maxCand * 8) {
+                        // similar rectangles across the lanes: all lanes walk one maxW x maxH window in lockstep, which
+                        // hoists the row terms out of the pixel loop (candidate numbering stays row-major per lane)
+                        int c = 0;
+                        #pragma unroll 1
+                        for (int yy = 0; yy < maxH; yy++) {
+                            const bool rowIn = small && yy < ch;
+                            const float yf = sYf[by + (rowIn ? yy : 0)];
+                            const float b0 = (yf - e0ay) * e0dx, b1 = (yf - e1ay) * e1dx, b2 = (yf - e2ay) * e2dx;
+                            #pragma unroll 1
+                            for (int xx = 0; xx < maxW; xx++) {
+                                const float xf = sXf[bx + xx]; // bx + xx <= 46: stays inside the xf/yf/lut block
+                                const bool out = (xf - e0ax) * e0dy < b0 || (xf - e1ax) * e1dy < b1 || (xf - e2ax) * e2dy < b2;
+                                if (rowIn && xx < cw) { cov |= (out ? 0u : 1u) << c; c++; }
+                            }
+                        }
+                    } else {
+                        int xx = 0, yy = 0;
+                        #pragma unroll 1
+                        for (int c = 0; c < maxCand; c++) {
+                            if (small && c < cand) {
+                                const float xf = sXf[bx + xx], yf = sYf[by + yy];
+                                const bool out = (xf - e0ax) * e0dy < (yf - e0ay) * e0dx || (xf - e1ax) * e1dy < (yf - e1ay) * e1dx ||
+                                                 (xf - e2ax) * e2dy < (yf - e2ay) * e2dx;
+                                if (!out) cov |= 1u << c;
+                                if (++xx == cw) { xx = 0; yy++; }
+                            }
                         }
                     }
                 }
