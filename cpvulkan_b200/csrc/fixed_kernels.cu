@@ -271,7 +271,9 @@ __global__ void __launch_bounds__(256) k_clear(CpvkDevAttachment img, CpvkClearA
     __syncthreads();
     const cpvk_u32 rowBytes = texel * img.width;
     cpvk_u8* base = reinterpret_cast<cpvk_u8*>(img.address);
-    const bool vec = ((img.address | img.rowPitch | rowBytes) & 15) == 0 && (16 % texel) == 0;
+    // D32_SFLOAT_S8_UINT is the one format whose texel has bytes SetPixel never writes (5 of 8, GlslFunctions.cpp:898-914)
+    const cpvk_u32 written = img.format == 130 ? 5u : texel;
+    const bool vec = ((img.address | img.rowPitch | rowBytes) & 15) == 0 && (16 % texel) == 0 && written == texel;
     if (vec) {
         const uint4 v = *reinterpret_cast<const uint4*>(pattern);
         if (img.rowPitch == rowBytes) { // one contiguous block
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(256) k_clear(CpvkDevAttachment img, CpvkClearA
         for (cpvk_u64 i = (cpvk_u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (cpvk_u64)gridDim.x * blockDim.x) {
             const cpvk_u64 r = i / img.width, x = i - r * img.width;
             cpvk_u8* d = base + r * img.rowPitch + x * texel;
-            for (cpvk_u32 k = 0; k < texel; k++) d[k] = pattern[k];
+            for (cpvk_u32 k = 0; k < written; k++) d[k] = pattern[k];
         }
     }
 }

@@ -162,6 +162,18 @@ __device__ __forceinline__ void cpvk_tile_copy(cpvk_u8* dst, cpvk_u32 dstPitch, 
     }
 }
 
+// Fill a whole 32x32 shared-memory tile with one packed texel (texel size is a compile-time constant per pipeline).
+CPVK_DEV void cpvk_tile_fill(cpvk_u8* dst, cpvk_u32 texel, const cpvk_u8* one) {
+    for (cpvk_u32 i = threadIdx.x; i < CPVK_TILE_W * CPVK_TILE_H; i += blockDim.x) {
+        cpvk_u8* d = dst + i * texel;
+        if (texel == 16) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(one);
+        else if (texel == 8) *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(one);
+        else if (texel == 4) *reinterpret_cast<cpvk_u32*>(d) = *reinterpret_cast<const cpvk_u32*>(one);
+        else if (texel == 2) *reinterpret_cast<unsigned short*>(d) = *reinterpret_cast<const unsigned short*>(one);
+        else for (cpvk_u32 b = 0; b < texel; b++) d[b] = one[b];
+    }
+}
+
 extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 
 // One CTA per screen tile. Warp w owns the 16x8 sub-rectangle (w&1, w>>1) of the tile, so no two warps ever touch
@@ -173,7 +185,8 @@ extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_raster(const __grid_constant__ CpvkDrawParams p) {
     const cpvk_u32 tile = blockIdx.x;
     const cpvk_u32 listBegin = p.tileOffsets[tile], listEnd = p.tileOffsets[tile + 1];
-    if (listBegin == listEnd) return;
+    const cpvk_u32 lazyMask = p.lazyMask;
+    if (listBegin == listEnd && lazyMask == 0) return;
     const cpvk_u32 ty = tile / p.tilesX, tx = tile - ty * p.tilesX;
     const int tileX0 = (int)tx * CPVK_TILE_W, tileY0 = (int)ty * CPVK_TILE_H;
 
@@ -225,15 +238,29 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
         sYf[j] = ((float)(tileY0 + j) / H + hp) * 2.0f - 1.0f;
     }
     sLut[threadIdx.x] = (float)threadIdx.x / 255.0f; // CPVK_RASTER_THREADS == 256
-    // ---- stage the tile: HBM -> shared ----
-    if (dsUsed)
-        cpvk_tile_copy(sDepth, dsPitch, reinterpret_cast<const cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel,
-                       p.ds.rowPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th);
+    // ---- stage the tile: HBM -> shared, or the packed clear value when a deferred clear is folded into this draw ----
+    if (dsUsed) {
+        if (lazyMask & 0x100u) {
+            __align__(16) cpvk_u8 one[16];
+            cpvk_set_depth_stencil(dsFormat, one, p.lazyDepth, p.lazyStencil);
+            cpvk_tile_fill(sDepth, dsTexel, one);
+        } else
+            cpvk_tile_copy(sDepth, dsPitch, reinterpret_cast<const cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel,
+                           p.ds.rowPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th);
+    }
     #pragma unroll
     for (int a = 0; a < CPVK_MAX_COLOR; a++)
-        if (sColor[a])
-            cpvk_tile_copy(sColor[a], cTexel[a] * CPVK_TILE_W, reinterpret_cast<const cpvk_u8*>(p.color[a].address) + (cpvk_u64)tileY0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a],
-                           p.color[a].rowPitch, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th);
+        if (sColor[a]) {
+            if (lazyMask & (1u << a)) {
+                const cpvk_u32 cf = cpvk_spec_u32(CPVK_SPEC_COLOR_FORMAT0 + a);
+                __align__(16) cpvk_u8 one[16];
+                if (cpvk_format_is_int(cf)) { const cpvk_u32 v[4] = {p.lazyColor[a][0], p.lazyColor[a][1], p.lazyColor[a][2], p.lazyColor[a][3]}; cpvk_set_pixel_int(cf, one, v); }
+                else { const float v[4] = {__uint_as_float(p.lazyColor[a][0]), __uint_as_float(p.lazyColor[a][1]), __uint_as_float(p.lazyColor[a][2]), __uint_as_float(p.lazyColor[a][3])}; cpvk_set_pixel_f32(cf, one, v); }
+                cpvk_tile_fill(sColor[a], cTexel[a], one);
+            } else
+                cpvk_tile_copy(sColor[a], cTexel[a] * CPVK_TILE_W, reinterpret_cast<const cpvk_u8*>(p.color[a].address) + (cpvk_u64)tileY0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a],
+                               p.color[a].rowPitch, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th);
+        }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -569,7 +596,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
     }
     __syncthreads();
     // ---- write the tile back: shared -> HBM, row segments are contiguous in the linear image ----
-    if (dsUsed && depthTest && depthWrite || (dsUsed && stencilOn))
+    if (dsUsed && ((depthTest && depthWrite) || stencilOn || (lazyMask & 0x100u)))
         cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel, p.ds.rowPitch,
                        sDepth, dsPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th);
     #pragma unroll

@@ -42,6 +42,13 @@ class Device:
     def set_stats(self, on):
         _check(self.lib, self.lib.cpvk_cuda_device_set_stats(self.handle, int(on)))
 
+    def set_lazy_clear(self, on):
+        """Deferred clears (default on): see cpvk_cuda_flush in include/cpvk_cuda.h."""
+        _check(self.lib, self.lib.cpvk_cuda_device_set_lazy_clear(self.handle, int(on)))
+
+    def flush(self):
+        _check(self.lib, self.lib.cpvk_cuda_flush(self.handle))
+
     # memory ------------------------------------------------------------------------------------
     def alloc(self, nbytes, host_shadow=False):
         dev = C.c_uint64()

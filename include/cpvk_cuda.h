@@ -266,6 +266,13 @@ uint64_t cpvk_cuda_launch_count(const CpvkDevice* device);
 /* Render-pass loadOp CLEAR / vkCmdClear*Image: whole subresource, per-texel SetPixel semantics
    (CommandBuffer.cpp:591-640, Draw.cpp:117-149). isDepthStencil selects VkClearDepthStencilValue. */
 int cpvk_cuda_clear(CpvkDevice* device, const CpvkAttachment* image, const CpvkClearValue* value, int isDepthStencil);
+/* Clears are deferred by default: a clear is recorded and folded into the next cpvk_cuda_draw that renders to the same
+   attachment (its tiles start from the clear value, so the clear costs no pass over HBM); every other entry point of
+   this library that could observe the memory materialises pending clears first. Code that reads the memory behind the
+   library's back in stream order (e.g. a collective enqueued on the same stream right after a clear) calls
+   cpvk_cuda_flush first; cpvk_cuda_device_set_lazy_clear(device, 0) turns the deferral off. */
+int cpvk_cuda_flush(CpvkDevice* device);
+int cpvk_cuda_device_set_lazy_clear(CpvkDevice* device, int enable);
 
 /* vkCmdCopyImage / CopyBufferToImage / CopyImageToBuffer: raw row memcpy (CommandBuffer.Copy.cpp:77-200). */
 int cpvk_cuda_copy_rows(CpvkDevice* device, uint64_t dst, uint32_t dstPitch, uint64_t src, uint32_t srcPitch,
