@@ -185,7 +185,7 @@ def run_ours(args):
     band_bytes = rows * scene.color.pitch
 
     def frame():
-        sod.clear()
+        sod.clear(band_only=world > 1)
         sod.draw()
         if world > 1:
             dist.all_gather_into_tensor(color_t, color_t[rank * band_bytes:(rank + 1) * band_bytes])
@@ -232,7 +232,7 @@ def run_ours(args):
     dev.set_timing(True)
     vs, su, bn, rs = [], [], [], []
     for _ in range(args.steps):
-        sod.clear()
+        sod.clear(band_only=world > 1)
         sod.draw()
         s2 = dev.stats()
         vs.append(s2.msVertex); su.append(s2.msSetup); bn.append(s2.msBin); rs.append(s2.msRaster)

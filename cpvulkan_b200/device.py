@@ -135,10 +135,15 @@ class SceneOnDevice:
         if band is not None:
             self.m.state.bandY0, self.m.state.bandY1 = band
 
-    def clear(self):
+    def clear(self, band_only=False):
+        """Render-pass clear of the attachments. band_only: just the rows of this GPU's sort-first band (the other
+        rows belong to other GPUs and are overwritten by the gather)."""
+        y0, y1 = self.m.state.bandY0, self.m.state.bandY1
         for img, att in ((self.scene.color, self.m.color_attachment), (self.scene.depth, self.m.depth_attachment)):
             if img is not None and img.clear is not None:
                 cv, is_ds = scenes.clear_value(img)
+                if band_only and y1 > y0:
+                    att = capi.Attachment(att.address + y0 * att.rowPitch, att.width, min(y1, att.height) - y0, att.rowPitch, att.format)
                 self.dev.clear(att, cv, is_ds)
 
     def draw(self):
