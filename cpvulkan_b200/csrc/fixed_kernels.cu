@@ -44,6 +44,13 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
     else if (a.topology == 4) { prov = p; i0 = p; i1 = p + 1; i2 = p + 2; }
     else { prov = p + 1; i0 = 0; i1 = p + 1; i2 = p + 2; }
     if (a.frontFace == 1) { const cpvk_u32 t = i0; i0 = i2; i2 = t; } // Draw.cpp:1532-1535
+    if (cpvk_vcache_on(a.vcache, a.nVerts)) { // stream position -> shaded vertex
+        const cpvk_u32 lo = a.vcache[0];
+        i0 = cpvk_fetch_index(a.indexBuffer, a.indexStride, (cpvk_u64)a.first + i0) - lo;
+        i1 = cpvk_fetch_index(a.indexBuffer, a.indexStride, (cpvk_u64)a.first + i1) - lo;
+        i2 = cpvk_fetch_index(a.indexBuffer, a.indexStride, (cpvk_u64)a.first + i2) - lo;
+        prov = cpvk_fetch_index(a.indexBuffer, a.indexStride, (cpvk_u64)a.first + prov) - lo;
+    }
     const cpvk_u32 idx[3] = {i0, i1, i2};
     float P[3][4];
     #pragma unroll
@@ -117,6 +124,17 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
     });
 }
 
+// Lowest and highest index of an indexed draw (vertex reuse, CpvkDrawParams::vcache).
+__global__ void __launch_bounds__(256) k_index_range(cpvk_u64 indexBuffer, cpvk_u32 indexStride, cpvk_u32 first, cpvk_u32 count, cpvk_u32* range) {
+    cpvk_u32 lo = 0xFFFFFFFFu, hi = 0u;
+    for (cpvk_u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const cpvk_u32 v = cpvk_fetch_index(indexBuffer, indexStride, (cpvk_u64)first + i);
+        lo = min(lo, v); hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(range, lo); atomicMax(range + 1, hi); }
+}
+
 // ---- binning ----
 // Pass 0 counts (primitive, tile) pairs, pass 1 writes primitive ids at atomically claimed positions inside each
 // tile's segment; k_bin_sort then sorts every segment ascending, which restores API order exactly (ids are unique).
@@ -161,37 +179,32 @@ __global__ void __launch_bounds__(256) k_bin_large(CpvkBinArgs a, int pass) {
 // meta[0] = total entries, meta[1] = longest list.
 __global__ void __launch_bounds__(1024) k_bin_scan(CpvkBinArgs a) {
     __shared__ cpvk_u32 warpSums[32];
-    __shared__ cpvk_u32 carry, maxShared;
+    __shared__ cpvk_u32 maxShared;
     const cpvk_u32 tiles = a.tilesX * a.tilesY;
-    if (threadIdx.x == 0) { carry = 0; maxShared = 0; }
+    // thread t owns the contiguous run [t * per, (t + 1) * per): one serial pass for its sum, one block-wide scan of
+    // the 1024 sums, one serial pass to write the offsets (three barriers in total, whatever the tile count)
+    const cpvk_u32 per = (tiles + blockDim.x - 1) / blockDim.x;
+    const cpvk_u32 begin = min(threadIdx.x * per, tiles), end = min(begin + per, tiles);
+    if (threadIdx.x == 0) maxShared = 0;
+    cpvk_u32 sum = 0, localMax = 0;
+    for (cpvk_u32 i = begin; i < end; i++) { const cpvk_u32 v = a.counts[i]; sum += v; localMax = max(localMax, v); }
+    cpvk_u32 x = sum;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const cpvk_u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+    if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = x;
+    localMax = __reduce_max_sync(0xFFFFFFFFu, localMax);
     __syncthreads();
-    cpvk_u32 localMax = 0;
-    for (cpvk_u32 base = 0; base < tiles; base += blockDim.x) {
-        const cpvk_u32 i = base + threadIdx.x;
-        const cpvk_u32 v = i < tiles ? a.counts[i] : 0u;
-        localMax = max(localMax, v);
-        cpvk_u32 x = v;
+    if (threadIdx.x < 32) {
+        cpvk_u32 w = warpSums[threadIdx.x];
         #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const cpvk_u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
-        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            cpvk_u32 w = warpSums[threadIdx.x];
-            #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const cpvk_u32 y = __shfl_up_sync(0xFFFFFFFFu, w, d); if (threadIdx.x >= d) w += y; }
-            warpSums[threadIdx.x] = w;
-        }
-        __syncthreads();
-        const cpvk_u32 warpBase = (threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u;
-        const cpvk_u32 excl = carry + warpBase + x - v;
-        if (i < tiles) { a.offsets[i] = excl; a.cursors[i] = excl; }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += warpSums[31];
-        __syncthreads();
+        for (int d = 1; d < 32; d <<= 1) { const cpvk_u32 y = __shfl_up_sync(0xFFFFFFFFu, w, d); if (threadIdx.x >= d) w += y; }
+        warpSums[threadIdx.x] = w;
     }
-    atomicMax(&maxShared, localMax);
+    if ((threadIdx.x & 31) == 0) atomicMax(&maxShared, localMax);
     __syncthreads();
-    if (threadIdx.x == 0) { a.offsets[tiles] = carry; a.meta[0] = carry; a.meta[1] = maxShared; }
+    cpvk_u32 run = ((threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u) + x - sum; // exclusive prefix of this thread's run
+    for (cpvk_u32 i = begin; i < end; i++) { a.offsets[i] = run; a.cursors[i] = run; run += a.counts[i]; }
+    if (threadIdx.x == 0) { const cpvk_u32 total = warpSums[31]; a.offsets[tiles] = total; a.meta[0] = total; a.meta[1] = maxShared; }
 }
 // Per-tile ascending sort. Lists that fit the dynamic shared buffer use a bitonic network; longer ones fall back
 // to an in-place stable LSD split sort through `scratch` (rare: > capacity primitives over one 32x32 tile).
@@ -356,6 +369,13 @@ cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, cudaStream_t s) {
     if (a->primCount == 0) return cudaSuccess;
     if (pass != 0) k_bin<<<cpvk_grid(a->primCount, 256), 256, 0, s>>>(*a, pass); // pass 0 of the small primitives is fused into k_setup
     k_bin_large<<<592, 256, 0, s>>>(*a, pass); // 148 SMs x 4 resident CTAs; loops over the deferred list
+    return cudaGetLastError();
+}
+cudaError_t cpvk_launch_index_range(unsigned long long indexBuffer, unsigned indexStride, unsigned first, unsigned count, cpvk_u32* range, cudaStream_t s) {
+    if (!count) return cudaSuccess;
+    unsigned grid = cpvk_grid(count, 256 * 8);
+    if (grid > 148 * 8) grid = 148 * 8;
+    k_index_range<<<grid, 256, 0, s>>>(indexBuffer, indexStride, first, count, range);
     return cudaGetLastError();
 }
 cudaError_t cpvk_launch_bin_scan(const CpvkBinArgs* a, cudaStream_t s) {

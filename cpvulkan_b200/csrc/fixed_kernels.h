@@ -9,6 +9,10 @@
 struct CpvkSetupArgs {
     const uint4* vsPos;
     cpvk_u32 nVerts, primCount;
+    // vertex reuse (see CpvkDrawParams::vcache): raw vertex of stream position i = index[first + i] - lowest index
+    const cpvk_u32* vcache;
+    cpvk_u64 indexBuffer;
+    cpvk_u32 indexStride, first;
     cpvk_u32 topology, frontFace, cullMode;
     float vpWidth, vpHeight;
     cpvk_i32 clipX0, clipY0, clipX1, clipY1;
@@ -50,6 +54,7 @@ struct CpvkBlitArgs {
 
 extern "C" {
 cudaError_t cpvk_launch_setup(const CpvkSetupArgs* a, cudaStream_t s);
+cudaError_t cpvk_launch_index_range(unsigned long long indexBuffer, unsigned indexStride, unsigned first, unsigned count, cpvk_u32* range /* [2], preset to {~0u, 0} */, cudaStream_t s);
 cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, cudaStream_t s); /* pass 0: only the deferred large primitives (small ones are counted by k_setup) */
 cudaError_t cpvk_launch_bin_scan(const CpvkBinArgs* a, cudaStream_t s);
 cudaError_t cpvk_launch_bin_sort(const CpvkBinArgs* a, unsigned capacity, cudaStream_t s);

@@ -256,6 +256,7 @@ public:
 
 private:
     const CpvkShaderStage& stage; uint32_t model; const CpvkPipelineDesc& desc; PipelineLayoutInfo& layout;
+    bool storesToMemory = false;
     Module m;
     std::ostringstream body;
     std::set<std::string> declF, declU, declB, declV;
@@ -371,6 +372,7 @@ private:
             for (uint32_t k = 0; k < t.words; k++) body << "  " << LocalIndex(p, k) << " = " << ToWord(t.leaves[k], W(ctx, valueId, k)) << ";\n";
         } else {
             if (!p.writable) throw Unsupported("store to a read-only buffer");
+            storesToMemory = true;
             std::vector<uint32_t> offs; BufferLeaves(p.type, p.off, p.matStride, offs);
             for (uint32_t k = 0; k < t.words; k++) {
                 std::string o = std::to_string(offs[k]) + "ull"; if (!p.dyn.empty()) o += " + (cpvk_u64)(" + p.dyn + ")";
@@ -550,6 +552,7 @@ private:
                 byteOff += AllocSize(pointee);
             }
             layout.recordWords = byteOff / 4;
+            layout.vsWritesMemory = storesToMemory;
         } else {
             layout.originUpperLeft = m.originUpperLeft;
             // FindShaderLocations (PipelineCompiler.cpp:1729-1798): output at Location L feeds attachment L

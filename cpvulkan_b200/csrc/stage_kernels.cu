@@ -18,14 +18,13 @@ extern "C" __global__ void __launch_bounds__(256) cpvk_k_vertex(const __grid_con
     cpvk_u32 vertexId;
     if (p.indexStride == 0) {
         vertexId = p.first + i;
+    } else if (cpvk_vcache_on(p.vcache, p.count)) {
+        // vertex reuse: thread i shades the i-th vertex of the draw's index range, whatever number of indices name it
+        const cpvk_u32 lo = p.vcache[0];
+        if (i > p.vcache[1] - lo) return;
+        vertexId = (cpvk_u32)p.vertexOffset + lo + i;
     } else {
-        const cpvk_u8* ib = reinterpret_cast<const cpvk_u8*>(p.indexBuffer);
-        const cpvk_u64 k = (cpvk_u64)p.first + i;
-        cpvk_u32 index;
-        if (p.indexStride == 4) index = __ldg(reinterpret_cast<const cpvk_u32*>(ib) + k);
-        else if (p.indexStride == 2) index = __ldg(reinterpret_cast<const cpvk_u16*>(ib) + k);
-        else index = __ldg(ib + k);
-        vertexId = (cpvk_u32)p.vertexOffset + index;
+        vertexId = (cpvk_u32)p.vertexOffset + cpvk_fetch_index(p.indexBuffer, p.indexStride, (cpvk_u64)p.first + i);
     }
     cpvk_vs_main(vertexId, p.instance, i, &p);
 }

@@ -149,3 +149,32 @@ def test_band_equals_oracle_window(dev, band):
     gc, gd, gst = run_cuda(dev, scene, band=band)
     assert gst.fragmentsCovered == ost.fragmentsCovered and gst.fragmentsWritten == ost.fragmentsWritten
     assert np.array_equal(oc, gc) and np.array_equal(od, gd)
+
+
+def _indexed_variant(kind):
+    s = scenes.random_triangles(tris=120, seed=17, indexed=4)
+    ib = s.buffers["ib"].view(np.uint32).copy()
+    vb = s.buffers["vb"].view(np.float32).reshape(-1, 8).copy()
+    if kind == "reuse":  # 120 triangles over 40 distinct vertices
+        ib = (ib % 40).astype(np.uint32)
+    elif kind == "sparse":  # index range 7x the index count: the vertex stage falls back to one invocation per index
+        big = np.zeros((len(vb) * 7, 8), dtype=np.float32); big[::7] = vb; vb = big
+        ib = (ib * 7).astype(np.uint32)
+    elif kind == "offset":  # firstIndex and a negative vertexOffset on top of reuse
+        ib = np.concatenate([np.array([9, 9, 9, 9, 9], dtype=np.uint32), (ib % 50) + 3]).astype(np.uint32)
+        s.first, s.vertex_offset = 5, -3
+    elif kind == "strip":
+        s = scenes.random_triangles(tris=90, seed=18, topology=scenes.TRIANGLE_STRIP, indexed=2)
+        ib16 = s.buffers["ib"].view(np.uint16).copy()
+        s.buffers["ib"] = (ib16 % 30).astype(np.uint16).view(np.uint8).reshape(-1)
+        return s
+    s.buffers["ib"] = ib.view(np.uint8).reshape(-1)
+    s.buffers["vb"] = vb.reshape(-1).view(np.uint8)
+    return s
+
+
+@pytest.mark.parametrize("kind", ["reuse", "sparse", "offset", "strip"])
+def test_indexed_vertex_reuse(dev, kind):
+    """Indexed draws shade each vertex of a compact index range once (the reference shades every index); the records
+    are the same bits either way, and a sparse range falls back to per-index shading."""
+    compare(dev, _indexed_variant(kind))
