@@ -154,7 +154,12 @@ def run_ours(args):
 
     build.build_cuda()
     scene = scenes.mesh_indexed(WIDTH, HEIGHT, NX, NY)
-    stream = torch.cuda.current_stream()
+    # One explicit stream for everything: the draw kernels, the NCCL gather and the timing events. (torch's default
+    # stream has handle 0, which the C ABI reads as "use the device's own stream" — events recorded on the default
+    # stream would then not be ordered against the kernels.)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     dev = Device(local, stream=stream.cuda_stream, stats=True)
     rows = HEIGHT // world
     band = (rank * rows, (rank + 1) * rows) if world > 1 else None

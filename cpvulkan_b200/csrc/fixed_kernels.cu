@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
     else { prov = p + 1; i0 = 0; i1 = p + 1; i2 = p + 2; }
     if (a.frontFace == 1) { const cpvk_u32 t = i0; i0 = i2; i2 = t; } // Draw.cpp:1532-1535
     if (cpvk_vcache_on(a.vcache, a.nVerts)) { // stream position -> shaded vertex
-        const cpvk_u32 lo = a.vcache[0];
+        const cpvk_u32 lo = cpvk_vcache_lowest(a.vcache);
         i0 = cpvk_fetch_index(a.indexBuffer, a.indexStride, (cpvk_u64)a.first + i0) - lo;
         i1 = cpvk_fetch_index(a.indexBuffer, a.indexStride, (cpvk_u64)a.first + i1) - lo;
         i2 = cpvk_fetch_index(a.indexBuffer, a.indexStride, (cpvk_u64)a.first + i2) - lo;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) k_index_range(cpvk_u64 indexBuffer, cpvk_
         lo = min(lo, v); hi = max(hi, v);
     }
     lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
-    if ((threadIdx.x & 31) == 0) { atomicMin(range, lo); atomicMax(range + 1, hi); }
+    if ((threadIdx.x & 31) == 0) { atomicMax(range, ~lo); atomicMax(range + 1, hi); } // the lowest index is kept complemented so that a zero fill initialises both
 }
 
 // ---- binning ----
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(256) k_index_range(cpvk_u64 indexBuffer, cpvk_
 // tile's segment; k_bin_sort then sorts every segment ascending, which restores API order exactly (ids are unique).
 // Primitives touching more than CPVK_BIN_SMALL tiles are deferred to k_bin_large, one CTA per primitive.
 __global__ void __launch_bounds__(256) k_bin(CpvkBinArgs a, int pass) {
+    if (pass != 0 && a.meta[3] != 0) return; // plan mismatch: the host replays the fill
     const cpvk_u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     bool small = false; int tx0 = 0, ty0 = 0, tw = 1, n = 0;
     if (p < a.primCount) {
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256) k_bin(CpvkBinArgs a, int pass) {
     });
 }
 __global__ void __launch_bounds__(256) k_bin_large(CpvkBinArgs a, int pass) {
+    if (pass != 0 && a.meta[3] != 0) return;
     const cpvk_u32 nLarge = a.meta[2];
     for (cpvk_u32 li = blockIdx.x; li < nLarge; li += gridDim.x) {
         const cpvk_u32 p = a.largeList[li];
@@ -204,13 +206,23 @@ __global__ void __launch_bounds__(1024) k_bin_scan(CpvkBinArgs a) {
     __syncthreads();
     cpvk_u32 run = ((threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u) + x - sum; // exclusive prefix of this thread's run
     for (cpvk_u32 i = begin; i < end; i++) { a.offsets[i] = run; a.cursors[i] = run; run += a.counts[i]; }
-    if (threadIdx.x == 0) { const cpvk_u32 total = warpSums[31]; a.offsets[tiles] = total; a.meta[0] = total; a.meta[1] = maxShared; }
+    if (threadIdx.x == 0) {
+        const cpvk_u32 total = warpSums[31], longest = maxShared;
+        a.offsets[tiles] = total; a.meta[0] = total; a.meta[1] = longest;
+        const bool fits = total <= a.planCapacity && (longest <= CPVK_CHUNK || longest <= a.planSortCap) && (a.meta[2] == 0 || a.planLargeCounted != 0);
+        a.meta[3] = fits ? 0u : 1u;
+        if (a.metaHost) { // the host reads the answers from here after an event / stream sync: no copy in the stream
+            a.metaHost[0] = total; a.metaHost[1] = longest; a.metaHost[2] = a.meta[2]; a.metaHost[3] = fits ? 0u : 1u;
+            __threadfence_system();
+        }
+    }
 }
 // Per-tile ascending sort. Lists that fit the dynamic shared buffer use a bitonic network; longer ones fall back
 // to an in-place stable LSD split sort through `scratch` (rare: > capacity primitives over one 32x32 tile).
 __global__ void __launch_bounds__(256) k_bin_sort(CpvkBinArgs a, cpvk_u32 capacity) {
     extern __shared__ cpvk_u32 sKeys[];
     const cpvk_u32 t = blockIdx.x;
+    if (a.meta[3] != 0 || a.meta[1] <= CPVK_CHUNK) return; // plan mismatch, or every list fits one raster chunk (ordered there)
     const cpvk_u32 begin = a.offsets[t], n = a.offsets[t + 1] - begin;
     if (n < 2) return;
     cpvk_u32* list = a.lists + begin;
@@ -365,10 +377,10 @@ cudaError_t cpvk_launch_setup(const CpvkSetupArgs* a, cudaStream_t s) {
     k_setup<<<cpvk_grid(a->primCount, 256), 256, 0, s>>>(*a);
     return cudaGetLastError();
 }
-cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, cudaStream_t s) {
+cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, int small, int large, cudaStream_t s) {
     if (a->primCount == 0) return cudaSuccess;
-    if (pass != 0) k_bin<<<cpvk_grid(a->primCount, 256), 256, 0, s>>>(*a, pass); // pass 0 of the small primitives is fused into k_setup
-    k_bin_large<<<592, 256, 0, s>>>(*a, pass); // 148 SMs x 4 resident CTAs; loops over the deferred list
+    if (small) k_bin<<<cpvk_grid(a->primCount, 256), 256, 0, s>>>(*a, pass);
+    if (large) k_bin_large<<<592, 256, 0, s>>>(*a, pass); // 148 SMs x 4 resident CTAs; loops over the deferred list
     return cudaGetLastError();
 }
 cudaError_t cpvk_launch_index_range(unsigned long long indexBuffer, unsigned indexStride, unsigned first, unsigned count, cpvk_u32* range, cudaStream_t s) {
@@ -383,8 +395,7 @@ cudaError_t cpvk_launch_bin_scan(const CpvkBinArgs* a, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t cpvk_launch_bin_sort(const CpvkBinArgs* a, unsigned capacity, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+    if (capacity * 4 > 48 * 1024) cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     k_bin_sort<<<a->tilesX * a->tilesY, 256, capacity * 4, s>>>(*a, capacity);
     return cudaGetLastError();
 }

@@ -34,7 +34,12 @@ struct CpvkBinArgs {
     cpvk_u32* lists;     // [total entries]
     cpvk_u32* scratch;   // [total entries] or null (only needed by the long-list sort fallback)
     cpvk_u32* largeList; // [primCount]
-    cpvk_u32* meta;      // [0] total entries, [1] longest list, [2] deferred-primitive count
+    cpvk_u32* meta;      // [0] total entries, [1] longest list, [2] deferred-primitive count, [3] plan mismatch
+    cpvk_u32* metaHost;  // the same four words in mapped host memory, stored by k_bin_scan
+    // The launch plan the host committed to before knowing the counts; k_bin_scan checks it and raises meta[3].
+    cpvk_u32 planCapacity;     // entries `lists` can hold
+    cpvk_u32 planSortCap;      // longest list k_bin_sort was sized for (0 = not launched: lists must fit one raster chunk)
+    cpvk_u32 planLargeCounted; // 1 = k_bin_large's count pass ran before the scan
 };
 
 struct CpvkClearArgs {
@@ -54,8 +59,8 @@ struct CpvkBlitArgs {
 
 extern "C" {
 cudaError_t cpvk_launch_setup(const CpvkSetupArgs* a, cudaStream_t s);
-cudaError_t cpvk_launch_index_range(unsigned long long indexBuffer, unsigned indexStride, unsigned first, unsigned count, cpvk_u32* range /* [2], preset to {~0u, 0} */, cudaStream_t s);
-cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, cudaStream_t s); /* pass 0: only the deferred large primitives (small ones are counted by k_setup) */
+cudaError_t cpvk_launch_index_range(unsigned long long indexBuffer, unsigned indexStride, unsigned first, unsigned count, cpvk_u32* range /* [2] = {~lowest, highest}, zeroed by the caller */, cudaStream_t s);
+cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, int small, int large, cudaStream_t s); /* pass 0 = count, 1 = fill; small/large select k_bin / k_bin_large (small primitives are counted by k_setup) */
 cudaError_t cpvk_launch_bin_scan(const CpvkBinArgs* a, cudaStream_t s);
 cudaError_t cpvk_launch_bin_sort(const CpvkBinArgs* a, unsigned capacity, cudaStream_t s);
 cudaError_t cpvk_launch_clear(const CpvkDevAttachment* img, const CpvkClearArgs* c, cudaStream_t s);

@@ -20,7 +20,7 @@ extern "C" __global__ void __launch_bounds__(256) cpvk_k_vertex(const __grid_con
         vertexId = p.first + i;
     } else if (cpvk_vcache_on(p.vcache, p.count)) {
         // vertex reuse: thread i shades the i-th vertex of the draw's index range, whatever number of indices name it
-        const cpvk_u32 lo = p.vcache[0];
+        const cpvk_u32 lo = cpvk_vcache_lowest(p.vcache);
         if (i > p.vcache[1] - lo) return;
         vertexId = (cpvk_u32)p.vertexOffset + lo + i;
     } else {
@@ -183,6 +183,8 @@ extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 // round trip (GlslFunctions.cpp:842-928) on shared memory, and HBM sees one read and one write per tile byte.
 extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_raster(const __grid_constant__ CpvkDrawParams p) {
     const cpvk_u32 tile = blockIdx.x;
+    if (p.binMeta[3] != 0) return; // the speculative launch plan did not fit this draw: the host replays it
+    const bool listsSorted = p.binMeta[1] > CPVK_CHUNK;
     const cpvk_u32 listBegin = p.tileOffsets[tile], listEnd = p.tileOffsets[tile + 1];
     const cpvk_u32 lazyMask = p.lazyMask;
     if (listBegin == listEnd && lazyMask == 0) return;
@@ -410,7 +412,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
     #pragma unroll 1
     for (cpvk_u32 chunkBase = listBegin; chunkBase < listEnd; chunkBase += CPVK_CHUNK) {
         const int n = (int)min((cpvk_u32)CPVK_CHUNK, listEnd - chunkBase);
-        if (!p.listsSorted) {
+        if (!listsSorted) {
             // Binning claims list slots with atomics, so a tile's ids arrive in arbitrary order. When every list fits
             // one chunk the host skips k_bin_sort and the tile orders its own list here: ids are unique, so each id's
             // rank (number of smaller ids) is its position in API order. Broadcast shared-memory reads, no barriers
@@ -433,8 +435,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_rast
             __syncthreads();
         }
         cpvk_u32 stagedPrim = 0;
-        if ((int)threadIdx.x < n) stagedPrim = p.listsSorted ? __ldg(p.tileLists + chunkBase + threadIdx.x) : reinterpret_cast<const cpvk_u32*>(sQ)[threadIdx.x];
-        if (!p.listsSorted) __syncthreads(); // every thread has read its sorted id before the planes are overwritten
+        if ((int)threadIdx.x < n) stagedPrim = listsSorted ? __ldg(p.tileLists + chunkBase + threadIdx.x) : reinterpret_cast<const cpvk_u32*>(sQ)[threadIdx.x];
+        if (!listsSorted) __syncthreads(); // every thread has read its sorted id before the planes are overwritten
         if ((int)threadIdx.x < n) { // CPVK_CHUNK == blockDim.x: one record per thread, 16-byte coalesced pieces
             const uint4* sp = reinterpret_cast<const uint4*>(p.setups + stagedPrim);
             #pragma unroll

@@ -46,6 +46,10 @@ class Device:
         """Deferred clears (default on): see cpvk_cuda_flush in include/cpvk_cuda.h."""
         _check(self.lib, self.lib.cpvk_cuda_device_set_lazy_clear(self.handle, int(on)))
 
+    def set_speculation(self, on):
+        """Speculative draw tails (default on): see cpvk_cuda_device_set_speculation in include/cpvk_cuda.h."""
+        _check(self.lib, self.lib.cpvk_cuda_device_set_speculation(self.handle, int(on)))
+
     def flush(self):
         _check(self.lib, self.lib.cpvk_cuda_flush(self.handle))
 

@@ -272,6 +272,11 @@ int cpvk_cuda_clear(CpvkDevice* device, const CpvkAttachment* image, const CpvkC
    library's back in stream order (e.g. a collective enqueued on the same stream right after a clear) calls
    cpvk_cuda_flush first; cpvk_cuda_device_set_lazy_clear(device, 0) turns the deferral off. */
 int cpvk_cuda_flush(CpvkDevice* device);
+/* Draws are enqueued to the end without waiting for the binning counts: list capacity, sort mode and the large-
+   primitive passes are guessed from the previous draw, checked on the device, and the tail of the draw is replayed
+   with exact sizes when the guess was wrong (the check happens before this library enqueues or reads anything else,
+   so results never depend on the guess). 0 turns this off: every draw then waits for its counts (one host round trip). */
+int cpvk_cuda_device_set_speculation(CpvkDevice* device, int enable);
 int cpvk_cuda_device_set_lazy_clear(CpvkDevice* device, int enable);
 
 /* vkCmdCopyImage / CopyBufferToImage / CopyImageToBuffer: raw row memcpy (CommandBuffer.Copy.cpp:77-200). */

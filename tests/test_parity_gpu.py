@@ -178,3 +178,24 @@ def test_indexed_vertex_reuse(dev, kind):
     """Indexed draws shade each vertex of a compact index range once (the reference shades every index); the records
     are the same bits either way, and a sparse range falls back to per-index shading."""
     compare(dev, _indexed_variant(kind))
+
+
+def test_speculative_plan_replays(built):
+    """Draw tails are enqueued on the previous draw's binning answers; a wrong guess must be replayed invisibly.
+    A fresh device starts with no sort and a small list capacity, so this sequence hits every kind of mismatch:
+    lists longer than a raster chunk, more list entries than the default capacity, large primitives after none,
+    and back to small ones."""
+    from cpvulkan_b200.device import Device
+    d = Device(0, stats=True)
+    try:
+        seq = [scenes.mesh_indexed(width=320, height=200, nx=40, ny=25),                  # small primitives only
+               scenes.random_triangles(width=64, height=64, tris=900, seed=51),            # lists > 256: needs k_bin_sort
+               scenes.overdraw_quads(256, 256, 40, 16),                                     # 80 full-screen triangles x 64 tiles > default capacity, large primitives
+               scenes.mesh_indexed(width=320, height=200, nx=40, ny=25),
+               scenes.random_triangles(width=64, height=64, tris=900, seed=52)]
+        for sc in seq + seq[::-1]:
+            compare(d, sc)
+        d.set_speculation(False)
+        compare(d, seq[1])
+    finally:
+        d.close()
