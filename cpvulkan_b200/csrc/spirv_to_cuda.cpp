@@ -511,8 +511,7 @@ private:
                 const Type& et = pt.kind == Type::Vector ? T(pt.elem) : pt;
                 if ((pt.kind != Type::Vector && pt.kind != Type::Float) || et.kind != Type::Float)
                     throw Unsupported("only 32-bit float scalars/vectors interpolate (FATAL_ERROR, Draw.cpp:863-869)");
-                for (uint32_t k = 0; k < pt.words; k++)
-                    o << "  " << g << "[" << k << "] = __float_as_uint(" << (linear ? "cpvk_interp_linear" : "cpvk_interp_perspective") << "(ctx, " << word + k << "u));\n";
+                o << "  " << (linear ? "cpvk_interp_linear_vec" : "cpvk_interp_perspective_vec") << "(ctx, " << word << "u, " << pt.words << ", " << g << ");\n";
             }
         }
     }
