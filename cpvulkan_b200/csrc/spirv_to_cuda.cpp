@@ -859,8 +859,11 @@ private:
             const uint32_t cn = T(TypeOf(in.ops[1])).words;
             const std::string t = "s" + std::to_string(tmpCounter++);
             declV.insert(t);
+            if (model == 4) layout.fsSamplesImages = true;
+            int dimsHint = 0; // OpTypeImage Dim: 1D, 2D, 3D -> 1, 2, 3
+            { const Type& st = T(TypeOf(in.ops[0])); const Type& it = st.kind == Type::SampledImage ? T(st.elem) : st; if (it.kind == Type::Image && it.count <= 2) dimsHint = (int)it.count + 1; }
             body << "  " << t << " = cpvk_image_sample(" << h->second << ", " << W(ctx, in.ops[1], 0) << ", " << (cn > 1 ? W(ctx, in.ops[1], 1) : "0.0f") << ", "
-                 << (cn > 2 ? W(ctx, in.ops[1], 2) : "0.0f") << ", " << lod << ", lut_);\n";
+                 << (cn > 2 ? W(ctx, in.ops[1], 2) : "0.0f") << ", " << lod << ", lut_, " << dimsHint << ");\n";
             if (T(T(in.type).kind == Type::Vector ? T(in.type).elem : in.type).kind != Type::Float) throw Unsupported("integer image sampling");
             Comp(ctx, in, [&](uint32_t k) { return t + ".v[" + std::to_string(k) + "]"; });
             break; }
@@ -870,6 +873,7 @@ private:
             const uint32_t cn = T(TypeOf(in.ops[1])).words;
             const std::string t = "s" + std::to_string(tmpCounter++);
             declV.insert(t);
+            if (model == 4) layout.fsSamplesImages = true;
             body << "  " << t << " = cpvk_image_fetch(" << h->second << ", (int)" << W(ctx, in.ops[1], 0) << ", " << (cn > 1 ? "(int)" + W(ctx, in.ops[1], 1) : "0") << ", "
                  << (cn > 2 ? "(int)" + W(ctx, in.ops[1], 2) : "0") << ", lut_);\n";
             if (T(T(in.type).kind == Type::Vector ? T(in.type).elem : in.type).kind != Type::Float) throw Unsupported("integer image fetch");

@@ -19,6 +19,7 @@ struct PipelineLayoutInfo {
     uint32_t slotCount = 0;
     uint32_t recordWords = 6;        // VS output record size in 32-bit words (24-byte builtin block + outputs)
     bool originUpperLeft = false;    // FS OriginUpperLeft execution mode (Pipeline.cpp:976-984)
+    bool fsSamplesImages = false;    // the fragment shader samples or fetches images (large software sampler inlined: more registers pay off)
     bool vsWritesMemory = false;     // the vertex shader stores to a buffer: its invocation count is observable
 };
 

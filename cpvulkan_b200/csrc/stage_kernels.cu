@@ -181,7 +181,10 @@ extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 // the ordering the reference gets from its nested loops (Draw.cpp:1526-1593). Colour and depth live in shared
 // memory in their *storage* format for the whole tile lifetime: every ROP is the reference's get/set-pixel
 // round trip (GlslFunctions.cpp:842-928) on shared memory, and HBM sees one read and one write per tile byte.
-extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, 4) cpvk_k_raster(const __grid_constant__ CpvkDrawParams p) {
+#ifndef CPVK_RASTER_MIN_CTAS
+#define CPVK_RASTER_MIN_CTAS 4 /* resident CTAs per SM the register allocation aims for; build.py builds 4, 3 and 2 */
+#endif
+extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MIN_CTAS) cpvk_k_raster(const __grid_constant__ CpvkDrawParams p) {
     const cpvk_u32 tile = blockIdx.x;
     if (p.binMeta[3] != 0) return; // the speculative launch plan did not fit this draw: the host replays it
     const bool listsSorted = p.binMeta[1] > CPVK_CHUNK;
