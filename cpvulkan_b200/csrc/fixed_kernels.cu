@@ -342,29 +342,74 @@ __global__ void __launch_bounds__(256) k_copy_rows(cpvk_u8* dst, cpvk_u32 dstPit
 }
 
 // vkCmdBlitImage, one 2-D colour region: the reference samples the source as a 3-D image with lod 1 on a one-level
-// chain (-> level 0), clamp-to-edge, both z taps on slice 0 with weight 0, then SetPixel (CommandBuffer.cpp:75-226).
+// chain (-> level 0, min filter), clamp-to-edge, then SetPixel (CommandBuffer.cpp:75-226). This kernel replays that
+// arithmetic with the per-axis work factored out: everything SampleImageOfLevel (ImageSampler.cpp:461-579) derives from
+// one coordinate (texel index / second tap / lerp weight) depends only on the destination column or only on the
+// destination row, so a thread computes its column's terms once, the CTA computes its rows' terms once, and the inner
+// loop is just taps + lerps + pack. The z axis always lands on slice 0 twice with weight 0; since both z planes are
+// then the same bits, the reference's last lerp is lerp(v, v, 0) and is evaluated as exactly that.
+struct CpvkBlitAxis { int c0, c1; float t; int dst; };
+#define CPVK_BLIT_ROWS 32
+__device__ __forceinline__ CpvkBlitAxis cpvk_blit_axis(int i, int dst0, int dst1, int src0, int src1, cpvk_u32 srcSize, cpvk_u32 filter) {
+    CpvkBlitAxis r;
+    r.dst = dst1 < dst0 ? i + dst1 : i + dst0;
+    const float coordTexel = ((float)r.dst + 0.5f - (float)dst0) * ((float)(src1 - src0) / (float)(dst1 - dst0)) + (float)src0;
+    const float coord = coordTexel / (float)srcSize;
+    if (filter == 0) { // NEAREST: floor(u * size + shift), shift = 0
+        r.c0 = r.c1 = cpvk_wrap((cpvk_i32)floorf(coord * (float)srcSize + 0.0f), (cpvk_i32)srcSize, 2); r.t = 0.0f;
+    } else {
+        const float sc = coord * (float)srcSize - 0.5f;
+        const cpvk_i32 raw = (cpvk_i32)floorf(sc);
+        r.c1 = cpvk_wrap(raw + 1, (cpvk_i32)srcSize, 2); r.c0 = cpvk_wrap(raw, (cpvk_i32)srcSize, 2);
+        r.t = sc - floorf(sc);
+    }
+    return r;
+}
 __global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
     __shared__ float lut[256]; // (float)k / 255.0f by the IEEE divide itself: exact UNORM8 decode without a divide per channel
+    __shared__ CpvkBlitAxis rows[CPVK_BLIT_ROWS];
     lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
-    __syncthreads();
     const int dstW = abs(b.dstX1 - b.dstX0), dstH = abs(b.dstY1 - b.dstY0);
-    const bool negW = b.dstX1 < b.dstX0, negH = b.dstY1 < b.dstY0;
-    const cpvk_u64 total = (cpvk_u64)dstW * dstH;
-    const cpvk_u32 dtexel = cpvk_texel_size(b.dst.format);
-    CpvkDevDescriptor d; // register-resident view of the source
-    d.type = 2; d.format = b.src.format; d.dimensions = 3; d.levelCount = 1;
-    d.levels[0].address = b.src.address; d.levels[0].width = b.src.width; d.levels[0].height = b.src.height; d.levels[0].depth = 1;
-    d.sampler.addressModeU = d.sampler.addressModeV = d.sampler.addressModeW = 2; d.sampler.mipmapMode = 0; d.sampler.borderColor = 0;
-    for (cpvk_u64 i = (cpvk_u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (cpvk_u64)gridDim.x * blockDim.x) {
-        const int y = (int)(i / dstW), x = (int)(i - (cpvk_u64)y * dstW);
-        const int dstX = negW ? x + b.dstX1 : x + b.dstX0, dstY = negH ? y + b.dstY1 : y + b.dstY0;
-        const float u = ((float)dstX + 0.5f - (float)b.dstX0) * ((float)(b.srcX1 - b.srcX0) / (float)(b.dstX1 - b.dstX0)) + (float)b.srcX0;
-        const float v = ((float)dstY + 0.5f - (float)b.dstY0) * ((float)(b.srcY1 - b.srcY0) / (float)(b.dstY1 - b.dstY0)) + (float)b.srcY0;
-        const float w = (0.0f + 0.5f - 0.0f) * ((float)(1 - 0) / (float)(1 - 0)) + 0.0f;
-        const float coord[3] = {u / (float)b.src.width, v / (float)b.src.height, w / 1.0f};
-        const CpvkVec4 value = cpvk_sample_image(&d, 3, coord, 1.0f, b.filter, b.filter, lut);
-        if (dstX < 0 || dstY < 0 || (cpvk_u32)dstX >= b.dst.width || (cpvk_u32)dstY >= b.dst.height) continue;
-        cpvk_set_pixel_f32_dyn(b.dst.format, reinterpret_cast<cpvk_u8*>(b.dst.address) + (cpvk_u64)dstY * b.dst.rowPitch + (cpvk_u64)dstX * dtexel, value.v);
+    const cpvk_u32 stexel = cpvk_texel_size(b.src.format), dtexel = cpvk_texel_size(b.dst.format);
+    const cpvk_u64 spitch = (cpvk_u64)stexel * b.src.width; // the sampler addresses a level as tightly packed rows (Formats.cpp:583-587)
+    const cpvk_u8* src = reinterpret_cast<const cpvk_u8*>(b.src.address);
+    const CpvkFormat fi = cpvk_format(b.src.format);
+    const cpvk_u32 comps = fi.type == CPVK_FT_DEPTH ? 1u : fi.comps;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const bool colLive = x < dstW;
+    const CpvkBlitAxis cx = cpvk_blit_axis(colLive ? x : 0, b.dstX0, b.dstX1, b.srcX0, b.srcX1, b.src.width, b.filter);
+    // the z axis: one destination "slice" 0, source slices [0, 1) of a depth-1 image
+    const CpvkBlitAxis cz = cpvk_blit_axis(0, 0, 1, 0, 1, 1u, b.filter);
+    for (int rowBase = (int)blockIdx.y * CPVK_BLIT_ROWS; rowBase < dstH; rowBase += (int)gridDim.y * CPVK_BLIT_ROWS) {
+        __syncthreads();
+        if (threadIdx.x < CPVK_BLIT_ROWS && rowBase + (int)threadIdx.x < dstH)
+            rows[threadIdx.x] = cpvk_blit_axis(rowBase + (int)threadIdx.x, b.dstY0, b.dstY1, b.srcY0, b.srcY1, b.src.height, b.filter);
+        __syncthreads();
+        if (!colLive) continue;
+        const int nRows = min(CPVK_BLIT_ROWS, dstH - rowBase);
+        for (int r = 0; r < nRows; r++) {
+            const CpvkBlitAxis cy = rows[r];
+            CpvkVec4 value;
+            if (b.filter == 0) {
+                cpvk_get_pixel_f32_dyn(b.src.format, src + (cpvk_u64)(cpvk_u32)cy.c0 * spitch + (cpvk_u64)(cpvk_u32)cx.c0 * stexel, value.v, lut);
+            } else {
+                const cpvk_u8* r0 = src + (cpvk_u64)(cpvk_u32)cy.c0 * spitch;
+                const cpvk_u8* r1 = src + (cpvk_u64)(cpvk_u32)cy.c1 * spitch;
+                CpvkVec4 i0j0, i1j0, i0j1, i1j1;
+                cpvk_get_pixel_f32_dyn(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx.c0 * stexel, i0j0.v, lut);
+                cpvk_get_pixel_f32_dyn(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx.c1 * stexel, i1j0.v, lut);
+                cpvk_get_pixel_f32_dyn(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx.c0 * stexel, i0j1.v, lut);
+                cpvk_get_pixel_f32_dyn(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx.c1 * stexel, i1j1.v, lut);
+                const CpvkVec4 ij0 = cpvk_lerp(i0j0, i1j0, cx.t), ij1 = cpvk_lerp(i0j1, i1j1, cx.t);
+                const CpvkVec4 plane = cpvk_lerp(ij0, ij1, cy.t);
+                value = cpvk_lerp(plane, plane, cz.t); // the two z planes are the same slice
+            }
+            if (comps < 2) value.v[1] = 0.0f; // SampleImage (ImageSampler.cpp:581-673): absent channels read 0, 0, 1
+            if (comps < 3) value.v[2] = 0.0f;
+            if (comps < 4) value.v[3] = 1.0f;
+            if (cx.dst < 0 || cy.dst < 0 || (cpvk_u32)cx.dst >= b.dst.width || (cpvk_u32)cy.dst >= b.dst.height) continue;
+            cpvk_set_pixel_f32_dyn(b.dst.format, reinterpret_cast<cpvk_u8*>(b.dst.address) + (cpvk_u64)cy.dst * b.dst.rowPitch + (cpvk_u64)cx.dst * dtexel, value.v);
+        }
     }
 }
 
@@ -417,8 +462,9 @@ cudaError_t cpvk_launch_copy_rows(unsigned long long dst, unsigned dstPitch, uns
 cudaError_t cpvk_launch_blit(const CpvkBlitArgs* b, cudaStream_t s) {
     const unsigned long long total = (unsigned long long)abs(b->dstX1 - b->dstX0) * (unsigned long long)abs(b->dstY1 - b->dstY0);
     if (!total) return cudaSuccess;
-    unsigned grid = cpvk_grid(total, 256);
-    if (grid > 148 * 32) grid = 148 * 32;
+    const unsigned w = (unsigned)abs(b->dstX1 - b->dstX0), h = (unsigned)abs(b->dstY1 - b->dstY0);
+    dim3 grid(cpvk_grid(w, 256), cpvk_grid(h, CPVK_BLIT_ROWS));
+    if (grid.y > 65535u) grid.y = 65535u; // the kernel strides over row blocks
     k_blit<<<grid, 256, 0, s>>>(*b);
     return cudaGetLastError();
 }
