@@ -50,6 +50,7 @@ DECL(vkBindImageMemory, VkResult, VkDevice, VkImage, VkDeviceMemory, VkDeviceSiz
 DECL(vkGetImageSubresourceLayout, void, VkDevice, VkImage, const VkImageSubresource*, VkSubresourceLayout*)
 DECL(vkCreateImageView, VkResult, VkDevice, const VkImageViewCreateInfo*, const VkAllocationCallbacks*, VkImageView*)
 DECL(vkCreateSampler, VkResult, VkDevice, const VkSamplerCreateInfo*, const VkAllocationCallbacks*, VkSampler*)
+DECL(vkCreateBufferView, VkResult, VkDevice, const VkBufferViewCreateInfo*, const VkAllocationCallbacks*, VkBufferView*)
 DECL(vkCreateShaderModule, VkResult, VkDevice, const VkShaderModuleCreateInfo*, const VkAllocationCallbacks*, VkShaderModule*)
 DECL(vkCreateDescriptorSetLayout, VkResult, VkDevice, const VkDescriptorSetLayoutCreateInfo*, const VkAllocationCallbacks*, VkDescriptorSetLayout*)
 DECL(vkCreatePipelineLayout, VkResult, VkDevice, const VkPipelineLayoutCreateInfo*, const VkAllocationCallbacks*, VkPipelineLayout*)
@@ -102,7 +103,7 @@ static void LoadIcd() {
     GET(vkCreateInstance) GET(vkDestroyInstance) GET(vkEnumeratePhysicalDevices) GET(vkGetPhysicalDeviceProperties) GET(vkGetPhysicalDeviceMemoryProperties)
     GET(vkGetPhysicalDeviceQueueFamilyProperties) GET(vkCreateDevice) GET(vkDestroyDevice) GET(vkGetDeviceQueue) GET(vkAllocateMemory) GET(vkMapMemory) GET(vkUnmapMemory)
     GET(vkCreateBuffer) GET(vkGetBufferMemoryRequirements) GET(vkBindBufferMemory) GET(vkCreateImage) GET(vkGetImageMemoryRequirements) GET(vkBindImageMemory)
-    GET(vkGetImageSubresourceLayout) GET(vkCreateImageView) GET(vkCreateSampler) GET(vkCreateShaderModule) GET(vkCreateDescriptorSetLayout) GET(vkCreatePipelineLayout)
+    GET(vkGetImageSubresourceLayout) GET(vkCreateImageView) GET(vkCreateSampler) GET(vkCreateBufferView) GET(vkCreateShaderModule) GET(vkCreateDescriptorSetLayout) GET(vkCreatePipelineLayout)
     GET(vkCreateDescriptorPool) GET(vkAllocateDescriptorSets) GET(vkUpdateDescriptorSets) GET(vkCreateRenderPass) GET(vkCreateFramebuffer) GET(vkCreateGraphicsPipelines)
     GET(vkCreateCommandPool) GET(vkAllocateCommandBuffers) GET(vkBeginCommandBuffer) GET(vkEndCommandBuffer) GET(vkCmdBeginRenderPass) GET(vkCmdEndRenderPass)
     GET(vkCmdBindPipeline) GET(vkCmdBindDescriptorSets) GET(vkCmdBindVertexBuffers) GET(vkCmdBindIndexBuffer) GET(vkCmdSetViewport) GET(vkCmdSetScissor) GET(vkCmdDraw)
@@ -133,6 +134,7 @@ struct SceneDesc {
     std::string indexBuffer; uint32_t indexStride = 0;
     struct Uni { uint32_t set, binding; std::string name; }; std::vector<Uni> uniforms;
     struct Tex { uint32_t set, binding, format, w, h, filter, address; std::string file; }; std::vector<Tex> textures;
+    struct TexelBuf { uint32_t set, binding, format; std::string name; }; std::vector<TexelBuf> texelBuffers;
     uint32_t colorFormat = 0, width = 0, height = 0; float clearColor[4] = {};
     uint32_t depthFormat = 0; float clearDepth = 1; uint32_t clearStencil = 0;
     float viewport[6] = {};
@@ -157,6 +159,7 @@ static SceneDesc ParseScene(const std::string& dir) {
         else if (key == "vertex_buffer") { uint32_t b; std::string n; is >> b >> n; s.vertexBuffers[b] = n; }
         else if (key == "index_buffer") is >> s.indexBuffer >> s.indexStride;
         else if (key == "uniform") { SceneDesc::Uni u; is >> u.set >> u.binding >> u.name; s.uniforms.push_back(u); }
+        else if (key == "texel_buffer") { SceneDesc::TexelBuf t; is >> t.set >> t.binding >> t.name >> t.format; s.texelBuffers.push_back(t); }
         else if (key == "texture") { SceneDesc::Tex t; is >> t.set >> t.binding >> t.format >> t.w >> t.h >> t.filter >> t.address >> t.file; s.textures.push_back(t); }
         else if (key == "color") { is >> s.colorFormat >> s.width >> s.height; for (auto& c : s.clearColor) is >> c; }
         else if (key == "depth") is >> s.depthFormat >> s.clearDepth >> s.clearStencil;
@@ -226,7 +229,7 @@ int main(int argc, char** argv) {
     for (auto& kv : sc.buffers) {
         std::vector<uint8_t> data = ReadFile(sceneDir + "/" + kv.second.file);
         VkDeviceMemory mem;
-        VkBuffer b = app.MakeBuffer(data.size(), VK_BUFFER_USAGE_VERTEX_BUFFER_BIT | VK_BUFFER_USAGE_INDEX_BUFFER_BIT | VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT, &mem);
+        VkBuffer b = app.MakeBuffer(data.size(), VK_BUFFER_USAGE_VERTEX_BUFFER_BIT | VK_BUFFER_USAGE_INDEX_BUFFER_BIT | VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT | VK_BUFFER_USAGE_UNIFORM_TEXEL_BUFFER_BIT, &mem);
         void* p; VK(vkMapMemory(app.device, mem, 0, data.size(), 0, &p)); memcpy(p, data.data(), data.size()); vkUnmapMemory(app.device, mem);
         bufs[kv.first] = b; bufMem[kv.first] = mem; bufData[kv.first] = std::move(data);
     }
@@ -262,6 +265,7 @@ int main(int argc, char** argv) {
     std::vector<VkDescriptorSetLayoutBinding> lb;
     for (auto& u : sc.uniforms) lb.push_back({u.binding, VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
     for (auto& t : sc.textures) lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 1, VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
+    for (auto& t : sc.texelBuffers) lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
     VkDescriptorSetLayoutCreateInfo li{VK_STRUCTURE_TYPE_DESCRIPTOR_SET_LAYOUT_CREATE_INFO, nullptr, 0, (uint32_t)lb.size(), lb.data()};
     VkDescriptorSetLayout setLayout; VK(vkCreateDescriptorSetLayout(app.device, &li, nullptr, &setLayout));
     VkPipelineLayoutCreateInfo pli{VK_STRUCTURE_TYPE_PIPELINE_LAYOUT_CREATE_INFO, nullptr, 0, 1, &setLayout, 0, nullptr};
@@ -280,8 +284,8 @@ int main(int argc, char** argv) {
     VkFramebufferCreateInfo fbi{VK_STRUCTURE_TYPE_FRAMEBUFFER_CREATE_INFO, nullptr, 0, renderPass, (uint32_t)atts.size(), fbViews, sc.width, sc.height, 1};
     VkFramebuffer framebuffer; VK(vkCreateFramebuffer(app.device, &fbi, nullptr, &framebuffer));
     // init_descriptor_pool / init_descriptor_set
-    VkDescriptorPoolSize ps[2] = {{VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 8}, {VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 8}};
-    VkDescriptorPoolCreateInfo dpi{VK_STRUCTURE_TYPE_DESCRIPTOR_POOL_CREATE_INFO, nullptr, 0, 1, 2, ps};
+    VkDescriptorPoolSize ps[3] = {{VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 8}, {VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 8}, {VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, 8}};
+    VkDescriptorPoolCreateInfo dpi{VK_STRUCTURE_TYPE_DESCRIPTOR_POOL_CREATE_INFO, nullptr, 0, 1, 3, ps};
     VkDescriptorPool dpool; VK(vkCreateDescriptorPool(app.device, &dpi, nullptr, &dpool));
     VkDescriptorSetAllocateInfo dsa{VK_STRUCTURE_TYPE_DESCRIPTOR_SET_ALLOCATE_INFO, nullptr, dpool, 1, &setLayout};
     VkDescriptorSet dset; VK(vkAllocateDescriptorSets(app.device, &dsa, &dset));
@@ -293,6 +297,13 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < sc.textures.size(); i++) {
         iinfos[i] = {texObjs[i].sampler, texObjs[i].view, VK_IMAGE_LAYOUT_SHADER_READ_ONLY_OPTIMAL};
         writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, sc.textures[i].binding, 0, 1, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, &iinfos[i], nullptr, nullptr});
+    }
+    // texel_buffer.cpp:146-158, :226-236: a buffer view over the whole buffer bound as UNIFORM_TEXEL_BUFFER
+    std::vector<VkBufferView> bufferViews(sc.texelBuffers.size());
+    for (size_t i = 0; i < sc.texelBuffers.size(); i++) {
+        VkBufferViewCreateInfo bvi{VK_STRUCTURE_TYPE_BUFFER_VIEW_CREATE_INFO, nullptr, 0, bufs.at(sc.texelBuffers[i].name), (VkFormat)sc.texelBuffers[i].format, 0, sc.buffers.at(sc.texelBuffers[i].name).size};
+        VK(vkCreateBufferView(app.device, &bvi, nullptr, &bufferViews[i]));
+        writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, sc.texelBuffers[i].binding, 0, 1, VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, nullptr, nullptr, &bufferViews[i]});
     }
     vkUpdateDescriptorSets(app.device, (uint32_t)writes.size(), writes.data(), 0, nullptr);
     // init_shaders (SPIR-V words exported by Python; the samples run glslang here) + init_pipeline

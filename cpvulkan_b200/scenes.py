@@ -81,6 +81,7 @@ class Scene:
         self.index_buffer, self.index_stride = None, 0
         self.uniforms = []                       # (set, binding, buffer name)
         self.textures = []                       # Texture
+        self.texel_buffers = []                  # (set, binding, buffer name, format)
         self.color = None                        # Image
         self.depth = None                        # Image or None
         self.viewport = None                     # (x, y, w, h, minDepth, maxDepth)
@@ -165,6 +166,11 @@ def materialize(scene, alloc):
         sm.magFilter = sm.minFilter = t.filter
         sm.addressModeU = sm.addressModeV = sm.addressModeW = t.address
         sm.minLod, sm.maxLod = 0.0, 0.0
+        nd += 1
+    for set_, binding, name, fmt in scene.texel_buffers:
+        ds = s.descriptors[nd]
+        ds.set, ds.binding, ds.type = set_, binding, capi.DESC_TEXEL_BUFFER
+        ds.address, ds.range, ds.format = m.addr[name], scene.buffers[name].nbytes, fmt
         nd += 1
     s.descriptorCount = nd
     pc = scene.push_constants
@@ -397,6 +403,21 @@ def overdraw_quads(width=7680, height=4320, quads=2000, tex_size=1024, seed=42, 
     return s
 
 
+def texel_buffer(width=500, height=500, texels=(1.0, 0.0, 1.0), triangles=1):
+    """Samples/texel_buffer (BASELINE C5, third item): a uniform texel buffer view of three R32_SFLOAT texels fetched in
+    the vertex shader, one triangle from a private array indexed by gl_VertexIndex % 3, no vertex buffers, no depth
+    (texel_buffer.cpp:35-62, :71, :286). `triangles` > 1 repeats the same triangle (vertex index modulo 3)."""
+    s = Scene("texel_buffer_%dx%d" % (width, height))
+    s.vs, s.fs = "texelbuf.vert", "cube.frag"
+    s.buffers["texels"] = np.array(texels, dtype=np.float32).view(np.uint8).reshape(-1)
+    s.texel_buffers = [(0, 0, "texels", R32_SFLOAT)]
+    s.topology = TRIANGLE_LIST
+    s.count = 3 * triangles
+    s.cull, s.front_face = CULL_NONE, FRONT_CW
+    _render_targets(s, width, height, B8G8R8A8_UNORM, None, (0.2, 0.2, 0.2, 0.2))
+    return s
+
+
 def random_triangles(width=256, height=192, tris=200, seed=1, depth_fmt=D32_SFLOAT, color_fmt=R8G8B8A8_UNORM,
                      cull=CULL_NONE, front_face=FRONT_CCW, perspective=True, depth_op=LESS_OR_EQUAL,
                      topology=TRIANGLE_LIST, indexed=None, snap=False):
@@ -469,6 +490,8 @@ def export_scene(scene, directory):
         lines.append("index_buffer %s %d" % (scene.index_buffer, scene.index_stride))
     for set_, binding, name in scene.uniforms:
         lines.append("uniform %d %d %s" % (set_, binding, name))
+    for set_, binding, name, fmt in scene.texel_buffers:
+        lines.append("texel_buffer %d %d %s %d" % (set_, binding, name, fmt))
     for t in scene.textures:
         fn = "tex_%d.bin" % t.binding
         np.ascontiguousarray(t.image.data).tofile(os.path.join(directory, fn))

@@ -40,3 +40,8 @@ def test_icd_frame_loop_rewrites_and_reads_mapped_memory(built, tmp_path):
     # several frames: vertex data rewritten through a mapping each frame, result read through a persistent mapping
     info = check(scenes.draw_cube(200, 120), tmp_path, frames=5)
     assert info["frames"] == 5
+
+
+def test_icd_texel_buffer_sample(built, tmp_path):
+    # Samples/texel_buffer: vkCreateBufferView + UNIFORM_TEXEL_BUFFER descriptor, texelFetch in the vertex shader
+    check(scenes.texel_buffer(200, 120), tmp_path)

@@ -199,3 +199,24 @@ def test_speculative_plan_replays(built):
         compare(d, seq[1])
     finally:
         d.close()
+
+
+def test_texel_buffer_sample(dev):
+    """BASELINE C5, third item (Samples/texel_buffer): texelFetch from a uniform texel buffer in the vertex shader, a
+    private array indexed by gl_VertexIndex % 3, no vertex buffers."""
+    st = compare(dev, scenes.texel_buffer(500, 500), check_depth=False)
+    assert st.primitives == 1 and st.fragmentsCovered > 50000
+    compare(dev, scenes.texel_buffer(96, 64, texels=(0.25, 0.5, 0.75), triangles=3), check_depth=False)
+
+
+def test_texel_buffer_8k_property(dev):
+    """The same draw at 7680x4320 (too large for the oracle): every pixel is either the clear colour or the fetched
+    colour, the covered count equals the device's own statistic, and the triangle is left-right symmetric."""
+    scene = scenes.texel_buffer(7680, 4320)
+    gc, _, st = run_cuda(dev, scene)
+    img = gc.view(np.uint32).reshape(4320, 7680)
+    clear, tri = np.uint32(0x33333333), np.uint32(0xFFFF00FF)  # BGRA8: (0.2,0.2,0.2,0.2) and (1,0,1,1)
+    inside = img == tri
+    assert np.all(inside | (img == clear))
+    assert int(inside.sum()) == st.fragmentsCovered == st.fragmentsWritten
+    assert abs(int(inside[:, :3840].sum()) - int(inside[:, 3840:].sum())) <= 4320
