@@ -9,7 +9,9 @@
 // driven by a scene description exported by cpvulkan_b200/scenes.py so tests can render the very same inputs with
 // the CPU oracle and byte-compare. Off-screen: the "swapchain image" is an ordinary colour image (Image.cpp:17-21).
 //
-//   cpvk_harness <scene dir> <out dir> [--frames K]
+//   cpvk_harness <scene dir> <out dir> [--frames K] [--blit W H FORMAT FILTER]
+//   --blit: after the render pass, vkCmdBlitImage the colour image to a W x H image of FORMAT (copy_blit_image.cpp:146-190),
+//   vkCmdCopyImage that to a second image (:192-222) and read the copy back as blit.bin
 #include <dlfcn.h>
 
 #include <chrono>
@@ -75,6 +77,8 @@ DECL(vkCmdSetScissor, void, VkCommandBuffer, uint32_t, uint32_t, const VkRect2D*
 DECL(vkCmdDraw, void, VkCommandBuffer, uint32_t, uint32_t, uint32_t, uint32_t)
 DECL(vkCmdDrawIndexed, void, VkCommandBuffer, uint32_t, uint32_t, uint32_t, int32_t, uint32_t)
 DECL(vkCmdCopyImageToBuffer, void, VkCommandBuffer, VkImage, VkImageLayout, VkBuffer, uint32_t, const VkBufferImageCopy*)
+DECL(vkCmdBlitImage, void, VkCommandBuffer, VkImage, VkImageLayout, VkImage, VkImageLayout, uint32_t, const VkImageBlit*, VkFilter)
+DECL(vkCmdCopyImage, void, VkCommandBuffer, VkImage, VkImageLayout, VkImage, VkImageLayout, uint32_t, const VkImageCopy*)
 DECL(vkCreateFence, VkResult, VkDevice, const VkFenceCreateInfo*, const VkAllocationCallbacks*, VkFence*)
 DECL(vkResetFences, VkResult, VkDevice, uint32_t, const VkFence*)
 DECL(vkWaitForFences, VkResult, VkDevice, uint32_t, const VkFence*, VkBool32, uint64_t)
@@ -107,7 +111,7 @@ static void LoadIcd() {
     GET(vkCreateDescriptorPool) GET(vkAllocateDescriptorSets) GET(vkUpdateDescriptorSets) GET(vkCreateRenderPass) GET(vkCreateFramebuffer) GET(vkCreateGraphicsPipelines)
     GET(vkCreateCommandPool) GET(vkAllocateCommandBuffers) GET(vkBeginCommandBuffer) GET(vkEndCommandBuffer) GET(vkCmdBeginRenderPass) GET(vkCmdEndRenderPass)
     GET(vkCmdBindPipeline) GET(vkCmdBindDescriptorSets) GET(vkCmdBindVertexBuffers) GET(vkCmdBindIndexBuffer) GET(vkCmdSetViewport) GET(vkCmdSetScissor) GET(vkCmdDraw)
-    GET(vkCmdDrawIndexed) GET(vkCmdCopyImageToBuffer) GET(vkCreateFence) GET(vkResetFences) GET(vkWaitForFences) GET(vkQueueSubmit) GET(vkDeviceWaitIdle)
+    GET(vkCmdDrawIndexed) GET(vkCmdCopyImageToBuffer) GET(vkCmdBlitImage) GET(vkCmdCopyImage) GET(vkCreateFence) GET(vkResetFences) GET(vkWaitForFences) GET(vkQueueSubmit) GET(vkDeviceWaitIdle)
 }
 
 static std::vector<uint8_t> ReadFile(const std::string& p) {
@@ -202,6 +206,8 @@ int main(int argc, char** argv) {
     const std::string sceneDir = argv[1], outDir = argv[2];
     int frames = 1;
     for (int i = 3; i + 1 < argc; i++) if (!strcmp(argv[i], "--frames")) frames = atoi(argv[i + 1]);
+    uint32_t blitW = 0, blitH = 0, blitFormat = 0, blitFilter = 0;
+    for (int i = 3; i + 4 < argc; i++) if (!strcmp(argv[i], "--blit")) { blitW = (uint32_t)atoi(argv[i + 1]); blitH = (uint32_t)atoi(argv[i + 2]); blitFormat = (uint32_t)atoi(argv[i + 3]); blitFilter = (uint32_t)atoi(argv[i + 4]); }
     LoadIcd();
     const SceneDesc sc = ParseScene(sceneDir);
     App app{};
@@ -358,6 +364,20 @@ int main(int argc, char** argv) {
     VkBufferImageCopy cp{0, 0, 0, {VK_IMAGE_ASPECT_COLOR_BIT, 0, 0, 1}, {0, 0, 0}, {sc.width, sc.height, 1}};
     vkCmdCopyImageToBuffer(app.cmd, colorImg, VK_IMAGE_LAYOUT_TRANSFER_SRC_OPTIMAL, rb, 1, &cp);
     if (depthBytes) { cp.imageSubresource.aspectMask = VK_IMAGE_ASPECT_DEPTH_BIT; vkCmdCopyImageToBuffer(app.cmd, depthImg, VK_IMAGE_LAYOUT_TRANSFER_SRC_OPTIMAL, rbDepth, 1, &cp); }
+    VkBuffer rbBlit = VK_NULL_HANDLE; VkDeviceMemory rbBlitMem = VK_NULL_HANDLE; uint64_t blitBytes = 0;
+    if (blitW) {
+        VkDeviceMemory m1, m2;
+        VkImage blitImg = app.MakeImage(blitFormat, blitW, blitH, VK_IMAGE_USAGE_TRANSFER_DST_BIT | VK_IMAGE_USAGE_TRANSFER_SRC_BIT, VK_IMAGE_TILING_OPTIMAL, &m1);
+        VkImage copyImg = app.MakeImage(blitFormat, blitW, blitH, VK_IMAGE_USAGE_TRANSFER_DST_BIT | VK_IMAGE_USAGE_TRANSFER_SRC_BIT, VK_IMAGE_TILING_LINEAR, &m2);
+        VkImageBlit region{{VK_IMAGE_ASPECT_COLOR_BIT, 0, 0, 1}, {{0, 0, 0}, {(int32_t)sc.width, (int32_t)sc.height, 1}}, {VK_IMAGE_ASPECT_COLOR_BIT, 0, 0, 1}, {{0, 0, 0}, {(int32_t)blitW, (int32_t)blitH, 1}}};
+        vkCmdBlitImage(app.cmd, colorImg, VK_IMAGE_LAYOUT_TRANSFER_SRC_OPTIMAL, blitImg, VK_IMAGE_LAYOUT_TRANSFER_DST_OPTIMAL, 1, &region, (VkFilter)blitFilter);
+        VkImageCopy copy{{VK_IMAGE_ASPECT_COLOR_BIT, 0, 0, 1}, {0, 0, 0}, {VK_IMAGE_ASPECT_COLOR_BIT, 0, 0, 1}, {0, 0, 0}, {blitW, blitH, 1}};
+        vkCmdCopyImage(app.cmd, blitImg, VK_IMAGE_LAYOUT_TRANSFER_SRC_OPTIMAL, copyImg, VK_IMAGE_LAYOUT_TRANSFER_DST_OPTIMAL, 1, &copy);
+        blitBytes = (uint64_t)TexelSize(blitFormat) * blitW * blitH;
+        rbBlit = app.MakeBuffer(blitBytes, VK_BUFFER_USAGE_TRANSFER_DST_BIT, &rbBlitMem);
+        VkBufferImageCopy bc{0, 0, 0, {VK_IMAGE_ASPECT_COLOR_BIT, 0, 0, 1}, {0, 0, 0}, {blitW, blitH, 1}};
+        vkCmdCopyImageToBuffer(app.cmd, copyImg, VK_IMAGE_LAYOUT_TRANSFER_SRC_OPTIMAL, rbBlit, 1, &bc);
+    }
     VK(vkEndCommandBuffer(app.cmd));
 
     VkFenceCreateInfo fi{VK_STRUCTURE_TYPE_FENCE_CREATE_INFO, nullptr, 0};
@@ -383,6 +403,10 @@ int main(int argc, char** argv) {
     if (depthBytes) {
         uint8_t* p; VK(vkMapMemory(app.device, rbDepthMem, 0, depthBytes, 0, (void**)&p));
         std::ofstream o(outDir + "/depth.bin", std::ios::binary); o.write((const char*)p, (std::streamsize)depthBytes);
+    }
+    if (blitBytes) {
+        uint8_t* p; VK(vkMapMemory(app.device, rbBlitMem, 0, blitBytes, 0, (void**)&p));
+        std::ofstream o(outDir + "/blit.bin", std::ios::binary); o.write((const char*)p, (std::streamsize)blitBytes);
     }
     double sum = 0, best = 1e30; const size_t skip = frameMs.size() > 3 ? 3 : 0;
     for (size_t i = skip; i < frameMs.size(); i++) { sum += frameMs[i]; if (frameMs[i] < best) best = frameMs[i]; }

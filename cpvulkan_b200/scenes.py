@@ -508,7 +508,7 @@ def export_scene(scene, directory):
         f.write("\n".join(lines) + "\n")
 
 
-def run_icd(scene, workdir, frames=1, env=None):
+def run_icd(scene, workdir, frames=1, env=None, blit=None):
     """Render `scene` through the Vulkan ICD (manifest -> vk_icd* -> vkCmdDraw* -> vkQueueSubmit) with the
     loader-harness. Returns (color bytes, depth bytes or None, harness JSON dict)."""
     import json
@@ -521,11 +521,14 @@ def run_icd(scene, workdir, frames=1, env=None):
     e["VK_ICD_FILENAMES"] = os.path.join(icd_dir, "CPVulkan_b200.json")
     if env:
         e.update(env)
-    out = subprocess.run([os.path.join(icd_dir, "cpvk_harness"), scene_dir, out_dir, "--frames", str(frames)], env=e, check=True,
+    extra = ["--blit"] + [str(v) for v in blit] if blit else []  # (width, height, format, filter): see cpvk_harness.cpp
+    out = subprocess.run([os.path.join(icd_dir, "cpvk_harness"), scene_dir, out_dir, "--frames", str(frames)] + extra, env=e, check=True,
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     info = json.loads(out.stdout.strip().splitlines()[-1])
     color = np.fromfile(os.path.join(out_dir, "color.bin"), dtype=np.uint8)
     depth = np.fromfile(os.path.join(out_dir, "depth.bin"), dtype=np.uint8) if scene.depth else None
+    if blit:
+        info["blit"] = np.fromfile(os.path.join(out_dir, "blit.bin"), dtype=np.uint8)
     return color, depth, info
 
 

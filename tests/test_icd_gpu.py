@@ -45,3 +45,23 @@ def test_icd_frame_loop_rewrites_and_reads_mapped_memory(built, tmp_path):
 def test_icd_texel_buffer_sample(built, tmp_path):
     # Samples/texel_buffer: vkCreateBufferView + UNIFORM_TEXEL_BUFFER descriptor, texelFetch in the vertex shader
     check(scenes.texel_buffer(200, 120), tmp_path)
+
+
+@pytest.mark.parametrize("w,h,fmt,filt", [(150, 90, 37, 0), (300, 200, 97, 1), (64, 64, 44, 1)])
+def test_icd_blit_and_copy_after_the_render_pass(built, tmp_path, w, h, fmt, filt):
+    """Samples/copy_blit_image through the ICD: vkCmdBlitImage (scaling + format conversion) of the rendered image,
+    vkCmdCopyImage of the result, vkCmdCopyImageToBuffer readback — against the oracle's blit of the oracle's frame."""
+    import ctypes as C
+    from cpvulkan_b200 import capi
+    scene = scenes.draw_cube(200, 120)
+    oc, _, _ = scenes.run_oracle(scene)
+    gc, _, info = scenes.run_icd(scene, str(tmp_path), blit=(w, h, fmt, filt))
+    assert np.array_equal(oc, gc)
+    lib = capi.load_oracle()
+    texel = {37: 4, 44: 4, 97: 8}[fmt]
+    src = np.ascontiguousarray(oc)
+    dst = np.zeros(w * h * texel, dtype=np.uint8)
+    b = capi.Blit(capi.Attachment(src.ctypes.data, 200, 120, 200 * 4, scene.color.format), capi.Attachment(dst.ctypes.data, w, h, w * texel, fmt),
+                  0, 0, 200, 120, 0, 0, w, h, filt)
+    assert lib.cpvk_oracle_blit(C.byref(b)) == 0
+    assert np.array_equal(info["blit"], dst)
