@@ -287,6 +287,9 @@ def run_ours(args):
             e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
             e2e = {"value": prims / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                    "through": "C ABI (cpvk_cuda_mem_upload / clear / draw / mem_download) with pinned host buffers"}
+        extras = None
+        if world == 1 and not args.no_extras:
+            extras = secondary_configs(dev, torch)
         cpu = None
         if world == 1 and not args.no_cpu:
             build.build_oracle()
@@ -302,21 +305,87 @@ def run_ours(args):
             "config": {"workload": "C3/M1: 1,000,000-triangle indexed grid, 3840x2160 RGBA8+D32, LESS_OR_EQUAL, opaque; step = clear + draw" +
                                    (" + NCCL all-gather of %d bands" % world if world > 1 else ""),
                        "parallelism": "sort-first bands x%d" % world,
-                       "l2": "working set (indices 12 MB + vertices 16 MB + VS records 120 MB + setup 104 MB + targets 66 MB) exceeds the 126 MB L2; no explicit flush"},
+                       "l2": "working set (indices 12 MB + vertices 16 MB + shaded vertices 16 MB + setup records 104 MB + tile lists 5 MB + targets 66 MB) exceeds the 126 MB L2; no explicit flush"},
             "gfragments_per_s": n_cov / (ms_step * 1e-3) / 1e9, "ms_per_frame": ms_step,
             "fragments_covered": n_cov, "fragments_written": n_pass, "bin_entries_rank0": bin_entries,
             "kernel_ms_rank0": {"vertex": statistics.mean(vs), "setup": statistics.mean(su), "bin": statistics.mean(bn), "raster": ms_raster},
             "roofline": {"bound": "hbm", "kernel": "cpvk_k_raster", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "traffic": raster_traffic(),
                          "note": "front end of C3/M1 is instruction-bound (8 px/triangle); see DESIGN.md"},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
         }
+        if extras:
+            line["other_configs"] = extras
     sod.close()
     dev.close()
     if world > 1:
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def raster_traffic():
+    """DRAM bytes of one cpvk_k_raster launch from the committed `ncu --set full` capture (never measured inside a bench run)."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "raster_traffic.json")) as f:
+            t = json.load(f)
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def secondary_configs(dev, torch):
+    """Short measurements of the other BASELINE configs on the same device (reduced so the default run stays short):
+    C4 = blended, LINEAR-filtered full-screen quads at 7680x4320 RGBA16F (40 of the 2,000 quads);
+    C5 = vkCmdBlitImage / vkCmdCopyImage at 7680x4320. CUDA events on the launching stream, inputs resident."""
+    from cpvulkan_b200 import capi
+    from cpvulkan_b200.device import SceneOnDevice
+    peak, _ = measured_peaks()
+    out = {}
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    quads = 40
+    sc = scenes.overdraw_quads(width=7680, height=4320, quads=quads, tex_size=1024)
+    s = SceneOnDevice(dev, sc)
+    dev.set_stats(True)
+    s.render()
+    frags = int(dev.stats().fragmentsCovered)
+    dev.set_stats(False)
+    ms = timed(s.render, 3)
+    out["C4_overdraw"] = {"workload": "%d of the 2,000 alpha-blended LINEAR-textured full-screen quads, 7680x4320 RGBA16F; step = clear + draw" % quads,
+                          "ms_per_step": ms, "gfragments_per_s": frags / (ms * 1e-3) / 1e9, "mtris_per_s": 2 * quads / (ms * 1e-3) / 1e6,
+                          "roofline_frac": frags * 16 / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_fragment": 16}
+    s.close()
+
+    W, H = 7680, 4320
+
+    def image(fmt, w, h, texel):
+        t = torch.randint(0, 255, (w * h * texel,), dtype=torch.uint8, device="cuda")
+        return t, capi.Attachment(t.data_ptr(), w, h, w * texel, fmt)
+
+    s8, a8 = image(37, W, H, 4)
+    d16, a16 = image(97, W, H, 8)
+    s4, a4 = image(37, W // 2, H // 2, 4)
+    d8, _ = image(37, W, H, 4)
+    b1 = capi.Blit(a8, a16, 0, 0, W, H, 0, 0, W, H, 0)
+    b2 = capi.Blit(a4, a16, 0, 0, W // 2, H // 2, 0, 0, W, H, 1)
+    for key, fn, nbytes in (("blit_8k_rgba8_to_rgba16f_nearest", lambda: dev.blit(b1), W * H * 12),
+                            ("blit_4k_to_8k_rgba16f_linear", lambda: dev.blit(b2), W * H * 8 + W * H),
+                            ("copy_image_8k_rgba8", lambda: dev.copy_rows(d8.data_ptr(), W * 4, s8.data_ptr(), W * 4, W * 4, H), W * H * 8)):
+        ms = timed(fn, 5)
+        out["C5_" + key] = {"ms": ms, "GBps": nbytes / ms / 1e6, "roofline_frac": nbytes / ms / 1e6 / peak, "algorithmic_bytes": nbytes}
+    return out
 
 
 def main():
@@ -326,6 +395,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short C4 / C5 measurements reported under other_configs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
