@@ -164,8 +164,17 @@ def run_ours(args):
     rows = HEIGHT // world
     band = (rank * rows, (rank + 1) * rows) if world > 1 else None
 
-    # colour attachment owned by torch so NCCL can gather the bands in place
-    color_t = torch.zeros(scene.color.nbytes, dtype=torch.uint8, device="cuda")
+    # Colour attachment owned by torch. Multi-GPU: peer-mapped (symmetric memory) so that k_raster can store every
+    # finished tile of this rank's band straight into the other GPUs' frames over NVLink — the gather of SURVEY §8(e)
+    # fused into rasterisation; `--gather nccl` keeps the frame private and all-gathers the bands afterwards.
+    symm = None
+    if world > 1 and args.gather == "fused":
+        import torch.distributed._symmetric_memory as symm_mem
+        color_t = symm_mem.empty(scene.color.nbytes, dtype=torch.uint8, device=torch.device("cuda", local))
+        color_t.zero_()
+        symm = symm_mem.rendezvous(color_t, dist.group.WORLD)
+    else:
+        color_t = torch.zeros(scene.color.nbytes, dtype=torch.uint8, device="cuda")
 
     class Placed(SceneOnDevice):
         pass
@@ -188,11 +197,18 @@ def run_ours(args):
     if band:
         sod.m.state.bandY0, sod.m.state.bandY1 = band
     band_bytes = rows * scene.color.pitch
+    if symm is not None:
+        peers = [int(p) for i, p in enumerate(symm.buffer_ptrs) if i != rank]
+        sod.m.state.mirrorCount = len(peers)
+        for i, ptr in enumerate(peers):
+            sod.m.state.mirrorColor0[i] = ptr
 
     def frame():
         sod.clear(band_only=world > 1)
         sod.draw()
-        if world > 1:
+        if symm is not None:
+            symm.barrier()  # every GPU's tiles have landed in every frame before anyone reads or redraws
+        elif world > 1:
             dist.all_gather_into_tensor(color_t, color_t[rank * band_bytes:(rank + 1) * band_bytes])
 
     def barrier():
@@ -205,6 +221,24 @@ def run_ours(args):
     barrier()
     st = dev.stats()
     n_cov, n_pass = int(st.fragmentsCovered), int(st.fragmentsWritten)
+    if world > 1:
+        # every rank must now hold the same, complete frame (cheap integrity check of the exchange, outside the timed region)
+        digest = torch.stack([color_t.view(torch.int32).to(torch.int64).sum(), (color_t.view(torch.int32)[::4097].to(torch.int64) * 31).sum()])
+        all_digests = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(all_digests, digest)
+        if any(not torch.equal(all_digests[0], x) for x in all_digests):
+            raise SystemExit("ranks disagree on the gathered frame")
+        # ... and that frame must be, byte for byte, what one GPU renders without bands
+        whole = torch.zeros_like(color_t)
+        saved = (sod.m.state.bandY0, sod.m.state.bandY1, sod.m.state.mirrorCount, sod.m.state.color[0].address, sod.m.color_attachment.address)
+        sod.m.state.bandY0 = sod.m.state.bandY1 = 0
+        sod.m.state.mirrorCount = 0
+        sod.m.state.color[0].address = sod.m.color_attachment.address = whole.data_ptr()
+        sod.clear(); sod.draw(); dev.sync()
+        sod.m.state.bandY0, sod.m.state.bandY1, sod.m.state.mirrorCount, sod.m.state.color[0].address, sod.m.color_attachment.address = saved
+        if not torch.equal(whole, color_t):
+            raise SystemExit("the gathered frame differs from the single-GPU frame")
+        del whole
     if world > 1:
         t = torch.tensor([n_cov, n_pass], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
@@ -303,7 +337,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C3/M1: 1,000,000-triangle indexed grid, 3840x2160 RGBA8+D32, LESS_OR_EQUAL, opaque; step = clear + draw" +
-                                   (" + NCCL all-gather of %d bands" % world if world > 1 else ""),
+                                   ((" + bands stored into the peers' frames by k_raster over NVLink (fused gather) + barrier" if symm is not None else " + NCCL all-gather of %d bands" % world) if world > 1 else ""),
                        "parallelism": "sort-first bands x%d" % world,
                        "l2": "working set (indices 12 MB + vertices 16 MB + shaded vertices 16 MB + setup records 104 MB + tile lists 5 MB + targets 66 MB) exceeds the 126 MB L2; no explicit flush"},
             "gfragments_per_s": n_cov / (ms_step * 1e-3) / 1e9, "ms_per_frame": ms_step,
@@ -395,6 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU exchange: peer stores from k_raster (default) or an NCCL all-gather after the draw")
     ap.add_argument("--no-extras", action="store_true", help="skip the short C4 / C5 measurements reported under other_configs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -102,6 +102,9 @@ class Descriptor(C.Structure):
                 ("levels", MipLevel * MAX_MIP_LEVELS), ("sampler", Sampler)]
 
 
+MAX_MIRRORS = 7
+
+
 class DrawState(C.Structure):
     _fields_ = [
         ("pipeline", C.c_void_p), ("viewport", Viewport),
@@ -112,6 +115,7 @@ class DrawState(C.Structure):
         ("pushConstantSize", u32), ("pushConstants", C.c_uint8 * MAX_PUSH_CONSTANT_BYTES),
         ("color", Attachment * MAX_COLOR_ATTACHMENTS), ("depthStencil", Attachment),
         ("bandY0", u32), ("bandY1", u32),
+        ("mirrorCount", u32), ("mirrorPad", u32), ("mirrorColor0", u64 * MAX_MIRRORS),
     ]
 
 

@@ -190,9 +190,10 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     const bool listsSorted = p.binMeta[1] > CPVK_CHUNK;
     const cpvk_u32 listBegin = p.tileOffsets[tile], listEnd = p.tileOffsets[tile + 1];
     const cpvk_u32 lazyMask = p.lazyMask;
-    if (listBegin == listEnd && lazyMask == 0) return;
     const cpvk_u32 ty = tile / p.tilesX, tx = tile - ty * p.tilesX;
     const int tileX0 = (int)tx * CPVK_TILE_W, tileY0 = (int)ty * CPVK_TILE_H;
+    // nothing to draw and no clear to fold: done — unless mirrors are on, then even untouched tiles of the band travel
+    if (listBegin == listEnd && lazyMask == 0 && !(p.mirrorCount != 0 && tileY0 + CPVK_TILE_H > p.clipY0)) return;
 
     const cpvk_u32 dsFormat = cpvk_spec_u32(CPVK_SPEC_DS_FORMAT);
     const bool depthTest = cpvk_spec_u32(CPVK_SPEC_DEPTH_TEST) != 0, depthWrite = cpvk_spec_u32(CPVK_SPEC_DEPTH_WRITE) != 0;
@@ -608,6 +609,14 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
         if (sColor[a])
             cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.color[a].address) + (cpvk_u64)tileY0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a], p.color[a].rowPitch,
                            sColor[a], cTexel[a] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th);
+    // ---- the fused gather: the band's rows of this tile go to every peer's copy of colour attachment 0 ----
+    if (p.mirrorCount && sColor[0]) {
+        const int my0 = max(tileY0, p.clipY0);
+        if (my0 < y1)
+            for (cpvk_u32 m = 0; m < p.mirrorCount; m++)
+                cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.mirror[m]) + (cpvk_u64)my0 * p.color[0].rowPitch + (cpvk_u64)tileX0 * cTexel[0], p.color[0].rowPitch,
+                               sColor[0] + (cpvk_u32)(my0 - tileY0) * cTexel[0] * CPVK_TILE_W, cTexel[0] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[0], (cpvk_u32)(y1 - my0));
+    }
     if (p.stats && lane == 0 && (nCov | nPass)) {
         atomicAdd(p.stats + 0, (cpvk_u64)nCov);
         atomicAdd(p.stats + 1, (cpvk_u64)nPass);

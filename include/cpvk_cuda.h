@@ -40,6 +40,7 @@ extern "C" {
 #define CPVK_MAX_VERTEX_ATTRIBUTES 16
 #define CPVK_MAX_COLOR_ATTACHMENTS 8  /* MAX_FRAGMENT_OUTPUT_ATTACHMENTS, CPVulkanBase/Config.h:144  */
 #define CPVK_MAX_DESCRIPTORS 16
+#define CPVK_MAX_MIRRORS 7 /* the other GPUs of one 8-GPU box */
 #define CPVK_MAX_MIP_LEVELS 13        /* MAX_MIP_LEVELS = clog2(4096), CPVulkanBase/Formats.h:105-115 */
 #define CPVK_MAX_PUSH_CONSTANT_BYTES 128
 #define CPVK_MAX_SPEC_ENTRIES 16
@@ -203,6 +204,13 @@ typedef struct CpvkDrawState {
 
     /* Sort-first band owned by this GPU: rows [bandY0, bandY1). 0,0 = whole target. */
     uint32_t bandY0, bandY1;
+    /* Gather fused into rasterisation: device addresses of the other GPUs' copies of color[0] (peer-mapped over
+       NVLink, same layout as color[0]). Every finished tile of this GPU's band is stored into each of them as well,
+       so the exchange of §8(e) overlaps the raster kernel tile by tile and no collective follows the draw; the caller
+       only orders the GPUs with a barrier before anyone reads a frame. 0 = off (gather the bands afterwards). */
+    uint32_t mirrorCount;
+    uint32_t mirrorPad;
+    uint64_t mirrorColor0[CPVK_MAX_MIRRORS];
 } CpvkDrawState;
 
 typedef struct CpvkDrawStats {

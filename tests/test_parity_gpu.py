@@ -220,3 +220,31 @@ def test_texel_buffer_8k_property(dev):
     assert np.all(inside | (img == clear))
     assert int(inside.sum()) == st.fragmentsCovered == st.fragmentsWritten
     assert abs(int(inside[:, :3840].sum()) - int(inside[:, 3840:].sum())) <= 4320
+
+
+def test_mirror_stores_copy_the_band(dev):
+    """CpvkDrawState.mirrorColor0 (the multi-GPU gather fused into k_raster): every tile row of the band is also stored
+    at the same offset of each mirror allocation — here two more buffers on the same GPU stand in for the peers."""
+    from cpvulkan_b200.device import SceneOnDevice
+    scene = scenes.random_triangles(width=96, height=96, tris=200, seed=61)
+    band = (37, 70)
+    s = SceneOnDevice(dev, scene, band)
+    mirrors = [dev.alloc(scene.color.nbytes) for _ in range(2)]
+    try:
+        for m in mirrors:
+            dev.upload(m, np.full(scene.color.nbytes, 0xAB, dtype=np.uint8))
+        s.m.state.mirrorCount = 2
+        for i, m in enumerate(mirrors):
+            s.m.state.mirrorColor0[i] = m
+        s.render()
+        own = s.read_color().reshape(96, -1)
+        oc, _, _ = scenes.run_oracle(scene, window=(0, band[0], 96, band[1]))
+        assert np.array_equal(own.reshape(-1), oc)
+        for m in mirrors:
+            got = dev.download(m, scene.color.nbytes).reshape(96, -1)
+            assert np.array_equal(got[band[0]:band[1]], own[band[0]:band[1]]), "band rows must arrive in the mirror"
+            assert np.all(got[:band[0]] == 0xAB) and np.all(got[band[1]:] == 0xAB), "rows outside the band belong to other GPUs"
+    finally:
+        for m in mirrors:
+            dev.free(m)
+        s.close()
