@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
         s.z[k] = P[k][2]; s.pw[k] = P[k][3]; s.idx[k] = idx[k];
     }
     s.area = area; s.flags = front ? 1u : 0u; s.provoking = prov;
-    {
+    // A primitive that is culled or outside the render area (this GPU's band) is never listed by a tile, so its record
+    // is never read: a warp whose 32 primitives are all like that skips the 3 KB store. With N bands that is most warps.
+    const bool listed = valid && !culled && endX > startX && endY > startY;
+    if (__any_sync(0xFFFFFFFFu, listed)) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const uint4* sv = reinterpret_cast<const uint4*>(&s);
         #pragma unroll
