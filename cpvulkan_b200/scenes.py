@@ -34,7 +34,8 @@ BF_ZERO, BF_ONE, BF_SRC_COLOR, BF_ONE_MINUS_SRC_COLOR, BF_DST_COLOR, BF_ONE_MINU
 BO_ADD, BO_SUBTRACT, BO_REVERSE_SUBTRACT, BO_MIN, BO_MAX = range(5)
 
 TEXEL_SIZE = {R8G8B8A8_UNORM: 4, B8G8R8A8_UNORM: 4, R16G16B16A16_SFLOAT: 8, D16_UNORM: 2, D32_SFLOAT: 4,
-              D24_UNORM_S8_UINT: 4, R32_SFLOAT: 4, R32G32B32A32_SFLOAT: 16}
+              D24_UNORM_S8_UINT: 4, R32_SFLOAT: 4, R32G32B32A32_SFLOAT: 16,
+              125: 4, 127: 1, 128: 3, 130: 8}  # X8_D24_UNORM_PACK32, S8_UINT, D16_UNORM_S8_UINT, D32_SFLOAT_S8_UINT
 
 _shader_cache = {}
 
@@ -87,6 +88,7 @@ class Scene:
         self.viewport = None                     # (x, y, w, h, minDepth, maxDepth)
         self.count, self.instances, self.first, self.vertex_offset, self.first_instance = 0, 1, 0, 0, 0
         self.push_constants = b""
+        self.mutate = None                       # optional callable(Materialized): last-minute edits of the PODs, applied on every backend
 
 
 class Materialized:
@@ -183,10 +185,15 @@ def materialize(scene, alloc):
     m.color_attachment = capi.Attachment(caddr, scene.color.width, scene.color.height, scene.color.pitch, scene.color.format)
     s.color[0] = m.color_attachment
     if scene.depth:
-        daddr = alloc("depth", scene.depth.nbytes, scene.depth.data)
+        ddata = scene.depth.data
+        if ddata is None and scene.depth.format == 130:  # D32_SFLOAT_S8_UINT has 3 bytes per texel nothing ever writes: start them at 0 on every backend
+            ddata = np.zeros(scene.depth.nbytes, dtype=np.uint8)
+        daddr = alloc("depth", scene.depth.nbytes, ddata)
         m.addr["depth"] = daddr
         m.depth_attachment = capi.Attachment(daddr, scene.depth.width, scene.depth.height, scene.depth.pitch, scene.depth.format)
         s.depthStencil = m.depth_attachment
+    if scene.mutate:
+        scene.mutate(m)
     return m
 
 

@@ -248,3 +248,111 @@ def test_mirror_stores_copy_the_band(dev):
         for m in mirrors:
             dev.free(m)
         s.close()
+
+
+# ---- fixed-function state outside C1-C5 (§8(f) f4): same bar, bit-exact ----
+
+def _with(scene, fn):
+    scene.mutate = fn
+    return scene
+
+
+STENCIL_OPS = [  # (fail, pass, depthFail, compare, compareMask, writeMask, reference)
+    (0, 2, 0, 7, 0xFF, 0xFF, 0x40),   # ALWAYS / REPLACE
+    (0, 3, 4, 1, 0xFF, 0xFF, 0x01),   # LESS, INCREMENT_AND_CLAMP on pass, DECREMENT_AND_CLAMP on depth fail (signed-saturate quirk)
+    (5, 6, 7, 3, 0x0F, 0xF0, 0x05),   # LESS_OR_EQUAL with masks, INVERT / INC_WRAP / DEC_WRAP
+    (1, 0, 2, 5, 0xFF, 0x3C, 0x80),   # NOT_EQUAL, ZERO on fail, REPLACE on depth fail, partial write mask
+    (2, 2, 2, 0, 0xFF, 0xFF, 0x7F),   # NEVER: only the fail op runs
+]
+
+
+@pytest.mark.parametrize("ops", STENCIL_OPS)
+@pytest.mark.parametrize("fmt", [scenes.D24_UNORM_S8_UINT, 130, 128])
+def test_stencil(dev, ops, fmt):
+    def edit(m):
+        m.desc.stencilTestEnable = 1
+        for st in (m.desc.front, m.desc.back):
+            st.failOp, st.passOp, st.depthFailOp, st.compareOp, st.compareMask, st.writeMask, st.reference = ops
+        m.desc.back.reference = (ops[6] + 3) & 0xFF
+        m.desc.back.compareOp = (ops[3] + 1) % 8
+    sc = scenes.random_triangles(width=96, height=64, tris=250, seed=71, depth_fmt=fmt)
+    sc.depth.clear = ("depth", (1.0, 0x10))
+    compare(dev, _with(sc, edit))
+
+
+def test_stencil_only_attachment(dev):
+    def edit(m):
+        m.desc.stencilTestEnable = 1
+        m.desc.depthTestEnable = m.desc.depthWriteEnable = 0
+        for st in (m.desc.front, m.desc.back):
+            st.failOp, st.passOp, st.depthFailOp, st.compareOp, st.compareMask, st.writeMask, st.reference = (0, 6, 0, 4, 0xFF, 0xFF, 2)
+    sc = scenes.random_triangles(width=64, height=64, tris=200, seed=72, depth_fmt=127)
+    sc.depth.clear = ("depth", (0.0, 0))
+    compare(dev, _with(sc, edit))
+
+
+@pytest.mark.parametrize("bounds", [(0.2, 0.7), (0.0, 0.0), (0.9, 0.1)])
+def test_depth_bounds(dev, bounds):
+    def edit(m):
+        m.desc.depthBoundsTestEnable = 1
+        m.desc.minDepthBounds, m.desc.maxDepthBounds = bounds
+    sc = scenes.random_triangles(width=96, height=64, tris=250, seed=73)
+    sc.depth.clear = ("depth", (0.5, 0))
+    compare(dev, _with(sc, edit))
+
+
+@pytest.mark.parametrize("depth_range", [(0.0, 1.0), (0.25, 0.75), (1.0, 0.0)])
+def test_viewport_depth_range(dev, depth_range):
+    sc = scenes.random_triangles(width=80, height=60, tris=200, seed=74)
+    sc.viewport = (0.0, 0.0, 80.0, 60.0, depth_range[0], depth_range[1])
+    compare(dev, sc)
+
+
+def test_viewport_larger_than_the_attachment(dev):
+    sc = scenes.random_triangles(width=80, height=60, tris=200, seed=75)
+    sc.viewport = (0.0, 0.0, 128.0, 100.0, 0.0, 1.0)
+    # The reference has no clamp: fragments beyond 80x60 are written out of bounds (undefined behaviour).
+    # The CUDA path drops them, which is the oracle restricted to the attachment's window.
+    oc, od, ost = scenes.run_oracle(sc, window=(0, 0, 80, 60))
+    gc, gd, gst = run_cuda(dev, sc)
+    assert gst.fragmentsCovered == ost.fragmentsCovered and gst.fragmentsWritten == ost.fragmentsWritten
+    assert np.array_equal(oc, gc) and np.array_equal(od, gd)
+
+
+BLENDS = [dict(src=1, dst=1, op=0), dict(src=6, dst=7, op=1), dict(src=4, dst=2, op=2, srcA=1, dstA=0, opA=0), dict(src=14, dst=1, op=0),
+          dict(src=10, dst=11, op=0, srcA=12, dstA=13, opA=0), dict(src=1, dst=1, op=3), dict(src=1, dst=1, op=4, srcA=6, dstA=7, opA=0),
+          dict(src=8, dst=9, op=0), dict(src=3, dst=5, op=0)]
+
+
+@pytest.mark.parametrize("blend", BLENDS, ids=lambda b: "-".join(str(v) for v in b.values()))
+@pytest.mark.parametrize("fmt", [scenes.R8G8B8A8_UNORM, scenes.R16G16B16A16_SFLOAT, scenes.R32G32B32A32_SFLOAT])
+def test_blend_factors_and_ops(dev, blend, fmt):
+    def edit(m):
+        for i, c in enumerate((0.25, 0.5, 0.75, 0.6)):
+            m.desc.blendConstants[i] = c
+    sc = scenes.random_triangles(width=64, height=48, tris=150, seed=76, color_fmt=fmt, depth_fmt=None)
+    sc.blend = blend
+    compare(dev, _with(sc, edit))
+
+
+@pytest.mark.parametrize("mask", [0x1, 0x6, 0x8, 0x0])
+@pytest.mark.parametrize("blend", [None, dict(src=6, dst=7, op=0)])
+def test_colour_write_mask(dev, mask, blend):
+    sc = scenes.random_triangles(width=64, height=48, tris=150, seed=77)
+    sc.write_mask, sc.blend = mask, blend
+    compare(dev, sc)
+
+
+def test_instanced_draw_with_instance_rate_attribute(dev):
+    """instanceCount > 1, firstInstance, and a per-instance colour fetched with VK_VERTEX_INPUT_RATE_INSTANCE."""
+    sc = scenes.random_triangles(width=96, height=64, tris=40, seed=78)
+    n_inst, first = 3, 2
+    inst_colors = np.random.RandomState(5).random_sample((n_inst + first, 4)).astype(np.float32)
+    sc.buffers["inst"] = inst_colors.view(np.uint8).reshape(-1)
+    sc.bindings = [(0, 32, 0), (1, 16, 1)]
+    sc.attributes = [(0, 0, scenes.R32G32B32A32_SFLOAT, 0), (1, 1, scenes.R32G32B32A32_SFLOAT, 0)]
+    sc.vertex_buffers = {0: "vb", 1: "inst"}
+    sc.instances, sc.first_instance = n_inst, first
+    sc.depth_op = scenes.ALWAYS  # every instance overwrites the previous one: the last instance's colour must win
+    st = compare(dev, sc)
+    assert st.primitives == 40 * n_inst
