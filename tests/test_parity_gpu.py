@@ -356,3 +356,21 @@ def test_instanced_draw_with_instance_rate_attribute(dev):
     sc.depth_op = scenes.ALWAYS  # every instance overwrites the previous one: the last instance's colour must win
     st = compare(dev, sc)
     assert st.primitives == 40 * n_inst
+
+
+@pytest.mark.parametrize("iterations,threshold,scale", [(4, 0.9, None), (0, 0.5, None), (9, 100.0, 1.25), (3, -1.0, 0.0)])
+def test_shader_front_end_breadth(dev, iterations, threshold, scale):
+    """a fragment shader with a phi-based loop with break, a called function, OpKill, a push-constant
+    block, a specialisation constant, bit operations and GLSL.std.450 calls — translator (CUDA) vs interpreter (oracle)."""
+    import struct
+
+    def edit(m):
+        if scale is not None:
+            m.desc.fragment.specCount = 1
+            m.desc.fragment.spec[0].constantId = 3
+            m.desc.fragment.spec[0].value = struct.unpack("<I", struct.pack("<f", scale))[0]
+    sc = scenes.random_triangles(width=64, height=48, tris=120, seed=81)
+    sc.fs = "complex.frag"
+    sc.push_constants = struct.pack("<4fif", 0.3, 0.1, 0.2, 0.05, iterations, threshold)
+    st = compare(dev, _with(sc, edit))
+    assert st.fragmentsCovered > 1000
