@@ -10,6 +10,10 @@
 // the CPU oracle and byte-compare. Off-screen: the "swapchain image" is an ordinary colour image (Image.cpp:17-21).
 //
 //   cpvk_harness <scene dir> <out dir> [--frames K] [--blit W H FORMAT FILTER]
+//   [--indirect] draw through vkCmdDraw[Indexed]Indirect (parameters written through a mapping, slot 1 of a 3-slot buffer)
+//   [--secondary] record the bind + draw commands into a secondary command buffer and vkCmdExecuteCommands it
+//   [--update-buffers] fill the uniform buffers with vkCmdFillBuffer(0) + vkCmdUpdateBuffer instead of a mapping
+//   [--clear-rect X Y W H] vkCmdClearAttachments of that rectangle (colour 0.5,0.25,0.75,1 / depth 0.5) after the draw
 //   --blit: after the render pass, vkCmdBlitImage the colour image to a W x H image of FORMAT (copy_blit_image.cpp:146-190),
 //   vkCmdCopyImage that to a second image (:192-222) and read the copy back as blit.bin
 #include <dlfcn.h>
@@ -77,6 +81,12 @@ DECL(vkCmdSetScissor, void, VkCommandBuffer, uint32_t, uint32_t, const VkRect2D*
 DECL(vkCmdDraw, void, VkCommandBuffer, uint32_t, uint32_t, uint32_t, uint32_t)
 DECL(vkCmdDrawIndexed, void, VkCommandBuffer, uint32_t, uint32_t, uint32_t, int32_t, uint32_t)
 DECL(vkCmdCopyImageToBuffer, void, VkCommandBuffer, VkImage, VkImageLayout, VkBuffer, uint32_t, const VkBufferImageCopy*)
+DECL(vkCmdDrawIndirect, void, VkCommandBuffer, VkBuffer, VkDeviceSize, uint32_t, uint32_t)
+DECL(vkCmdDrawIndexedIndirect, void, VkCommandBuffer, VkBuffer, VkDeviceSize, uint32_t, uint32_t)
+DECL(vkCmdExecuteCommands, void, VkCommandBuffer, uint32_t, const VkCommandBuffer*)
+DECL(vkCmdUpdateBuffer, void, VkCommandBuffer, VkBuffer, VkDeviceSize, VkDeviceSize, const void*)
+DECL(vkCmdFillBuffer, void, VkCommandBuffer, VkBuffer, VkDeviceSize, VkDeviceSize, uint32_t)
+DECL(vkCmdClearAttachments, void, VkCommandBuffer, uint32_t, const VkClearAttachment*, uint32_t, const VkClearRect*)
 DECL(vkCmdBlitImage, void, VkCommandBuffer, VkImage, VkImageLayout, VkImage, VkImageLayout, uint32_t, const VkImageBlit*, VkFilter)
 DECL(vkCmdCopyImage, void, VkCommandBuffer, VkImage, VkImageLayout, VkImage, VkImageLayout, uint32_t, const VkImageCopy*)
 DECL(vkCreateFence, VkResult, VkDevice, const VkFenceCreateInfo*, const VkAllocationCallbacks*, VkFence*)
@@ -111,7 +121,7 @@ static void LoadIcd() {
     GET(vkCreateDescriptorPool) GET(vkAllocateDescriptorSets) GET(vkUpdateDescriptorSets) GET(vkCreateRenderPass) GET(vkCreateFramebuffer) GET(vkCreateGraphicsPipelines)
     GET(vkCreateCommandPool) GET(vkAllocateCommandBuffers) GET(vkBeginCommandBuffer) GET(vkEndCommandBuffer) GET(vkCmdBeginRenderPass) GET(vkCmdEndRenderPass)
     GET(vkCmdBindPipeline) GET(vkCmdBindDescriptorSets) GET(vkCmdBindVertexBuffers) GET(vkCmdBindIndexBuffer) GET(vkCmdSetViewport) GET(vkCmdSetScissor) GET(vkCmdDraw)
-    GET(vkCmdDrawIndexed) GET(vkCmdCopyImageToBuffer) GET(vkCmdBlitImage) GET(vkCmdCopyImage) GET(vkCreateFence) GET(vkResetFences) GET(vkWaitForFences) GET(vkQueueSubmit) GET(vkDeviceWaitIdle)
+    GET(vkCmdDrawIndexed) GET(vkCmdCopyImageToBuffer) GET(vkCmdBlitImage) GET(vkCmdCopyImage) GET(vkCmdDrawIndirect) GET(vkCmdDrawIndexedIndirect) GET(vkCmdExecuteCommands) GET(vkCmdUpdateBuffer) GET(vkCmdFillBuffer) GET(vkCmdClearAttachments) GET(vkCreateFence) GET(vkResetFences) GET(vkWaitForFences) GET(vkQueueSubmit) GET(vkDeviceWaitIdle)
 }
 
 static std::vector<uint8_t> ReadFile(const std::string& p) {
@@ -206,6 +216,13 @@ int main(int argc, char** argv) {
     const std::string sceneDir = argv[1], outDir = argv[2];
     int frames = 1;
     for (int i = 3; i + 1 < argc; i++) if (!strcmp(argv[i], "--frames")) frames = atoi(argv[i + 1]);
+    bool indirect = false, secondary = false, updateBuffers = false; int clearRect[4] = {0, 0, 0, 0};
+    for (int i = 3; i < argc; i++) {
+        if (!strcmp(argv[i], "--indirect")) indirect = true;
+        if (!strcmp(argv[i], "--secondary")) secondary = true;
+        if (!strcmp(argv[i], "--update-buffers")) updateBuffers = true;
+        if (!strcmp(argv[i], "--clear-rect") && i + 4 < argc) for (int k = 0; k < 4; k++) clearRect[k] = atoi(argv[i + 1 + k]);
+    }
     uint32_t blitW = 0, blitH = 0, blitFormat = 0, blitFilter = 0;
     for (int i = 3; i + 4 < argc; i++) if (!strcmp(argv[i], "--blit")) { blitW = (uint32_t)atoi(argv[i + 1]); blitH = (uint32_t)atoi(argv[i + 2]); blitFormat = (uint32_t)atoi(argv[i + 3]); blitFilter = (uint32_t)atoi(argv[i + 4]); }
     LoadIcd();
@@ -235,8 +252,9 @@ int main(int argc, char** argv) {
     for (auto& kv : sc.buffers) {
         std::vector<uint8_t> data = ReadFile(sceneDir + "/" + kv.second.file);
         VkDeviceMemory mem;
-        VkBuffer b = app.MakeBuffer(data.size(), VK_BUFFER_USAGE_VERTEX_BUFFER_BIT | VK_BUFFER_USAGE_INDEX_BUFFER_BIT | VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT | VK_BUFFER_USAGE_UNIFORM_TEXEL_BUFFER_BIT, &mem);
-        void* p; VK(vkMapMemory(app.device, mem, 0, data.size(), 0, &p)); memcpy(p, data.data(), data.size()); vkUnmapMemory(app.device, mem);
+        VkBuffer b = app.MakeBuffer(data.size(), VK_BUFFER_USAGE_VERTEX_BUFFER_BIT | VK_BUFFER_USAGE_INDEX_BUFFER_BIT | VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT | VK_BUFFER_USAGE_UNIFORM_TEXEL_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT, &mem);
+        bool isUniform = false; for (auto& u : sc.uniforms) if (u.name == kv.first) isUniform = true;
+        if (!(updateBuffers && isUniform)) { void* p; VK(vkMapMemory(app.device, mem, 0, data.size(), 0, &p)); memcpy(p, data.data(), data.size()); vkUnmapMemory(app.device, mem); }
         bufs[kv.first] = b; bufMem[kv.first] = mem; bufData[kv.first] = std::move(data);
     }
     // init_texture: linear image written through vkGetImageSubresourceLayout + map (util_init.cpp:1783-1799)
@@ -347,19 +365,54 @@ int main(int argc, char** argv) {
     // record: the 15-draw_cube command sequence (15-draw_cube.cpp:100-160)
     VkCommandBufferBeginInfo bi{VK_STRUCTURE_TYPE_COMMAND_BUFFER_BEGIN_INFO, nullptr, 0, nullptr};
     VK(vkBeginCommandBuffer(app.cmd, &bi));
+    if (updateBuffers) // vkCmdFillBuffer + vkCmdUpdateBuffer outside the render pass (CommandBuffer.cpp:241-330)
+        for (auto& u : sc.uniforms) {
+            const auto& data = bufData.at(u.name);
+            vkCmdFillBuffer(app.cmd, bufs.at(u.name), 0, VK_WHOLE_SIZE, 0xDEADBEEFu);
+            vkCmdUpdateBuffer(app.cmd, bufs.at(u.name), 0, data.size(), data.data());
+        }
+    // indirect parameters: slot 1 of three (offset = stride = 32), the other slots hold garbage that must not be read
+    VkBuffer indirectBuf = VK_NULL_HANDLE; VkDeviceMemory indirectMem = VK_NULL_HANDLE;
+    if (indirect) {
+        indirectBuf = app.MakeBuffer(96, VK_BUFFER_USAGE_INDIRECT_BUFFER_BIT, &indirectMem);
+        uint32_t* w; VK(vkMapMemory(app.device, indirectMem, 0, 96, 0, (void**)&w));
+        for (int i = 0; i < 24; i++) w[i] = 0x7FFFFFFFu;
+        if (sc.indexStride) { w[8] = sc.count; w[9] = sc.instances; w[10] = sc.first; w[11] = (uint32_t)sc.vertexOffset; w[12] = sc.firstInstance; }
+        else { w[8] = sc.count; w[9] = sc.instances; w[10] = sc.first; w[11] = sc.firstInstance; }
+        vkUnmapMemory(app.device, indirectMem);
+    }
     VkClearValue clears[2]; memcpy(clears[0].color.float32, sc.clearColor, 16); clears[1].depthStencil = {sc.clearDepth, sc.clearStencil};
     VkRenderPassBeginInfo rbi{VK_STRUCTURE_TYPE_RENDER_PASS_BEGIN_INFO, nullptr, renderPass, framebuffer, {{0, 0}, {sc.width, sc.height}}, (uint32_t)atts.size(), clears};
-    vkCmdBeginRenderPass(app.cmd, &rbi, VK_SUBPASS_CONTENTS_INLINE);
-    vkCmdBindPipeline(app.cmd, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeline);
-    vkCmdBindDescriptorSets(app.cmd, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeLayout, 0, 1, &dset, 0, nullptr);
-    for (auto& kv : sc.vertexBuffers) { VkDeviceSize off = 0; VkBuffer b = bufs.at(kv.second); vkCmdBindVertexBuffers(app.cmd, kv.first, 1, &b, &off); }
+    vkCmdBeginRenderPass(app.cmd, &rbi, secondary ? VK_SUBPASS_CONTENTS_SECONDARY_COMMAND_BUFFERS : VK_SUBPASS_CONTENTS_INLINE);
+    VkCommandBuffer rec = app.cmd;
+    if (secondary) { // vkCmdExecuteCommands (CommandBuffer.cpp:704-731): the draw lives in a secondary command buffer
+        VkCommandBufferAllocateInfo sbi{VK_STRUCTURE_TYPE_COMMAND_BUFFER_ALLOCATE_INFO, nullptr, app.pool, VK_COMMAND_BUFFER_LEVEL_SECONDARY, 1};
+        VK(vkAllocateCommandBuffers(app.device, &sbi, &rec));
+        VkCommandBufferInheritanceInfo inh{VK_STRUCTURE_TYPE_COMMAND_BUFFER_INHERITANCE_INFO, nullptr, renderPass, 0, framebuffer, VK_FALSE, 0, 0};
+        VkCommandBufferBeginInfo sbeg{VK_STRUCTURE_TYPE_COMMAND_BUFFER_BEGIN_INFO, nullptr, 0x2 /* VK_COMMAND_BUFFER_USAGE_RENDER_PASS_CONTINUE_BIT */, &inh};
+        VK(vkBeginCommandBuffer(rec, &sbeg));
+    }
+    vkCmdBindPipeline(rec, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeline);
+    vkCmdBindDescriptorSets(rec, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeLayout, 0, 1, &dset, 0, nullptr);
+    for (auto& kv : sc.vertexBuffers) { VkDeviceSize off = 0; VkBuffer b = bufs.at(kv.second); vkCmdBindVertexBuffers(rec, kv.first, 1, &b, &off); }
     VkViewport vp{sc.viewport[0], sc.viewport[1], sc.viewport[2], sc.viewport[3], sc.viewport[4], sc.viewport[5]};
-    vkCmdSetViewport(app.cmd, 0, 1, &vp);
-    VkRect2D scissor{{0, 0}, {sc.width, sc.height}}; vkCmdSetScissor(app.cmd, 0, 1, &scissor);
+    vkCmdSetViewport(rec, 0, 1, &vp);
+    VkRect2D scissor{{0, 0}, {sc.width, sc.height}}; vkCmdSetScissor(rec, 0, 1, &scissor);
     if (sc.indexStride) {
-        vkCmdBindIndexBuffer(app.cmd, bufs.at(sc.indexBuffer), 0, sc.indexStride == 2 ? VK_INDEX_TYPE_UINT16 : sc.indexStride == 4 ? VK_INDEX_TYPE_UINT32 : VK_INDEX_TYPE_UINT8_EXT);
-        vkCmdDrawIndexed(app.cmd, sc.count, sc.instances, sc.first, sc.vertexOffset, sc.firstInstance);
-    } else vkCmdDraw(app.cmd, sc.count, sc.instances, sc.first, sc.firstInstance);
+        vkCmdBindIndexBuffer(rec, bufs.at(sc.indexBuffer), 0, sc.indexStride == 2 ? VK_INDEX_TYPE_UINT16 : sc.indexStride == 4 ? VK_INDEX_TYPE_UINT32 : VK_INDEX_TYPE_UINT8_EXT);
+        if (indirect) vkCmdDrawIndexedIndirect(rec, indirectBuf, 32, 1, 32);
+        else vkCmdDrawIndexed(rec, sc.count, sc.instances, sc.first, sc.vertexOffset, sc.firstInstance);
+    } else if (indirect) vkCmdDrawIndirect(rec, indirectBuf, 32, 1, 32);
+    else vkCmdDraw(rec, sc.count, sc.instances, sc.first, sc.firstInstance);
+    if (clearRect[2] > 0) { // vkCmdClearAttachments (Draw.cpp:2226-2348) after the draw, inside the pass
+        VkClearAttachment ca[2]; uint32_t nca = 1;
+        ca[0].aspectMask = VK_IMAGE_ASPECT_COLOR_BIT; ca[0].colorAttachment = 0;
+        ca[0].clearValue.color.float32[0] = 0.5f; ca[0].clearValue.color.float32[1] = 0.25f; ca[0].clearValue.color.float32[2] = 0.75f; ca[0].clearValue.color.float32[3] = 1.0f;
+        if (sc.depthFormat) { ca[1].aspectMask = VK_IMAGE_ASPECT_DEPTH_BIT | VK_IMAGE_ASPECT_STENCIL_BIT; ca[1].colorAttachment = 0; ca[1].clearValue.depthStencil = {0.5f, 0}; nca = 2; }
+        VkClearRect cr{{{clearRect[0], clearRect[1]}, {(uint32_t)clearRect[2], (uint32_t)clearRect[3]}}, 0, 1};
+        vkCmdClearAttachments(rec, nca, ca, 1, &cr);
+    }
+    if (secondary) { VK(vkEndCommandBuffer(rec)); vkCmdExecuteCommands(app.cmd, 1, &rec); }
     vkCmdEndRenderPass(app.cmd);
     VkBufferImageCopy cp{0, 0, 0, {VK_IMAGE_ASPECT_COLOR_BIT, 0, 0, 1}, {0, 0, 0}, {sc.width, sc.height, 1}};
     vkCmdCopyImageToBuffer(app.cmd, colorImg, VK_IMAGE_LAYOUT_TRANSFER_SRC_OPTIMAL, rb, 1, &cp);

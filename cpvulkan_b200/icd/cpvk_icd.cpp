@@ -658,6 +658,47 @@ VKFN(void) CmdDraw(VkCommandBuffer cb, uint32_t vertexCount, uint32_t instanceCo
 VKFN(void) CmdDrawIndexed(VkCommandBuffer cb, uint32_t indexCount, uint32_t instanceCount, uint32_t firstIndex, int32_t vertexOffset, uint32_t firstInstance) {
     RECORD(cb)([=](Device& d) { ExecDraw(d, indexCount, instanceCount, firstIndex, vertexOffset, firstInstance, true); });
 }
+// Indirect draws (Draw.cpp:1874-1996): the parameters are read from the buffer when the command executes.
+VKFN(void) CmdDrawIndirect(VkCommandBuffer cb, VkBuffer buffer, VkDeviceSize offset, uint32_t drawCount, uint32_t stride) {
+    auto* b = reinterpret_cast<Buffer*>(buffer);
+    RECORD(cb)([=](Device& d) {
+        for (uint32_t j = 0; j < drawCount; j++) {
+            VkDrawIndirectCommand c;
+            CU_CHECK(cpvk_cuda_mem_download(d.cuda, &c, b->address(offset + (VkDeviceSize)j * stride), sizeof c));
+            ExecDraw(d, c.vertexCount, c.instanceCount, c.firstVertex, 0, c.firstInstance, false);
+        }
+    });
+}
+VKFN(void) CmdDrawIndexedIndirect(VkCommandBuffer cb, VkBuffer buffer, VkDeviceSize offset, uint32_t drawCount, uint32_t stride) {
+    auto* b = reinterpret_cast<Buffer*>(buffer);
+    RECORD(cb)([=](Device& d) {
+        for (uint32_t j = 0; j < drawCount; j++) {
+            VkDrawIndexedIndirectCommand c;
+            CU_CHECK(cpvk_cuda_mem_download(d.cuda, &c, b->address(offset + (VkDeviceSize)j * stride), sizeof c));
+            ExecDraw(d, c.indexCount, c.instanceCount, c.firstIndex, c.vertexOffset, c.firstInstance, true);
+        }
+    });
+}
+// Secondary command buffers (CommandBuffer.cpp:704-731): their commands run in place, on the same device state.
+VKFN(void) CmdExecuteCommands(VkCommandBuffer cb, uint32_t n, const VkCommandBuffer* buffers) {
+    std::vector<CommandBuffer*> v; for (uint32_t i = 0; i < n; i++) v.push_back(Unwrap<CommandBuffer>(buffers[i]));
+    RECORD(cb)([v](Device& d) { for (CommandBuffer* c : v) for (Command& k : c->commands) k(d); });
+}
+VKFN(void) CmdFillBuffer(VkCommandBuffer cb, VkBuffer dst, VkDeviceSize offset, VkDeviceSize size, uint32_t data) { // CommandBuffer.cpp:278-330: 32-bit words
+    auto* t = reinterpret_cast<Buffer*>(dst);
+    RECORD(cb)([=](Device& d) {
+        const VkDeviceSize bytes = size == VK_WHOLE_SIZE ? t->size - offset : size;
+        CpvkAttachment a{t->address(offset), (uint32_t)(bytes / 4), 1, (uint32_t)(bytes & ~(VkDeviceSize)3), 98 /* R32_UINT */};
+        CpvkClearValue cv{}; cv.uint32[0] = data;
+        if (a.width) CU_CHECK(cpvk_cuda_clear(d.cuda, &a, &cv, 0));
+        TouchedByGpu(t->mem);
+    });
+}
+VKFN(void) CmdUpdateBuffer(VkCommandBuffer cb, VkBuffer dst, VkDeviceSize offset, VkDeviceSize size, const void* data) { // CommandBuffer.cpp:241-276: data captured at record time
+    auto* t = reinterpret_cast<Buffer*>(dst);
+    std::vector<uint8_t> v(static_cast<const uint8_t*>(data), static_cast<const uint8_t*>(data) + size);
+    RECORD(cb)([t, offset, v](Device& d) { CU_CHECK(cpvk_cuda_mem_upload(d.cuda, t->address(offset), v.data(), v.size())); CU_CHECK(cpvk_cuda_sync(d.cuda)); TouchedByGpu(t->mem); });
+}
 VKFN(void) CmdPipelineBarrier(VkCommandBuffer, VkPipelineStageFlags, VkPipelineStageFlags, VkDependencyFlags, uint32_t, const VkMemoryBarrier*, uint32_t, const VkBufferMemoryBarrier*, uint32_t, const VkImageMemoryBarrier*) {} // no-op (F13)
 
 // transfer path: raw row copies and the blit
@@ -733,6 +774,52 @@ VKFN(void) CmdClearColorImage(VkCommandBuffer cb, VkImage image, VkImageLayout, 
     });
 }
 
+VKFN(void) CmdClearDepthStencilImage(VkCommandBuffer cb, VkImage image, VkImageLayout, const VkClearDepthStencilValue* value, uint32_t n, const VkImageSubresourceRange* ranges) { // Draw.cpp:2102-2224
+    auto* img = reinterpret_cast<Image*>(image); CpvkClearValue cv{}; cv.depthStencil.depth = value->depth; cv.depthStencil.stencil = value->stencil;
+    std::vector<VkImageSubresourceRange> r(ranges, ranges + n);
+    RECORD(cb)([img, cv, r](Device& d) {
+        for (auto& rg : r) {
+            const uint32_t f = (uint32_t)img->format;
+            const VkImageAspectFlags all = (f == 127 ? 0u : (uint32_t)VK_IMAGE_ASPECT_DEPTH_BIT) | (f >= 127 && f <= 130 ? (uint32_t)VK_IMAGE_ASPECT_STENCIL_BIT : 0u);
+            if ((rg.aspectMask & all) != all) Fatal("clearing one aspect of a combined depth/stencil image is not built");
+            const uint32_t levels = rg.levelCount == VK_REMAINING_MIP_LEVELS ? img->mipLevels - rg.baseMipLevel : rg.levelCount;
+            const uint32_t layers = rg.layerCount == VK_REMAINING_ARRAY_LAYERS ? img->arrayLayers - rg.baseArrayLayer : rg.layerCount;
+            for (uint32_t la = 0; la < layers; la++) for (uint32_t le = 0; le < levels; le++) {
+                const MipInfo& m = img->levels[rg.baseMipLevel + le];
+                CpvkAttachment a{img->address(rg.baseMipLevel + le, rg.baseArrayLayer + la), m.width, m.height * m.depth, (uint32_t)m.stride, f};
+                CU_CHECK(cpvk_cuda_clear(d.cuda, &a, &cv, 1));
+            }
+        }
+        TouchedByGpu(img->mem);
+    });
+}
+// vkCmdClearAttachments (Draw.cpp:2226-2348): rectangles of the current subpass's attachments, SetPixel per texel.
+VKFN(void) CmdClearAttachments(VkCommandBuffer cb, uint32_t na, const VkClearAttachment* atts, uint32_t nr, const VkClearRect* rects) {
+    std::vector<VkClearAttachment> a(atts, atts + na); std::vector<VkClearRect> r(rects, rects + nr);
+    RECORD(cb)([a, r](Device& d) {
+        DeviceState& s = d.state;
+        if (!s.renderPass || !s.framebuffer) Fatal("vkCmdClearAttachments outside a render pass");
+        const Subpass& sp = s.renderPass->subpasses[s.subpass];
+        for (const VkClearAttachment& ca : a) {
+            const bool colour = (ca.aspectMask & VK_IMAGE_ASPECT_COLOR_BIT) != 0;
+            const uint32_t index = colour ? (ca.colorAttachment < sp.color.size() ? sp.color[ca.colorAttachment].attachment : VK_ATTACHMENT_UNUSED) : sp.depthStencil.attachment;
+            if (index == VK_ATTACHMENT_UNUSED) continue;
+            ImageView* v = s.framebuffer->views[index];
+            const uint32_t texel = TexelSize((uint32_t)s.renderPass->attachments[index].format);
+            for (const VkClearRect& cr : r) {
+                CpvkAttachment full = AttachmentOf(v); full.format = (uint32_t)s.renderPass->attachments[index].format;
+                const uint32_t x0 = (uint32_t)std::max(cr.rect.offset.x, 0), y0 = (uint32_t)std::max(cr.rect.offset.y, 0);
+                const uint32_t x1 = std::min(full.width, x0 + cr.rect.extent.width), y1 = std::min(full.height, y0 + cr.rect.extent.height);
+                if (x1 <= x0 || y1 <= y0) continue;
+                CpvkAttachment sub{full.address + (uint64_t)y0 * full.rowPitch + (uint64_t)x0 * texel, x1 - x0, y1 - y0, full.rowPitch, full.format};
+                CpvkClearValue cv; memcpy(&cv, &ca.clearValue, sizeof cv);
+                CU_CHECK(cpvk_cuda_clear(d.cuda, &sub, &cv, colour ? 0 : 1));
+            }
+            TouchedByGpu(v->image->mem);
+        }
+    });
+}
+
 // ---- sync + submit ----
 VKFN(VkResult) CreateFence(VkDevice, const VkFenceCreateInfo* info, const VkAllocationCallbacks*, VkFence* pFence) {
     auto* f = new Fence(); f->signaled = (info->flags & VK_FENCE_CREATE_SIGNALED_BIT) != 0; *pFence = reinterpret_cast<VkFence>(f); return VK_SUCCESS;
@@ -777,6 +864,7 @@ const Entry kEntries[] = {
     E(CreateGraphicsPipelines), E(DestroyPipeline), E(CreateCommandPool), E(DestroyCommandPool), E(AllocateCommandBuffers), E(FreeCommandBuffers),
     E(BeginCommandBuffer), E(EndCommandBuffer), E(ResetCommandBuffer), E(CmdBindPipeline), E(CmdSetViewport), E(CmdSetScissor), E(CmdBindDescriptorSets),
     E(CmdBindVertexBuffers), E(CmdBindIndexBuffer), E(CmdPushConstants), E(CmdBeginRenderPass), E(CmdNextSubpass), E(CmdEndRenderPass), E(CmdDraw), E(CmdDrawIndexed),
+    E(CmdDrawIndirect), E(CmdDrawIndexedIndirect), E(CmdExecuteCommands), E(CmdFillBuffer), E(CmdUpdateBuffer), E(CmdClearDepthStencilImage), E(CmdClearAttachments),
     E(CmdPipelineBarrier), E(CmdCopyBuffer), E(CmdCopyImage), E(CmdCopyBufferToImage), E(CmdCopyImageToBuffer), E(CmdBlitImage), E(CmdClearColorImage),
     E(CreateFence), E(DestroyFence), E(ResetFences), E(GetFenceStatus), E(WaitForFences), E(CreateSemaphore), E(DestroySemaphore), E(QueueSubmit),
     E(GetDeviceProcAddr), E(GetInstanceProcAddr),

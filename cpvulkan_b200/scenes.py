@@ -515,7 +515,7 @@ def export_scene(scene, directory):
         f.write("\n".join(lines) + "\n")
 
 
-def run_icd(scene, workdir, frames=1, env=None, blit=None):
+def run_icd(scene, workdir, frames=1, env=None, blit=None, flags=()):
     """Render `scene` through the Vulkan ICD (manifest -> vk_icd* -> vkCmdDraw* -> vkQueueSubmit) with the
     loader-harness. Returns (color bytes, depth bytes or None, harness JSON dict)."""
     import json
@@ -529,6 +529,7 @@ def run_icd(scene, workdir, frames=1, env=None, blit=None):
     if env:
         e.update(env)
     extra = ["--blit"] + [str(v) for v in blit] if blit else []  # (width, height, format, filter): see cpvk_harness.cpp
+    extra += [str(f) for f in flags]                              # --indirect, --secondary, --update-buffers, --clear-rect X Y W H
     out = subprocess.run([os.path.join(icd_dir, "cpvk_harness"), scene_dir, out_dir, "--frames", str(frames)] + extra, env=e, check=True,
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     info = json.loads(out.stdout.strip().splitlines()[-1])

@@ -369,11 +369,15 @@ typedef struct VkCommandBufferBeginInfo { VkStructureType sType; const void* pNe
 typedef struct VkBufferCopy { VkDeviceSize srcOffset, dstOffset, size; } VkBufferCopy;
 typedef struct VkImageSubresourceLayers { VkImageAspectFlags aspectMask; uint32_t mipLevel, baseArrayLayer, layerCount; } VkImageSubresourceLayers;
 typedef struct VkImageCopy { VkImageSubresourceLayers srcSubresource; VkOffset3D srcOffset; VkImageSubresourceLayers dstSubresource; VkOffset3D dstOffset; VkExtent3D extent; } VkImageCopy;
+typedef struct VkDrawIndirectCommand { uint32_t vertexCount; uint32_t instanceCount; uint32_t firstVertex; uint32_t firstInstance; } VkDrawIndirectCommand;
+typedef struct VkDrawIndexedIndirectCommand { uint32_t indexCount; uint32_t instanceCount; uint32_t firstIndex; int32_t vertexOffset; uint32_t firstInstance; } VkDrawIndexedIndirectCommand;
 typedef struct VkImageBlit { VkImageSubresourceLayers srcSubresource; VkOffset3D srcOffsets[2]; VkImageSubresourceLayers dstSubresource; VkOffset3D dstOffsets[2]; } VkImageBlit;
 typedef struct VkBufferImageCopy { VkDeviceSize bufferOffset; uint32_t bufferRowLength, bufferImageHeight; VkImageSubresourceLayers imageSubresource; VkOffset3D imageOffset; VkExtent3D imageExtent; } VkBufferImageCopy;
 typedef union VkClearColorValue { float float32[4]; int32_t int32[4]; uint32_t uint32[4]; } VkClearColorValue;
 typedef struct VkClearDepthStencilValue { float depth; uint32_t stencil; } VkClearDepthStencilValue;
 typedef union VkClearValue { VkClearColorValue color; VkClearDepthStencilValue depthStencil; } VkClearValue;
+typedef struct VkClearAttachment { VkImageAspectFlags aspectMask; uint32_t colorAttachment; VkClearValue clearValue; } VkClearAttachment;
+typedef struct VkClearRect { VkRect2D rect; uint32_t baseArrayLayer; uint32_t layerCount; } VkClearRect;
 typedef struct VkRenderPassBeginInfo { VkStructureType sType; const void* pNext; VkRenderPass renderPass; VkFramebuffer framebuffer; VkRect2D renderArea; uint32_t clearValueCount; const VkClearValue* pClearValues; } VkRenderPassBeginInfo;
 typedef struct VkMemoryBarrier { VkStructureType sType; const void* pNext; VkAccessFlags srcAccessMask, dstAccessMask; } VkMemoryBarrier;
 typedef struct VkBufferMemoryBarrier { VkStructureType sType; const void* pNext; VkAccessFlags srcAccessMask, dstAccessMask; uint32_t srcQueueFamilyIndex, dstQueueFamilyIndex; VkBuffer buffer; VkDeviceSize offset, size; } VkBufferMemoryBarrier;
@@ -406,6 +410,7 @@ static_assert(sizeof(VkDescriptorSetLayoutBinding) == 24 && sizeof(VkDescriptorS
 static_assert(sizeof(VkDescriptorSetAllocateInfo) == 40 && sizeof(VkDescriptorImageInfo) == 24 && sizeof(VkDescriptorBufferInfo) == 24 && sizeof(VkWriteDescriptorSet) == 64, "ABI");
 static_assert(sizeof(VkAttachmentDescription) == 36 && sizeof(VkSubpassDescription) == 72 && sizeof(VkSubpassDependency) == 28 && sizeof(VkRenderPassCreateInfo) == 64, "ABI");
 static_assert(sizeof(VkFramebufferCreateInfo) == 64 && sizeof(VkCommandPoolCreateInfo) == 24 && sizeof(VkCommandBufferAllocateInfo) == 32 && sizeof(VkCommandBufferBeginInfo) == 32, "ABI");
+static_assert(sizeof(VkDrawIndirectCommand) == 16 && sizeof(VkDrawIndexedIndirectCommand) == 20 && sizeof(VkClearAttachment) == 24 && sizeof(VkClearRect) == 24, "ABI");
 static_assert(sizeof(VkClearValue) == 16 && sizeof(VkRenderPassBeginInfo) == 64 && sizeof(VkImageCopy) == 68 && sizeof(VkImageBlit) == 80 && sizeof(VkBufferImageCopy) == 56, "ABI");
 static_assert(sizeof(VkImageMemoryBarrier) == 72 && sizeof(VkBufferMemoryBarrier) == 56 && sizeof(VkSpecializationInfo) == 32 && sizeof(VkSpecializationMapEntry) == 16, "ABI");
 #endif

@@ -65,3 +65,35 @@ def test_icd_blit_and_copy_after_the_render_pass(built, tmp_path, w, h, fmt, fil
                   0, 0, 200, 120, 0, 0, w, h, filt)
     assert lib.cpvk_oracle_blit(C.byref(b)) == 0
     assert np.array_equal(info["blit"], dst)
+
+
+@pytest.mark.parametrize("flags", [("--indirect",), ("--secondary",), ("--update-buffers",), ("--indirect", "--secondary", "--update-buffers")],
+                         ids=lambda f: "+".join(x.strip("-") for x in f))
+@pytest.mark.parametrize("indexed", [False, True])
+def test_icd_other_ways_to_issue_the_same_draw(built, tmp_path, flags, indexed):
+    """vkCmdDraw[Indexed]Indirect, vkCmdExecuteCommands of a secondary command buffer, and uniform data delivered by
+    vkCmdFillBuffer + vkCmdUpdateBuffer must produce the frame of the plain draw."""
+    scene = scenes.mesh_indexed(width=160, height=90, nx=40, ny=22) if indexed else scenes.draw_cube(160, 90)
+    oc, od, _ = scenes.run_oracle(scene)
+    gc, gd, _ = scenes.run_icd(scene, str(tmp_path), flags=flags)
+    assert np.array_equal(oc, gc) and np.array_equal(od, gd)
+
+
+def test_icd_clear_attachments_rectangle(built, tmp_path):
+    """vkCmdClearAttachments after the draw: the rectangle of colour and depth takes the clear values, the rest is kept."""
+    import ctypes as C
+    from cpvulkan_b200 import capi
+    scene = scenes.draw_cube(160, 90)
+    oc, od, _ = scenes.run_oracle(scene)
+    gc, gd, _ = scenes.run_icd(scene, str(tmp_path), flags=("--clear-rect", 20, 10, 70, 45))
+    lib = capi.load_oracle()
+    oc, od = np.ascontiguousarray(oc), np.ascontiguousarray(od)
+    cv = capi.ClearValue()
+    for i, v in enumerate((0.5, 0.25, 0.75, 1.0)):
+        cv.float32[i] = v
+    sub = capi.Attachment(oc.ctypes.data + 10 * scene.color.pitch + 20 * 4, 70, 45, scene.color.pitch, scene.color.format)
+    assert lib.cpvk_oracle_clear(C.byref(sub), C.byref(cv), 0) == 0
+    dv = capi.ClearValue(); dv.depthStencil.depth, dv.depthStencil.stencil = 0.5, 0
+    dsub = capi.Attachment(od.ctypes.data + 10 * scene.depth.pitch + 20 * 2, 70, 45, scene.depth.pitch, scene.depth.format)
+    assert lib.cpvk_oracle_clear(C.byref(dsub), C.byref(dv), 1) == 0
+    assert np.array_equal(oc, gc) and np.array_equal(od, gd)
