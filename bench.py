@@ -288,39 +288,61 @@ def run_ours(args):
 
     line = None
     if rank == 0:
-        # e2e through the C ABI with HOST buffers: H2D of the step's inputs from pinned memory, clear + draw, D2H of the colour result
+        # e2e through the C ABI with HOST buffers: every frame uploads its inputs (vertices, indices, uniforms) from pinned
+        # host memory, clears, draws and reads the colour result back into pinned host memory. Like a double-buffered
+        # application, two device objects (each with its own stream, scratch and frame) alternate frames, so the read-back of
+        # frame k overlaps the upload and rendering of frame k+1; a frame's buffers are reused only after its read-back is done.
         e2e = None
         if world == 1:
             names = ["vb", "ib", "ubo"]
-            staged = {}
-            for nme in names:
-                data = scene.buffers[nme]
-                a = dev.alloc(data.nbytes, host_shadow=True)
-                dev.shadow(a)[:data.nbytes] = data
-                staged[nme] = (a, data.nbytes)
-            out_dev = dev.alloc(scene.color.nbytes, host_shadow=True)  # only its pinned shadow is used as the readback target
-            out_host = dev.allocs[out_dev][1]
-            h2d = sum(v[1] for v in staged.values())
+            lanes = []
+            n_lanes = int(os.environ.get("CPVK_E2E_LANES", "2"))
+            for i in range(n_lanes):
+                ldev = dev if i == 0 else Device(local, stats=False)  # the second one runs on its own stream
+                lsod = sod if i == 0 else SceneOnDevice(ldev, scene)
+                staged = {}
+                for nme in names:
+                    data = scene.buffers[nme]
+                    a = ldev.alloc(data.nbytes, host_shadow=True)
+                    ldev.shadow(a)[:data.nbytes] = data
+                    staged[nme] = (a, data.nbytes)
+                out_dev = ldev.alloc(scene.color.nbytes, host_shadow=True)  # only its pinned shadow is used as the readback target
+                lanes.append((ldev, lsod, staged, ldev.allocs[out_dev][1]))
+            h2d = sum(v[1] for v in lanes[0][2].values())
             d2h = scene.color.nbytes
 
-            def e2e_step():
+            def e2e_step(k):
+                ldev, lsod, staged, out_host = lanes[k % n_lanes]
+                ldev.sync()  # frame k-2 (same lane) has been read back: its buffers are free
                 for nme in names:
                     src_alloc, nbytes = staged[nme]
-                    dev.upload_async(sod.m.addr[nme], dev.allocs[src_alloc][1], nbytes)
-                sod.clear()
-                sod.draw()
-                dev.download_into(out_host, sod.m.addr["color"], d2h)  # synchronises
+                    ldev.upload_async(lsod.m.addr[nme], ldev.allocs[src_alloc][1], nbytes)
+                lsod.clear()
+                lsod.draw()
+                ldev.download_into_async(out_host, lsod.m.addr["color"], d2h)
 
-            for _ in range(2):
-                e2e_step()
+            for k in range(2 * n_lanes):
+                e2e_step(k)
+            for lane in lanes:
+                lane[0].sync()
+            # the read-back frame must be the frame the resident path produced
+            ref_frame = color_t.cpu().numpy()
+            for lane in lanes:
+                got = np.ctypeslib.as_array(C.cast(lane[3], C.POINTER(C.c_uint8)), shape=(d2h,))
+                if not np.array_equal(got, ref_frame):
+                    raise SystemExit("e2e read-back differs from the resident frame")
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for _ in range(args.steps):
-                e2e_step()
-            torch.cuda.synchronize()
+            for k in range(args.steps):
+                e2e_step(k)
+            for lane in lanes:
+                lane[0].sync()
             e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
             e2e = {"value": prims / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                   "through": "C ABI (cpvk_cuda_mem_upload / clear / draw / mem_download) with pinned host buffers"}
+                   "through": "C ABI (cpvk_cuda_mem_upload / clear / draw / mem_download_async + sync) with pinned host buffers; two device objects alternate frames (double buffering)"}
+            for lane in lanes[1:]:
+                lane[1].close()
+                lane[0].close()
         extras = None
         if world == 1 and not args.no_extras:
             extras = secondary_configs(dev, torch)

@@ -86,6 +86,9 @@ class Device:
     def download_into(self, host_ptr, addr, nbytes):
         _check(self.lib, self.lib.cpvk_cuda_mem_download(self.handle, C.c_void_p(host_ptr), addr, nbytes))
 
+    def download_into_async(self, host_ptr, addr, nbytes):
+        _check(self.lib, self.lib.cpvk_cuda_mem_download_async(self.handle, C.c_void_p(host_ptr), addr, nbytes))
+
     def sync(self):
         _check(self.lib, self.lib.cpvk_cuda_sync(self.handle))
 

@@ -253,6 +253,9 @@ int cpvk_cuda_mem_alloc(CpvkDevice* device, size_t size, uint64_t* outDeviceAddr
 int cpvk_cuda_mem_free(CpvkDevice* device, uint64_t deviceAddress);
 int cpvk_cuda_mem_upload(CpvkDevice* device, uint64_t deviceAddress, const void* host, size_t size);
 int cpvk_cuda_mem_download(CpvkDevice* device, void* host, uint64_t deviceAddress, size_t size);
+/* The same without waiting: the bytes are in `host` (pinned memory) once a later cpvk_cuda_sync returns. Lets a frame
+   loop overlap the read-back of frame k with the upload and rendering of frame k+1 on a second device object. */
+int cpvk_cuda_mem_download_async(CpvkDevice* device, void* host, uint64_t deviceAddress, size_t size);
 
 /* vkCreateGraphicsPipelines: SPIR-V -> CUDA C++ device functions -> NVRTC (LTO-IR) -> nvJitLink with the
    prebuilt stage kernels -> cubin. Replaces CompileVertexPipeline/CompileFragmentPipeline + the x86 ORC JIT. */
