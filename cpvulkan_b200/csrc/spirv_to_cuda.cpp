@@ -536,7 +536,8 @@ private:
             if (positionVar) for (int q = 0; q < 4; q++) pos[q] = "g" + std::to_string(positionVar) + "[" + std::to_string(q) + "]";
             if (pointSizeVar) psz = "g" + std::to_string(pointSizeVar) + "[0]";
             body << "  dp->vsPos[rawId] = make_uint4(" << pos[0] << ", " << pos[1] << ", " << pos[2] << ", " << pos[3] << ");\n";
-            (void)psz; (void)clip; // words 4..5 of the record have no consumer on the triangle path
+            if (desc.topology == 0) body << "  dp->vsPointSize[rawId] = " << psz << ";\n"; // point lists read the size back (Draw.cpp:1345)
+            (void)clip; // clip distances have no consumer (no clipping)
             uint32_t byteOff = 24;
             std::function<void(uint32_t, const std::string&, uint32_t&, uint32_t)> store = [&](uint32_t ty, const std::string& g, uint32_t& srcWord, uint32_t dstByte) {
                 const Type& t = T(ty);

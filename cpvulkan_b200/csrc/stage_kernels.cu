@@ -173,6 +173,9 @@ CPVK_DEV void cpvk_tile_fill(cpvk_u8* dst, cpvk_u32 texel, const cpvk_u8* one) {
     }
 }
 
+// x86 cvttss2si semantics for static_cast<int32_t>(float): NaN and out-of-range inputs give INT_MIN.
+__device__ __forceinline__ int cpvk_cvtt(float v) { return (v >= 2147483648.0f || v < -2147483648.0f || v != v) ? (int)0x80000000 : (int)v; }
+
 extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 
 // One CTA per screen tile. Warp w owns the 16x8 sub-rectangle (w&1, w>>1) of the tile, so no two warps ever touch
@@ -186,9 +189,10 @@ extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 #endif
 extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MIN_CTAS) cpvk_k_raster(const __grid_constant__ CpvkDrawParams p) {
     const cpvk_u32 tile = blockIdx.x;
-    if (p.binMeta[3] != 0) return; // the speculative launch plan did not fit this draw: the host replays it
-    const bool listsSorted = p.binMeta[1] > CPVK_CHUNK;
-    const cpvk_u32 listBegin = p.tileOffsets[tile], listEnd = p.tileOffsets[tile + 1];
+    const bool triangles = cpvk_prim_vertices() == 3; // points and lines are not binned: every tile walks all of them (below)
+    if (triangles && p.binMeta[3] != 0) return; // the speculative launch plan did not fit this draw: the host replays it
+    const bool listsSorted = triangles && p.binMeta[1] > CPVK_CHUNK;
+    const cpvk_u32 listBegin = triangles ? p.tileOffsets[tile] : 0u, listEnd = triangles ? p.tileOffsets[tile + 1] : 1u;
     const cpvk_u32 lazyMask = p.lazyMask;
     const cpvk_u32 ty = tile / p.tilesX, tx = tile - ty * p.tilesX;
     const int tileX0 = (int)tx * CPVK_TILE_W, tileY0 = (int)ty * CPVK_TILE_H;
@@ -413,8 +417,136 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     };
 
     const bool regionLive = rx0 < rx1 && ry0 < ry1;
+    if (!triangles) {
+        // ---- points and lines (ProcessPoints / ProcessLines, Draw.cpp:1315-1508) ----
+        // The reference tests every pixel of the viewport against every line; here each tile walks all primitives in API
+        // order, 256 at a time: one thread derives one primitive's terms into shared memory, then every lane tests its own
+        // four pixels of the warp's region against primitives whose (conservative) pixel box touches the region. A pixel
+        // belongs to one lane for the whole draw, so its fragments reach the ROP in API order by construction.
+        const bool points = cpvk_spec_u32(CPVK_SPEC_TOPOLOGY) == 0u;
+        float* sRec = reinterpret_cast<float*>(sQ); // [CPVK_CHUNK][24]
+        const bool useCache = p.indexStride != 0 && cpvk_vcache_on(p.vcache, p.count);
+        auto slotOf = [&](cpvk_u32 i) -> cpvk_u32 { return useCache ? cpvk_fetch_index(p.indexBuffer, p.indexStride, (cpvk_u64)p.first + i) - cpvk_vcache_lowest(p.vcache) : i; };
+        #pragma unroll 1
+        for (cpvk_u32 base = 0; base < p.primCount; base += CPVK_CHUNK) {
+            const int n = (int)min((cpvk_u32)CPVK_CHUNK, p.primCount - base);
+            __syncthreads();
+            if ((int)threadIdx.x < n) {
+                const cpvk_u32 prim = base + threadIdx.x;
+                float* r = sRec + threadIdx.x * 24;
+                int bx0, by0, bx1, by1;
+                const float W = p.vpWidth, H = p.vpHeight;
+                if (points) {
+                    const cpvk_u32 s0 = slotOf(prim);
+                    const uint4 pv = __ldg(p.vsPos + s0);
+                    const float pw = __uint_as_float(pv.w);
+                    const float X = __uint_as_float(pv.x) / pw, Y = __uint_as_float(pv.y) / pw, Z = __uint_as_float(pv.z) / pw;
+                    const float pointSize = __uint_as_float(__ldg(p.vsPointSize + s0));
+                    const int sx = cpvk_cvtt((X + 1.0f) * 0.5f * (W - 1.0f)), sy = cpvk_cvtt((Y + 1.0f) * 0.5f * (H - 1.0f));
+                    const int half = cpvk_cvtt(ceilf(pointSize / 2.0f));
+                    bx0 = max(0, sx - half); by0 = max(0, sy - half);                               // Draw.cpp:1348-1351: the pixel loop's exact domain
+                    bx1 = min(cpvk_cvtt(W), sx + half + 1); by1 = min(cpvk_cvtt(H), sy + half + 1);
+                    r[0] = __int_as_float(sx); r[1] = __int_as_float(sy); r[2] = pointSize; r[3] = Z; r[4] = pw; r[17] = __uint_as_float(s0); r[18] = __uint_as_float(s0);
+                } else {
+                    const cpvk_u32 i0 = cpvk_spec_u32(CPVK_SPEC_TOPOLOGY) == 1u ? prim * 2u : prim;
+                    const cpvk_u32 s0 = slotOf(i0), s1 = slotOf(i0 + 1u);
+                    const uint4 v0 = __ldg(p.vsPos + s0), v1 = __ldg(p.vsPos + s1);
+                    const float w0 = __uint_as_float(v0.w), w1 = __uint_as_float(v1.w);
+                    const float P0[4] = {__uint_as_float(v0.x) / w0, __uint_as_float(v0.y) / w0, __uint_as_float(v0.z) / w0, w0};
+                    const float P1[4] = {__uint_as_float(v1.x) / w1, __uint_as_float(v1.y) / w1, __uint_as_float(v1.z) / w1, w1};
+                    const float lw = cpvk_spec_f32(6);
+                    const float lwx = lw / W, lwy = lw / H;
+                    const float d0 = P1[0] - P0[0], d1 = P1[1] - P0[1], d2 = P1[2] - P0[2], d3 = P1[3] - P0[3];
+                    const float sqr = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;  // glm::normalize(vec4): x * (1 / sqrt(dot))
+                    const float inv = 1.0f / sqrtf(sqr);
+                    const float dirx = d0 * inv, diry = d1 * inv;
+                    const float ox = diry * lwx, oy = (-dirx) * lwy;           // perpendicular (dir.y, -dir.x) * lineWidth, component-wise
+                    r[0] = P0[0] + ox; r[1] = P0[1] + oy; r[2] = P0[0] - ox; r[3] = P0[1] - oy; // p00, p01
+                    r[4] = P1[0] + ox; r[5] = P1[1] + oy; r[6] = P1[0] - ox; r[7] = P1[1] - oy; // p10, p11
+                    r[8] = P0[0]; r[9] = P0[1]; r[10] = d0; r[11] = d1;
+                    const float len = sqrtf(d0 * d0 + d1 * d1);                 // glm::length(vec2)
+                    r[12] = len * len; r[13] = P0[2]; r[14] = P1[2]; r[15] = w0; r[16] = w1;
+                    r[17] = __uint_as_float(s0); r[18] = __uint_as_float(s1);
+                    // Pixel box: exact for a proper parallelogram (+2 px for rounding); a degenerate or non-finite quad can pass
+                    // the four >= 0 tests anywhere (all-zero edge functions), so it keeps the whole viewport like the reference.
+                    bx0 = 0; by0 = 0; bx1 = cpvk_cvtt(ceilf(W)); by1 = cpvk_cvtt(ceilf(H));
+                    const float cross = (r[2] - r[0]) * (r[5] - r[1]) - (r[3] - r[1]) * (r[4] - r[0]);
+                    float mnx = fminf(fminf(r[0], r[2]), fminf(r[4], r[6])), mxx = fmaxf(fmaxf(r[0], r[2]), fmaxf(r[4], r[6]));
+                    float mny = fminf(fminf(r[1], r[3]), fminf(r[5], r[7])), mxy = fmaxf(fmaxf(r[1], r[3]), fmaxf(r[5], r[7]));
+                    const float sum = ((r[0] + r[2]) + (r[4] + r[6])) + ((r[1] + r[3]) + (r[5] + r[7]));
+                    if (fabsf(cross) > 0.0f && fabsf(sum) < 1e30f && fabsf(cross) < 1e30f) { // finite corners, non-zero area
+                        const float fx0 = (mnx + 1.0f) * 0.5f * W - 2.0f, fx1 = (mxx + 1.0f) * 0.5f * W + 3.0f;
+                        const float fy0 = (mny + 1.0f) * 0.5f * H - 2.0f, fy1 = (mxy + 1.0f) * 0.5f * H + 3.0f;
+                        bx0 = max(bx0, cpvk_cvtt(floorf(fmaxf(fx0, -1.0f)))); bx1 = min(bx1, cpvk_cvtt(ceilf(fminf(fx1, 40000.0f))));
+                        by0 = max(by0, cpvk_cvtt(floorf(fmaxf(fy0, -1.0f)))); by1 = min(by1, cpvk_cvtt(ceilf(fminf(fy1, 40000.0f))));
+                    }
+                }
+                bx0 = max(bx0, p.clipX0); by0 = max(by0, p.clipY0); bx1 = min(bx1, p.clipX1); by1 = min(by1, p.clipY1);
+                r[19] = __int_as_float(bx0); r[20] = __int_as_float(by0); r[21] = __int_as_float(bx1); r[22] = __int_as_float(by1);
+            }
+            __syncthreads();
+            if (!regionLive) continue;
+            #pragma unroll 1
+            for (int j = 0; j < n; j++) {
+                const float* r = sRec + j * 24;
+                const int bx0 = __float_as_int(r[19]), by0 = __float_as_int(r[20]), bx1 = __float_as_int(r[21]), by1 = __float_as_int(r[22]);
+                if (!(bx0 < rx1 && bx1 > rx0 && by0 < ry1 && by1 > ry0)) continue; // warp-uniform
+                #pragma unroll 1
+                for (int k = 0; k < 4; k++) {
+                    const int x = rx0 + (lane & 15), y = ry0 + (lane >> 4) + 2 * k;
+                    bool covered = x >= bx0 && x < bx1 && y >= by0 && y < by1 && x < rx1 && y < ry1;
+                    float t = 0.0f;
+                    if (covered) {
+                        if (points) {
+                            const float ps = r[2];
+                            const float sx = 0.5f + (float)(x - __float_as_int(r[0])) / ps, sy = 0.5f + (float)(y - __float_as_int(r[1])) / ps;
+                            covered = sx >= 0.0f && sy >= 0.0f && sx <= 1.0f && sy <= 1.0f;
+                        } else {
+                            const float xf = sXf[x - tileX0], yf = sYf[y - tileY0];
+                            // EdgeFunction(a, b, c) = (c.x - a.x) * (b.y - a.y) - (c.y - a.y) * (b.x - a.x), Draw.cpp:410-413
+                            const float e0 = (xf - r[0]) * (r[3] - r[1]) - (yf - r[1]) * (r[2] - r[0]); // (p00, p01)
+                            const float e1 = (xf - r[6]) * (r[5] - r[7]) - (yf - r[7]) * (r[4] - r[6]); // (p11, p10)
+                            const float e2 = (xf - r[4]) * (r[1] - r[5]) - (yf - r[5]) * (r[0] - r[4]); // (p10, p00)
+                            const float e3 = (xf - r[2]) * (r[7] - r[3]) - (yf - r[3]) * (r[6] - r[2]); // (p01, p11)
+                            covered = e0 >= 0.0f && e1 >= 0.0f && e2 >= 0.0f && e3 >= 0.0f;
+                            t = ((xf - r[8]) * r[10] + (yf - r[9]) * r[11]) / r[12];
+                        }
+                    }
+                    const cpvk_u32 covMask = __ballot_sync(0xFFFFFFFFu, covered);
+                    if (covMask == 0) continue;
+                    nCov += __popc(covMask);
+                    CpvkFragOut out;
+                    bool wrote = false;
+                    if (covered) {
+                        CpvkFragCtx ctx;
+                        float depth;
+                        if (points) {
+                            ctx.w[0] = 1.0f; ctx.w[1] = 0.0f; ctx.w[2] = 0.0f; ctx.pw[0] = r[4]; ctx.pw[1] = 1.0f; ctx.pw[2] = 1.0f;
+                            depth = r[3];
+                        } else {
+                            ctx.w[0] = 1.0f - t; ctx.w[1] = t; ctx.w[2] = 0.0f; ctx.pw[0] = r[15]; ctx.pw[1] = r[16]; ctx.pw[2] = 1.0f;
+                            depth = r[13] * t + r[14] * (1.0f - t); // Draw.cpp:1494: the depth weights are the attribute weights swapped
+                        }
+                        ctx.unitW = ctx.pw[0] == 1.0f && ctx.pw[1] == 1.0f;
+                        { float den = 0.0f;
+                          if (ctx.unitW) { den += ctx.w[0]; den += ctx.w[1]; } else { den += ctx.w[0] / ctx.pw[0]; den += ctx.w[1] / ctx.pw[1]; }
+                          ctx.persDen = den; }
+                        const cpvk_u32 s0 = __float_as_uint(r[17]), s1 = __float_as_uint(r[18]);
+                        ctx.idx[0] = s0; ctx.idx[1] = s1; ctx.idx[2] = s1; ctx.provoking = s0;
+                        ctx.v[0] = p.vsOut + (cpvk_u64)s0 * p.vsStride; ctx.v[1] = p.vsOut + (cpvk_u64)s1 * p.vsStride; ctx.v[2] = ctx.v[1]; ctx.vProv = ctx.v[0];
+                        ctx.fragCoord[0] = cpvk_spec_u32(CPVK_SPEC_ORIGIN_UPPER) ? (float)x : p.vpWidth - (float)x - 1.0f;
+                        ctx.fragCoord[1] = (float)y; ctx.fragCoord[2] = depth; ctx.fragCoord[3] = 1.0f;
+                        ctx.dp = &p; ctx.unorm8 = sLut;
+                        const float fragDepth = (p.vpMaxDepth - p.vpMinDepth) * depth + p.vpMinDepth;
+                        if (!cpvk_fs_main(&ctx, &out)) wrote = rop(x - tileX0, y - tileY0, fragDepth, true, out);
+                    }
+                    nPass += __popc(__ballot_sync(0xFFFFFFFFu, wrote));
+                }
+            }
+        }
+    }
     #pragma unroll 1
-    for (cpvk_u32 chunkBase = listBegin; chunkBase < listEnd; chunkBase += CPVK_CHUNK) {
+    for (cpvk_u32 chunkBase = listBegin; triangles && chunkBase < listEnd; chunkBase += CPVK_CHUNK) {
         const int n = (int)min((cpvk_u32)CPVK_CHUNK, listEnd - chunkBase);
         if (!listsSorted) {
             // Binning claims list slots with atomics, so a tile's ids arrive in arbitrary order. When every list fits

@@ -142,6 +142,7 @@ struct SceneDesc {
     std::vector<VkVertexInputBindingDescription> bindings;
     std::vector<VkVertexInputAttributeDescription> attributes;
     uint32_t topology = 3, cull = 0, front = 0, depthTest = 0, depthWrite = 0, depthOp = 3, writeMask = 0xF;
+    float lineWidth = 1.0f;
     bool blend = false; uint32_t bl[6] = {};
     struct Buf { std::string file; uint64_t size; }; std::map<std::string, Buf> buffers;
     std::map<uint32_t, std::string> vertexBuffers;
@@ -165,6 +166,7 @@ static SceneDesc ParseScene(const std::string& dir) {
         if (key == "vs") is >> s.vs; else if (key == "fs") is >> s.fs;
         else if (key == "binding") { VkVertexInputBindingDescription b{}; uint32_t rate; is >> b.binding >> b.stride >> rate; b.inputRate = (VkVertexInputRate)rate; s.bindings.push_back(b); }
         else if (key == "attribute") { VkVertexInputAttributeDescription a{}; uint32_t fmt; is >> a.location >> a.binding >> fmt >> a.offset; a.format = (VkFormat)fmt; s.attributes.push_back(a); }
+        else if (key == "line_width") is >> s.lineWidth;
         else if (key == "topology") is >> s.topology; else if (key == "cull") is >> s.cull; else if (key == "front") is >> s.front;
         else if (key == "depth_test") is >> s.depthTest; else if (key == "depth_write") is >> s.depthWrite; else if (key == "depth_op") is >> s.depthOp;
         else if (key == "write_mask") is >> s.writeMask;
@@ -340,7 +342,7 @@ int main(int argc, char** argv) {
     VkPipelineVertexInputStateCreateInfo vis{VK_STRUCTURE_TYPE_PIPELINE_VERTEX_INPUT_STATE_CREATE_INFO, nullptr, 0, (uint32_t)sc.bindings.size(), sc.bindings.data(), (uint32_t)sc.attributes.size(), sc.attributes.data()};
     VkPipelineInputAssemblyStateCreateInfo ias{VK_STRUCTURE_TYPE_PIPELINE_INPUT_ASSEMBLY_STATE_CREATE_INFO, nullptr, 0, (VkPrimitiveTopology)sc.topology, VK_FALSE};
     VkPipelineViewportStateCreateInfo vps{VK_STRUCTURE_TYPE_PIPELINE_VIEWPORT_STATE_CREATE_INFO, nullptr, 0, 1, nullptr, 1, nullptr};
-    VkPipelineRasterizationStateCreateInfo rss{VK_STRUCTURE_TYPE_PIPELINE_RASTERIZATION_STATE_CREATE_INFO, nullptr, 0, VK_FALSE, VK_FALSE, VK_POLYGON_MODE_FILL, sc.cull, (VkFrontFace)sc.front, VK_FALSE, 0, 0, 0, 1.0f};
+    VkPipelineRasterizationStateCreateInfo rss{VK_STRUCTURE_TYPE_PIPELINE_RASTERIZATION_STATE_CREATE_INFO, nullptr, 0, VK_FALSE, VK_FALSE, VK_POLYGON_MODE_FILL, sc.cull, (VkFrontFace)sc.front, VK_FALSE, 0, 0, 0, sc.lineWidth};
     VkPipelineMultisampleStateCreateInfo mss{VK_STRUCTURE_TYPE_PIPELINE_MULTISAMPLE_STATE_CREATE_INFO, nullptr, 0, VK_SAMPLE_COUNT_1_BIT, VK_FALSE, 0.0f, nullptr, VK_FALSE, VK_FALSE};
     VkStencilOpState sop{VK_STENCIL_OP_KEEP, VK_STENCIL_OP_KEEP, VK_STENCIL_OP_KEEP, VK_COMPARE_OP_ALWAYS, 0, 0, 0};
     VkPipelineDepthStencilStateCreateInfo dss{VK_STRUCTURE_TYPE_PIPELINE_DEPTH_STENCIL_STATE_CREATE_INFO, nullptr, 0, sc.depthTest, sc.depthWrite, (VkCompareOp)sc.depthOp, VK_FALSE, VK_FALSE, sop, sop, 0.0f, 1.0f};

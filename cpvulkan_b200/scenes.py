@@ -21,6 +21,7 @@ R8G8B8A8_UNORM, B8G8R8A8_UNORM, R16G16B16A16_SFLOAT = 37, 44, 97
 R32_SFLOAT, R32G32_SFLOAT, R32G32B32_SFLOAT, R32G32B32A32_SFLOAT = 100, 103, 106, 109
 D16_UNORM, D32_SFLOAT, D24_UNORM_S8_UINT = 124, 126, 129
 # VkPrimitiveTopology / VkCullMode / VkFrontFace / VkCompareOp
+POINT_LIST, LINE_LIST, LINE_STRIP = 0, 1, 2
 TRIANGLE_LIST, TRIANGLE_STRIP, TRIANGLE_FAN = 3, 4, 5
 CULL_NONE, CULL_FRONT, CULL_BACK = 0, 1, 2
 FRONT_CCW, FRONT_CW = 0, 1
@@ -88,6 +89,7 @@ class Scene:
         self.viewport = None                     # (x, y, w, h, minDepth, maxDepth)
         self.count, self.instances, self.first, self.vertex_offset, self.first_instance = 0, 1, 0, 0, 0
         self.push_constants = b""
+        self.line_width = 1.0
         self.mutate = None                       # optional callable(Materialized): last-minute edits of the PODs, applied on every backend
 
 
@@ -123,7 +125,7 @@ def materialize(scene, alloc):
     for i, a in enumerate(scene.attributes):
         d.attributes[i] = capi.VertexAttribute(*a)
     d.topology = scene.topology
-    d.polygonMode, d.cullMode, d.frontFace, d.lineWidth = 0, scene.cull, scene.front_face, 1.0
+    d.polygonMode, d.cullMode, d.frontFace, d.lineWidth = 0, scene.cull, scene.front_face, scene.line_width
     d.rasterizationSamples = 1
     d.depthTestEnable, d.depthWriteEnable, d.depthCompareOp = int(scene.depth_test), int(scene.depth_write), scene.depth_op
     d.minDepthBounds, d.maxDepthBounds = 0.0, 1.0
@@ -425,6 +427,31 @@ def texel_buffer(width=500, height=500, texels=(1.0, 0.0, 1.0), triangles=1):
     return s
 
 
+def random_points_lines(width=96, height=64, count=60, seed=1, topology=POINT_LIST, line_width=3.0, depth_fmt=D32_SFLOAT,
+                        color_fmt=R8G8B8A8_UNORM, perspective=True, fs="cube.frag"):
+    """Points / line lists / line strips: random positions (optionally varying w), per-vertex colour
+    and point size (1..9 px)."""
+    s = Scene("prims_t%d_%d_%dx%d_s%d" % (topology, count, width, height, seed))
+    s.vs, s.fs = "points.vert", fs
+    rng = np.random.RandomState(seed)
+    n = count if topology != LINE_LIST else count * 2
+    xy = rng.uniform(-1.05, 1.05, size=(n, 2)).astype(np.float32)
+    z = rng.uniform(0.0, 1.0, size=(n, 1)).astype(np.float32)
+    w = rng.uniform(0.5, 3.0, size=(n, 1)).astype(np.float32) if perspective else np.ones((n, 1), dtype=np.float32)
+    pos = np.concatenate([xy * w, z * w, w], axis=1).astype(np.float32)
+    col = rng.random_sample((n, 4)).astype(np.float32)
+    size = rng.uniform(1.0, 9.0, size=(n, 1)).astype(np.float32)
+    vb = np.concatenate([pos, col, size], axis=1).astype(np.float32)  # 36 bytes per vertex
+    s.buffers["vb"] = vb.view(np.uint8).reshape(-1)
+    s.bindings = [(0, 36, 0)]
+    s.attributes = [(0, 0, R32G32B32A32_SFLOAT, 0), (1, 0, R32G32B32A32_SFLOAT, 16), (2, 0, R32_SFLOAT, 32)]
+    s.vertex_buffers = {0: "vb"}
+    s.topology, s.count, s.line_width = topology, n, line_width
+    s.depth_test = s.depth_write = depth_fmt is not None
+    _render_targets(s, width, height, color_fmt, depth_fmt, (0.1, 0.2, 0.3, 1.0))
+    return s
+
+
 def random_triangles(width=256, height=192, tris=200, seed=1, depth_fmt=D32_SFLOAT, color_fmt=R8G8B8A8_UNORM,
                      cull=CULL_NONE, front_face=FRONT_CCW, perspective=True, depth_op=LESS_OR_EQUAL,
                      topology=TRIANGLE_LIST, indexed=None, snap=False):
@@ -483,7 +510,7 @@ def export_scene(scene, directory):
         lines.append("attribute %d %d %d %d" % a)
     lines += ["topology %d" % scene.topology, "cull %d" % scene.cull, "front %d" % scene.front_face,
               "depth_test %d" % int(scene.depth_test), "depth_write %d" % int(scene.depth_write), "depth_op %d" % scene.depth_op,
-              "write_mask %d" % scene.write_mask]
+              "write_mask %d" % scene.write_mask, "line_width %r" % float(np.float32(scene.line_width))]
     if scene.blend:
         bl = scene.blend
         lines.append("blend %d %d %d %d %d %d" % (bl["src"], bl["dst"], bl["op"], bl.get("srcA", bl["src"]), bl.get("dstA", bl["dst"]), bl.get("opA", bl["op"])))

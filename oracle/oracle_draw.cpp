@@ -388,8 +388,10 @@ void RunVertexStage(DrawContext& c, uint32_t instance, uint32_t n) {
 }
 
 // One fragment: FS call + epilogue (PipelineCompiler.cpp:1058-1080). Returns nothing; updates attachments.
+// nv = vertices of the primitive: 3 triangle, 2 line (SetDatum<.., 2>, Draw.cpp:1458-1482), 1 point (every input is a
+// plain copy of the vertex's value whatever its interpolation qualifier, Draw.cpp:1366-1370).
 void Fragment(DrawContext& c, int32_t x, int32_t y, float depth, bool front, const float w[3], const float pw[3],
-              const uint32_t idx[3], uint32_t provoking) {
+              const uint32_t idx[3], uint32_t provoking, int nv = 3) {
     const CpvkPipelineDesc& d = *c.desc;
     const CpvkDrawState& st = *c.st;
     Module& m = c.fs.mod;
@@ -399,21 +401,22 @@ void Fragment(DrawContext& c, int32_t x, int32_t y, float depth, bool front, con
     for (const InOut& in : c.fs.inputs) {
         uint32_t* dst = c.fsi.VarData(in.var);
         const uint8_t* data[3];
-        for (int k = 0; k < 3; k++) data[k] = c.vertexStorage.data() + (size_t)idx[k] * c.vs.outputStride + in.offset;
+        for (int k = 0; k < nv; k++) data[k] = c.vertexStorage.data() + (size_t)idx[k] * c.vs.outputStride + in.offset;
+        if (nv == 1) { std::memcpy(dst, data[0], in.size); continue; }
         if (in.interpolation == 2) { std::memcpy(dst, c.vertexStorage.data() + (size_t)provoking * c.vs.outputStride + in.offset, in.size); continue; }
         const Type& t = m.types[in.type];
         const Type& et = t.kind == Type::Vector ? m.types[t.elem] : t;
         if (et.kind != Type::Float || (t.kind != Type::Vector && t.kind != Type::Float)) Fail("SetDatum: only 32-bit float inputs interpolate (FATAL_ERROR, Draw.cpp:863-869)");
         const uint32_t comps = t.kind == Type::Vector ? t.count : 1;
         for (uint32_t e = 0; e < comps; e++) {
-            float values[3]; for (int k = 0; k < 3; k++) std::memcpy(&values[k], data[k] + 4 * e, 4);
+            float values[3]; for (int k = 0; k < nv; k++) std::memcpy(&values[k], data[k] + 4 * e, 4);
             float result;
             if (in.interpolation == 0) {
                 float numerator = 0.0f, denominator = 0.0f;
-                for (int k = 0; k < 3; k++) { numerator += w[k] * values[k] / pw[k]; denominator += w[k] / pw[k]; }
+                for (int k = 0; k < nv; k++) { numerator += w[k] * values[k] / pw[k]; denominator += w[k] / pw[k]; }
                 result = numerator / denominator;
             } else {
-                result = 0.0f; for (int k = 0; k < 3; k++) result += w[k] * values[k];
+                result = 0.0f; for (int k = 0; k < nv; k++) result += w[k] * values[k];
             }
             std::memcpy(&dst[e], &result, 4);
         }
@@ -509,6 +512,83 @@ void Fragment(DrawContext& c, int32_t x, int32_t y, float depth, bool front, con
     }
 }
 
+// EdgeFunction on vec2 (Draw.cpp:410-413)
+static float EdgeFunction2(const float a[2], const float b[2], const float c[2]) { return (c[0] - a[0]) * (b[1] - a[1]) - (c[1] - a[1]) * (b[0] - a[0]); }
+
+// ProcessPoints (Draw.cpp:1315-1380): a square of ceil(pointSize / 2) pixels around the truncated screen position,
+// s/t test against the point size, inputs copied from the vertex, depth = p0.z, always front-facing.
+void ProcessPoints(DrawContext& c, uint32_t primCount) {
+    const CpvkDrawState& st = *c.st;
+    const float W = st.viewport.width, H = st.viewport.height;
+    for (uint32_t p = 0; p < primCount; p++) {
+        float pos[4], pointSize;
+        std::memcpy(pos, c.vertexStorage.data() + (size_t)p * c.vs.outputStride, 16);
+        std::memcpy(&pointSize, c.vertexStorage.data() + (size_t)p * c.vs.outputStride + 16, 4);
+        float P[4]; for (int q = 0; q < 4; q++) P[q] = pos[q] / pos[3];
+        P[3] = pos[3];
+        const int32_t px = (int32_t)((P[0] + 1) * 0.5f * (W - 1)), py = (int32_t)((P[1] + 1) * 0.5f * (H - 1));
+        const int32_t half = (int32_t)std::ceil(pointSize / 2);
+        int32_t startX = std::max(0, px - half), startY = std::max(0, py - half);
+        int32_t endX = std::min((int32_t)W, px + half + 1), endY = std::min((int32_t)H, py + half + 1);
+        startX = std::max(startX, c.win.x0); startY = std::max(startY, c.win.y0);
+        endX = std::min(endX, c.win.x1); endY = std::min(endY, c.win.y1);
+        const uint32_t idx[3] = {p, p, p}; const float w[3] = {1.0f, 0.0f, 0.0f}; const float pw[3] = {P[3], 1.0f, 1.0f};
+        for (int32_t y = startY; y < endY; y++)
+            for (int32_t x = startX; x < endX; x++) {
+                const float s = 0.5f + (x - px) / pointSize;
+                const float t = 0.5f + (y - py) / pointSize;
+                if (s >= 0 && t >= 0 && s <= 1 && t <= 1) Fragment(c, x, y, P[2], true, w, pw, idx, p, 1);
+            }
+    }
+}
+
+// ProcessLines (Draw.cpp:1382-1508), rectangular mode: a quad of +-perpendicular * (lineWidth / viewport) around the
+// segment in NDC; the perpendicular comes from glm::normalize of the *4-component* difference (so z and w shorten it);
+// every pixel of the viewport is tested against the four quad edges; t by projection on the segment;
+// attributes weigh (1 - t, t), depth weighs (t, 1 - t) — as written there.
+void ProcessLines(DrawContext& c, uint32_t primCount, uint32_t topology) {
+    const CpvkDrawState& st = *c.st;
+    const CpvkPipelineDesc& d = *c.desc;
+    const float W = st.viewport.width, H = st.viewport.height;
+    const float halfPixel[2] = {(1.0f / W) * 0.5f, (1.0f / H) * 0.5f};
+    for (uint32_t p = 0; p < primCount; p++) {
+        const uint32_t i0 = topology == 1 ? p * 2 : p, i1 = i0 + 1, provoking = i0;
+        float P[2][4];
+        const uint32_t iv[2] = {i0, i1};
+        for (int k = 0; k < 2; k++) {
+            float pos[4]; std::memcpy(pos, c.vertexStorage.data() + (size_t)iv[k] * c.vs.outputStride, 16);
+            for (int q = 0; q < 4; q++) P[k][q] = pos[q] / pos[3];
+            P[k][3] = pos[3];
+        }
+        const float lineWidth[2] = {d.lineWidth / W, d.lineWidth / H};
+        float diff[4]; for (int q = 0; q < 4; q++) diff[q] = P[1][q] - P[0][q];
+        const float sqr = diff[0] * diff[0] + diff[1] * diff[1] + diff[2] * diff[2] + diff[3] * diff[3]; // glm normalize(vec4), func_geometric.inl:269-278
+        const float inv = 1.0f / std::sqrt(sqr);                                                          // glm inversesqrt(float), func_exponential.inl:226-229
+        const float dir[2] = {diff[0] * inv, diff[1] * inv};
+        const float perp[2] = {dir[1], -dir[0]};
+        const float off[2] = {perp[0] * lineWidth[0], perp[1] * lineWidth[1]};
+        const float p00[2] = {P[0][0] + off[0], P[0][1] + off[1]}, p01[2] = {P[0][0] - off[0], P[0][1] - off[1]};
+        const float p10[2] = {P[1][0] + off[0], P[1][1] + off[1]}, p11[2] = {P[1][0] - off[0], P[1][1] - off[1]};
+        const float seg[2] = {P[1][0] - P[0][0], P[1][1] - P[0][1]};
+        const float len = std::sqrt(seg[0] * seg[0] + seg[1] * seg[1]); // glm length(vec2)
+        const int32_t y1 = std::min((int32_t)std::ceil(H), c.win.y1), x1 = std::min((int32_t)std::ceil(W), c.win.x1); // `y < viewport.height` with y unsigned
+        const uint32_t idx[3] = {i0, i1, i1}; const float pw[3] = {P[0][3], P[1][3], 1.0f};
+        for (int32_t y = std::max(0, c.win.y0); y < y1; y++) {
+            const float yf = ((float)y / H + halfPixel[1]) * 2 - 1;
+            for (int32_t x = std::max(0, c.win.x0); x < x1; x++) {
+                const float xf = ((float)x / W + halfPixel[0]) * 2 - 1;
+                const float pt[2] = {xf, yf};
+                if (!(EdgeFunction2(p00, p01, pt) >= 0 && EdgeFunction2(p11, p10, pt) >= 0 && EdgeFunction2(p10, p00, pt) >= 0 && EdgeFunction2(p01, p11, pt) >= 0)) continue;
+                const float rel[2] = {pt[0] - P[0][0], pt[1] - P[0][1]};
+                const float t = (rel[0] * seg[0] + rel[1] * seg[1]) / (len * len); // glm dot(vec2) = tmp.x + tmp.y
+                const float w[3] = {1 - t, t, 0.0f};
+                const float depth = P[0][2] * t + P[1][2] * (1 - t);
+                Fragment(c, x, y, depth, true, w, pw, idx, provoking, 2);
+            }
+        }
+    }
+}
+
 void ProcessTriangles(DrawContext& c, uint32_t primCount, uint32_t topology) {
     const CpvkDrawState& st = *c.st;
     const CpvkPipelineDesc& d = *c.desc;
@@ -580,13 +660,19 @@ int DrawImpl(const CpvkPipelineDesc* desc, const CpvkDrawState* st, Window win, 
         switch (desc->topology) {
         case 3: primCount = n / 3; break;
         case 4: case 5: primCount = n > 2 ? n - 2 : 0; break;
-        case 0: case 1: case 2: Fail("points/lines: NEXT (SURVEY 8(f) f4)");
+        case 0: primCount = n; break;
+        case 1: primCount = n / 2; break;
+        case 2: primCount = n > 1 ? n - 1 : 0; break;
         default: Fail("topology unsupported (TODO_ERROR, Draw.cpp:663-668)");
         }
         for (uint32_t i = 0; i < st->instanceCount; i++) {
             RunVertexStage(c, st->firstInstance + i, n);
             // vkCmdDraw skips raster without a fragment stage (Draw.cpp:1799-1802)
-            if (c.hasFs) ProcessTriangles(c, primCount, desc->topology);
+            if (c.hasFs) {
+                if (desc->topology == 0) ProcessPoints(c, primCount);
+                else if (desc->topology <= 2) ProcessLines(c, primCount, desc->topology);
+                else ProcessTriangles(c, primCount, desc->topology);
+            }
             c.stats.primitives += primCount;
         }
         if (stats) *stats = c.stats;

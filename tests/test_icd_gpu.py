@@ -97,3 +97,8 @@ def test_icd_clear_attachments_rectangle(built, tmp_path):
     dsub = capi.Attachment(od.ctypes.data + 10 * scene.depth.pitch + 20 * 2, 70, 45, scene.depth.pitch, scene.depth.format)
     assert lib.cpvk_oracle_clear(C.byref(dsub), C.byref(dv), 1) == 0
     assert np.array_equal(oc, gc) and np.array_equal(od, gd)
+
+
+@pytest.mark.parametrize("topology", [scenes.POINT_LIST, scenes.LINE_LIST, scenes.LINE_STRIP])
+def test_icd_points_and_lines(built, tmp_path, topology):
+    check(scenes.random_points_lines(topology=topology, count=50, seed=9, line_width=2.5), tmp_path)

@@ -374,3 +374,44 @@ def test_shader_front_end_breadth(dev, iterations, threshold, scale):
     sc.push_constants = struct.pack("<4fif", 0.3, 0.1, 0.2, 0.05, iterations, threshold)
     st = compare(dev, _with(sc, edit))
     assert st.fragmentsCovered > 1000
+
+
+# ---- points and lines (ProcessPoints / ProcessLines, Draw.cpp:1315-1508) ----
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("perspective", [True, False])
+def test_points(dev, seed, perspective):
+    st = compare(dev, scenes.random_points_lines(topology=scenes.POINT_LIST, count=150, seed=seed, perspective=perspective))
+    assert st.primitives == 150 and st.fragmentsCovered > 1000
+
+
+@pytest.mark.parametrize("topology", [scenes.LINE_LIST, scenes.LINE_STRIP])
+@pytest.mark.parametrize("width", [1.0, 3.0, 7.5])
+def test_lines(dev, topology, width):
+    st = compare(dev, scenes.random_points_lines(topology=topology, count=40, seed=3, line_width=width))
+    assert st.fragmentsCovered > 500
+
+
+def test_lines_unit_w_and_blend(dev):
+    sc = scenes.random_points_lines(topology=scenes.LINE_STRIP, count=50, seed=4, line_width=4.0, perspective=False, depth_fmt=None,
+                                    color_fmt=scenes.R16G16B16A16_SFLOAT)
+    sc.blend = dict(src=6, dst=7, op=0)
+    compare(dev, sc)
+
+
+def test_points_many_tiles_and_chunks(dev):
+    # more than one 256-primitive chunk, several tiles, indexed with vertex reuse
+    sc = scenes.random_points_lines(width=200, height=150, topology=scenes.POINT_LIST, count=700, seed=5)
+    sc.buffers["ib"] = (np.random.RandomState(6).permutation(700) % 350).astype(np.uint16).view(np.uint8).reshape(-1)
+    sc.index_buffer, sc.index_stride = "ib", 2
+    compare(dev, sc)
+
+
+def test_degenerate_line_covers_like_the_reference(dev):
+    """p0 == p1 in x and y: the four quad edges collapse, every edge function is 0 >= 0 and the reference shades the whole
+    viewport (with t = NaN). The conservative pixel box must not clip that."""
+    sc = scenes.random_points_lines(width=40, height=30, topology=scenes.LINE_LIST, count=2, seed=7, perspective=False)
+    vb = sc.buffers["vb"].view(np.float32).reshape(-1, 9).copy()
+    vb[1, 0:2] = vb[0, 0:2]  # same x, y; different z
+    sc.buffers["vb"] = vb.reshape(-1).view(np.uint8)
+    compare(dev, sc)
