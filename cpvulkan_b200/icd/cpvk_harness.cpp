@@ -83,6 +83,8 @@ DECL(vkCmdDrawIndexed, void, VkCommandBuffer, uint32_t, uint32_t, uint32_t, int3
 DECL(vkCmdCopyImageToBuffer, void, VkCommandBuffer, VkImage, VkImageLayout, VkBuffer, uint32_t, const VkBufferImageCopy*)
 DECL(vkCmdDrawIndirect, void, VkCommandBuffer, VkBuffer, VkDeviceSize, uint32_t, uint32_t)
 DECL(vkCmdDrawIndexedIndirect, void, VkCommandBuffer, VkBuffer, VkDeviceSize, uint32_t, uint32_t)
+DECL(vkCmdDrawIndirectCount, void, VkCommandBuffer, VkBuffer, VkDeviceSize, VkBuffer, VkDeviceSize, uint32_t, uint32_t)
+DECL(vkCmdDrawIndexedIndirectCount, void, VkCommandBuffer, VkBuffer, VkDeviceSize, VkBuffer, VkDeviceSize, uint32_t, uint32_t)
 DECL(vkCmdExecuteCommands, void, VkCommandBuffer, uint32_t, const VkCommandBuffer*)
 DECL(vkCmdUpdateBuffer, void, VkCommandBuffer, VkBuffer, VkDeviceSize, VkDeviceSize, const void*)
 DECL(vkCmdFillBuffer, void, VkCommandBuffer, VkBuffer, VkDeviceSize, VkDeviceSize, uint32_t)
@@ -121,7 +123,7 @@ static void LoadIcd() {
     GET(vkCreateDescriptorPool) GET(vkAllocateDescriptorSets) GET(vkUpdateDescriptorSets) GET(vkCreateRenderPass) GET(vkCreateFramebuffer) GET(vkCreateGraphicsPipelines)
     GET(vkCreateCommandPool) GET(vkAllocateCommandBuffers) GET(vkBeginCommandBuffer) GET(vkEndCommandBuffer) GET(vkCmdBeginRenderPass) GET(vkCmdEndRenderPass)
     GET(vkCmdBindPipeline) GET(vkCmdBindDescriptorSets) GET(vkCmdBindVertexBuffers) GET(vkCmdBindIndexBuffer) GET(vkCmdSetViewport) GET(vkCmdSetScissor) GET(vkCmdDraw)
-    GET(vkCmdDrawIndexed) GET(vkCmdCopyImageToBuffer) GET(vkCmdBlitImage) GET(vkCmdCopyImage) GET(vkCmdDrawIndirect) GET(vkCmdDrawIndexedIndirect) GET(vkCmdExecuteCommands) GET(vkCmdUpdateBuffer) GET(vkCmdFillBuffer) GET(vkCmdClearAttachments) GET(vkCreateFence) GET(vkResetFences) GET(vkWaitForFences) GET(vkQueueSubmit) GET(vkDeviceWaitIdle)
+    GET(vkCmdDrawIndexed) GET(vkCmdCopyImageToBuffer) GET(vkCmdBlitImage) GET(vkCmdCopyImage) GET(vkCmdDrawIndirect) GET(vkCmdDrawIndexedIndirect) GET(vkCmdDrawIndirectCount) GET(vkCmdDrawIndexedIndirectCount) GET(vkCmdExecuteCommands) GET(vkCmdUpdateBuffer) GET(vkCmdFillBuffer) GET(vkCmdClearAttachments) GET(vkCreateFence) GET(vkResetFences) GET(vkWaitForFences) GET(vkQueueSubmit) GET(vkDeviceWaitIdle)
 }
 
 static std::vector<uint8_t> ReadFile(const std::string& p) {
@@ -218,9 +220,10 @@ int main(int argc, char** argv) {
     const std::string sceneDir = argv[1], outDir = argv[2];
     int frames = 1;
     for (int i = 3; i + 1 < argc; i++) if (!strcmp(argv[i], "--frames")) frames = atoi(argv[i + 1]);
-    bool indirect = false, secondary = false, updateBuffers = false; int clearRect[4] = {0, 0, 0, 0};
+    bool indirect = false, indirectCount = false, secondary = false, updateBuffers = false; int clearRect[4] = {0, 0, 0, 0};
     for (int i = 3; i < argc; i++) {
         if (!strcmp(argv[i], "--indirect")) indirect = true;
+        if (!strcmp(argv[i], "--indirect-count")) indirect = indirectCount = true; // the draw count (1, capped at 3) is word 0 of the same buffer
         if (!strcmp(argv[i], "--secondary")) secondary = true;
         if (!strcmp(argv[i], "--update-buffers")) updateBuffers = true;
         if (!strcmp(argv[i], "--clear-rect") && i + 4 < argc) for (int k = 0; k < 4; k++) clearRect[k] = atoi(argv[i + 1 + k]);
@@ -379,6 +382,7 @@ int main(int argc, char** argv) {
         indirectBuf = app.MakeBuffer(96, VK_BUFFER_USAGE_INDIRECT_BUFFER_BIT, &indirectMem);
         uint32_t* w; VK(vkMapMemory(app.device, indirectMem, 0, 96, 0, (void**)&w));
         for (int i = 0; i < 24; i++) w[i] = 0x7FFFFFFFu;
+        w[0] = 1;
         if (sc.indexStride) { w[8] = sc.count; w[9] = sc.instances; w[10] = sc.first; w[11] = (uint32_t)sc.vertexOffset; w[12] = sc.firstInstance; }
         else { w[8] = sc.count; w[9] = sc.instances; w[10] = sc.first; w[11] = sc.firstInstance; }
         vkUnmapMemory(app.device, indirectMem);
@@ -402,9 +406,11 @@ int main(int argc, char** argv) {
     VkRect2D scissor{{0, 0}, {sc.width, sc.height}}; vkCmdSetScissor(rec, 0, 1, &scissor);
     if (sc.indexStride) {
         vkCmdBindIndexBuffer(rec, bufs.at(sc.indexBuffer), 0, sc.indexStride == 2 ? VK_INDEX_TYPE_UINT16 : sc.indexStride == 4 ? VK_INDEX_TYPE_UINT32 : VK_INDEX_TYPE_UINT8_EXT);
-        if (indirect) vkCmdDrawIndexedIndirect(rec, indirectBuf, 32, 1, 32);
+        if (indirectCount) vkCmdDrawIndexedIndirectCount(rec, indirectBuf, 32, indirectBuf, 0, 3, 32);
+        else if (indirect) vkCmdDrawIndexedIndirect(rec, indirectBuf, 32, 1, 32);
         else vkCmdDrawIndexed(rec, sc.count, sc.instances, sc.first, sc.vertexOffset, sc.firstInstance);
-    } else if (indirect) vkCmdDrawIndirect(rec, indirectBuf, 32, 1, 32);
+    } else if (indirectCount) vkCmdDrawIndirectCount(rec, indirectBuf, 32, indirectBuf, 0, 3, 32);
+    else if (indirect) vkCmdDrawIndirect(rec, indirectBuf, 32, 1, 32);
     else vkCmdDraw(rec, sc.count, sc.instances, sc.first, sc.firstInstance);
     if (clearRect[2] > 0) { // vkCmdClearAttachments (Draw.cpp:2226-2348) after the draw, inside the pass
         VkClearAttachment ca[2]; uint32_t nca = 1;

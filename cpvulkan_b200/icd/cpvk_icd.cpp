@@ -679,6 +679,27 @@ VKFN(void) CmdDrawIndexedIndirect(VkCommandBuffer cb, VkBuffer buffer, VkDeviceS
         }
     });
 }
+// Indirect-count draws (Draw.cpp:1998-2030): the number of draws comes from a second buffer, capped by maxDrawCount.
+VKFN(void) CmdDrawIndirectCount(VkCommandBuffer cb, VkBuffer buffer, VkDeviceSize offset, VkBuffer countBuffer, VkDeviceSize countOffset, uint32_t maxDrawCount, uint32_t stride) {
+    auto* b = reinterpret_cast<Buffer*>(buffer); auto* cbuf = reinterpret_cast<Buffer*>(countBuffer);
+    RECORD(cb)([=](Device& d) {
+        uint32_t count = 0; CU_CHECK(cpvk_cuda_mem_download(d.cuda, &count, cbuf->address(countOffset), 4));
+        for (uint32_t j = 0; j < std::min(count, maxDrawCount); j++) {
+            VkDrawIndirectCommand c; CU_CHECK(cpvk_cuda_mem_download(d.cuda, &c, b->address(offset + (VkDeviceSize)j * stride), sizeof c));
+            ExecDraw(d, c.vertexCount, c.instanceCount, c.firstVertex, 0, c.firstInstance, false);
+        }
+    });
+}
+VKFN(void) CmdDrawIndexedIndirectCount(VkCommandBuffer cb, VkBuffer buffer, VkDeviceSize offset, VkBuffer countBuffer, VkDeviceSize countOffset, uint32_t maxDrawCount, uint32_t stride) {
+    auto* b = reinterpret_cast<Buffer*>(buffer); auto* cbuf = reinterpret_cast<Buffer*>(countBuffer);
+    RECORD(cb)([=](Device& d) {
+        uint32_t count = 0; CU_CHECK(cpvk_cuda_mem_download(d.cuda, &count, cbuf->address(countOffset), 4));
+        for (uint32_t j = 0; j < std::min(count, maxDrawCount); j++) {
+            VkDrawIndexedIndirectCommand c; CU_CHECK(cpvk_cuda_mem_download(d.cuda, &c, b->address(offset + (VkDeviceSize)j * stride), sizeof c));
+            ExecDraw(d, c.indexCount, c.instanceCount, c.firstIndex, c.vertexOffset, c.firstInstance, true);
+        }
+    });
+}
 // Secondary command buffers (CommandBuffer.cpp:704-731): their commands run in place, on the same device state.
 VKFN(void) CmdExecuteCommands(VkCommandBuffer cb, uint32_t n, const VkCommandBuffer* buffers) {
     std::vector<CommandBuffer*> v; for (uint32_t i = 0; i < n; i++) v.push_back(Unwrap<CommandBuffer>(buffers[i]));
@@ -864,7 +885,8 @@ const Entry kEntries[] = {
     E(CreateGraphicsPipelines), E(DestroyPipeline), E(CreateCommandPool), E(DestroyCommandPool), E(AllocateCommandBuffers), E(FreeCommandBuffers),
     E(BeginCommandBuffer), E(EndCommandBuffer), E(ResetCommandBuffer), E(CmdBindPipeline), E(CmdSetViewport), E(CmdSetScissor), E(CmdBindDescriptorSets),
     E(CmdBindVertexBuffers), E(CmdBindIndexBuffer), E(CmdPushConstants), E(CmdBeginRenderPass), E(CmdNextSubpass), E(CmdEndRenderPass), E(CmdDraw), E(CmdDrawIndexed),
-    E(CmdDrawIndirect), E(CmdDrawIndexedIndirect), E(CmdExecuteCommands), E(CmdFillBuffer), E(CmdUpdateBuffer), E(CmdClearDepthStencilImage), E(CmdClearAttachments),
+    E(CmdDrawIndirect), E(CmdDrawIndexedIndirect), E(CmdDrawIndirectCount), E(CmdDrawIndexedIndirectCount),
+    {"vkCmdDrawIndirectCountKHR", reinterpret_cast<PFN_vkVoidFunction>(CmdDrawIndirectCount)}, {"vkCmdDrawIndexedIndirectCountKHR", reinterpret_cast<PFN_vkVoidFunction>(CmdDrawIndexedIndirectCount)}, E(CmdExecuteCommands), E(CmdFillBuffer), E(CmdUpdateBuffer), E(CmdClearDepthStencilImage), E(CmdClearAttachments),
     E(CmdPipelineBarrier), E(CmdCopyBuffer), E(CmdCopyImage), E(CmdCopyBufferToImage), E(CmdCopyImageToBuffer), E(CmdBlitImage), E(CmdClearColorImage),
     E(CreateFence), E(DestroyFence), E(ResetFences), E(GetFenceStatus), E(WaitForFences), E(CreateSemaphore), E(DestroySemaphore), E(QueueSubmit),
     E(GetDeviceProcAddr), E(GetInstanceProcAddr),

@@ -67,7 +67,7 @@ def test_icd_blit_and_copy_after_the_render_pass(built, tmp_path, w, h, fmt, fil
     assert np.array_equal(info["blit"], dst)
 
 
-@pytest.mark.parametrize("flags", [("--indirect",), ("--secondary",), ("--update-buffers",), ("--indirect", "--secondary", "--update-buffers")],
+@pytest.mark.parametrize("flags", [("--indirect",), ("--indirect-count",), ("--secondary",), ("--update-buffers",), ("--indirect", "--secondary", "--update-buffers")],
                          ids=lambda f: "+".join(x.strip("-") for x in f))
 @pytest.mark.parametrize("indexed", [False, True])
 def test_icd_other_ways_to_issue_the_same_draw(built, tmp_path, flags, indexed):
