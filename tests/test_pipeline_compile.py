@@ -44,10 +44,15 @@ def test_reference_aborts_are_refused(built):
     lib, rc, _, _ = compile_only(scenes.draw_cube(32, 32), wire)
     assert rc == capi.E_UNSUPPORTED
 
-    def points(d):
+    def adjacency(d):
+        d.topology = 6
+    lib, rc, _, _ = compile_only(scenes.draw_cube(32, 32), adjacency)
+    assert rc == capi.E_UNSUPPORTED and b"adjacency" in lib.cpvk_cuda_last_error()
+
+    def points(d):  # points and lines are built (ProcessPoints / ProcessLines)
         d.topology = 0
     lib, rc, _, _ = compile_only(scenes.draw_cube(32, 32), points)
-    assert rc == capi.E_UNSUPPORTED
+    assert rc == 0
 
 
 def test_malformed_spirv_is_an_error(built):
