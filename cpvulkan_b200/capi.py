@@ -249,5 +249,11 @@ def load_oracle():
     lib.cpvk_oracle_float_to_half.restype = C.c_uint16
     lib.cpvk_oracle_half_to_float.argtypes = [C.c_uint16]
     lib.cpvk_oracle_half_to_float.restype = f32
+    lib.cpvk_oracle_format_row.argtypes = [C.c_uint32, C.c_void_p]
+    lib.cpvk_oracle_format_row.restype = C.c_int
+    lib.cpvk_oracle_image_layout.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
+    lib.cpvk_oracle_image_layout.restype = C.c_int
+    lib.cpvk_oracle_pixel_offset.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32]
+    lib.cpvk_oracle_pixel_offset.restype = C.c_uint64
     _oracle_lib = lib
     return lib

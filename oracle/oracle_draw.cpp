@@ -777,6 +777,40 @@ void cpvk_oracle_sample(const CpvkDescriptor* d, const float* coords, uint32_t c
         std::memcpy(out + 4 * (size_t)i, r.v, 16);
     }
 }
+// Full format-table row in the column order oracle/ref_formats_check.cpp prints the reference's FormatInformation:
+// type total element base v0 v1 v2 v3 b0 b1 b2 b3 (Normal: byte offsets; Packed: bit offsets + widths; DepthStencil:
+// depth/stencil offsets). FmtType here is {Invalid, Normal, Packed, DepthStencil}; the reference's FormatType starts
+// at Normal = 0 (Formats.h:4-12), hence the -1.
+int cpvk_oracle_format_row(uint32_t format, uint32_t out[12]) {
+    const FormatInfo fi = GetFormatInformation(format);
+    for (int i = 0; i < 12; i++) out[i] = 0;
+    if (fi.type == FmtType::Invalid) return CPVK_E_UNSUPPORTED;
+    out[0] = (uint32_t)fi.type - 1u; out[1] = fi.totalSize; out[2] = fi.elementSize; out[3] = (uint32_t)fi.base;
+    if (fi.type == FmtType::Normal) { for (int c = 0; c < 4; c++) out[4 + c] = fi.offset[c]; }
+    else if (fi.type == FmtType::Packed) { for (int c = 0; c < 4; c++) { out[4 + c] = fi.offset[c]; out[8 + c] = fi.bits[c]; } }
+    else { out[4] = fi.depthOffset; out[5] = fi.stencilOffset; }
+    return 0;
+}
+// GetNormalImageSize (Formats.cpp:455-483) + GetImagePixelOffset (:583-587): linear images, Stride = texel * width, mip
+// levels back to back inside a layer, layers back to back. out = {total, layerSize, pixelSize, then per level
+// offset, stride, planeSize, width, height, depth}.
+int cpvk_oracle_image_layout(uint32_t format, uint32_t width, uint32_t height, uint32_t depth, uint32_t layers, uint32_t mips, uint64_t* out) {
+    const FormatInfo fi = GetFormatInformation(format);
+    if (fi.type == FmtType::Invalid) return CPVK_E_UNSUPPORTED;
+    uint64_t layerSize = 0;
+    for (uint32_t i = 0; i < mips; i++) {
+        uint64_t* l = out + 3 + 6 * (size_t)i;
+        l[0] = layerSize; l[1] = (uint64_t)fi.totalSize * width; l[2] = l[1] * height; l[3] = width; l[4] = height; l[5] = depth;
+        layerSize += l[2] * depth;
+        width = width / 2 > 1u ? width / 2 : 1u; height = height / 2 > 1u ? height / 2 : 1u; depth = depth / 2 > 1u ? depth / 2 : 1u;
+    }
+    out[0] = layerSize * layers; out[1] = layerSize; out[2] = fi.totalSize;
+    return 0;
+}
+uint64_t cpvk_oracle_pixel_offset(const uint64_t* layout, int32_t i, int32_t j, int32_t k, uint32_t level, uint32_t layer) {
+    const uint64_t* l = layout + 3 + 6 * (size_t)level;
+    return layout[1] * layer + l[0] + (uint64_t)(int64_t)k * l[2] + (uint64_t)(int64_t)j * l[1] + (uint64_t)(int64_t)i * layout[2];
+}
 uint16_t cpvk_oracle_float_to_half(float v) { return FloatToHalf(v); }
 float cpvk_oracle_half_to_float(uint16_t v) { return HalfToFloat(v); }
 
