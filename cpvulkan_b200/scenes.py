@@ -58,7 +58,7 @@ class Image:
 
     @property
     def nbytes(self):
-        return self.pitch * self.height
+        return getattr(self, "chain_bytes", self.pitch * self.height)  # chain_bytes: a whole mip chain, levels back to back
 
 
 class Texture:
@@ -409,6 +409,52 @@ def overdraw_quads(width=7680, height=4320, quads=2000, tex_size=1024, seed=42, 
         s.blend = dict(src=BF_SRC_ALPHA, dst=BF_ONE_MINUS_SRC_ALPHA, op=BO_ADD)
     s.count = 6 * quads
     _render_targets(s, width, height, color_fmt, None, (0.0, 0.0, 0.0, 0.0))
+    return s
+
+
+def sampler_matrix(width=96, height=64, tex_fmt=R8G8B8A8_UNORM, address=(REPEAT, REPEAT), mag=LINEAR, min_=LINEAR, mipmap=0,
+                   min_lod=0.0, border=0, tex_size=(8, 4), levels=3, seed=3):
+    """One opaque full-screen quad whose uv runs from -1.5 to 2.5 over a small mip-mapped texture, written to an RGBA32F
+    target so every sampled float is visible. The sampler state (address modes per axis, mag / min filter, mipmap mode,
+    border colour) and the mip chain (levels back to back, Formats.cpp:455-483) are patched into the descriptor on every
+    backend; min_lod > 0 forces the minification path without touching the shader: lambda = clamp(0 + bias, minLod, maxLod)
+    (GlslFunctions.cpp:598-654)."""
+    s = overdraw_quads(width, height, quads=1, tex_size=8, blend=False, color_fmt=R32G32B32A32_SFLOAT)
+    s.name = "sampler_matrix"
+    vb = s.buffers["vb"].view(np.float32).reshape(-1, 6).copy()
+    vb[:, 4:6] = vb[:, 4:6] - 1.5  # 0 / 4 -> -1.5 / 2.5
+    s.buffers["vb"] = vb.view(np.uint8).reshape(-1)
+    rng = np.random.RandomState(seed)
+    texel = TEXEL_SIZE[tex_fmt]
+    w, h = tex_size
+    chain, dims = [], []
+    for _ in range(levels):
+        if tex_fmt == R32G32B32A32_SFLOAT:
+            data = rng.uniform(-2.0, 2.0, size=(h, w, 4)).astype(np.float32).view(np.uint8).reshape(-1)
+        else:
+            data = rng.randint(0, 256, size=h * w * texel, dtype=np.uint8)
+        chain.append(data); dims.append((w, h))
+        w, h = max(w // 2, 1), max(h // 2, 1)
+    img = Image(tex_fmt, tex_size[0], tex_size[1], data=np.concatenate(chain))
+    img.chain_bytes = sum(len(c) for c in chain)
+    s.textures = [Texture(1, img, mag, address[0])]
+
+    def patch(m):
+        for i in range(m.state.descriptorCount):
+            d = m.state.descriptors[i]
+            if d.type != capi.DESC_IMAGE:
+                continue
+            base, off = d.levels[0].address, 0
+            d.levelCount = levels
+            for l, (lw, lh) in enumerate(dims):
+                d.levels[l] = capi.MipLevel(base + off, lw, lh, 1, 0)
+                off += lw * lh * texel
+            sm = d.sampler
+            sm.magFilter, sm.minFilter, sm.mipmapMode = mag, min_, mipmap
+            sm.addressModeU, sm.addressModeV = address
+            sm.borderColor = border
+            sm.minLod, sm.maxLod = min_lod, 1000.0
+    s.mutate = patch
     return s
 
 

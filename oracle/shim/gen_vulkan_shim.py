@@ -114,6 +114,9 @@ typedef struct VkExtent3D { uint32_t width, height, depth; } VkExtent3D;
 typedef struct VkOffset2D { int32_t x, y; } VkOffset2D;
 typedef struct VkOffset3D { int32_t x, y, z; } VkOffset3D;
 typedef struct VkRect2D { VkOffset2D offset; VkExtent2D extent; } VkRect2D;
+typedef struct VkViewport { float x, y, width, height, minDepth, maxDepth; } VkViewport;
+#define VK_KHR_swapchain 1
+typedef struct VkSwapchainKHR_T* VkSwapchainKHR;
 typedef struct VkMemoryRequirements { VkDeviceSize size, alignment; uint32_t memoryTypeBits; } VkMemoryRequirements;
 typedef struct VkImageSubresource { VkImageAspectFlags aspectMask; uint32_t mipLevel, arrayLayer; } VkImageSubresource;
 typedef struct VkSubresourceLayout { VkDeviceSize offset, size, rowPitch, arrayPitch, depthPitch; } VkSubresourceLayout;

@@ -1,7 +1,7 @@
 """Generates tests/golden/ref_*.{txt,npz}: outputs of the REFERENCE's own code for the pieces of the path that execute
-in this image — CPVulkanBase/Formats.cpp (format table, image layout, GetImagePixelOffset) and CPVulkanBase/FloatFormat.h
-(half <-> float, the codec behind R16G16B16A16_SFLOAT) — compiled in place into oracle/_ref/formats_check
-(oracle/Makefile, oracle/ref_formats_check.cpp). Run in the build container (needs /root/reference):
+in this image — CPVulkanBase/Formats.cpp (format table, image layout, GetImagePixelOffset), CPVulkanBase/FloatFormat.h
+(half <-> float, the codec behind R16G16B16A16_SFLOAT) and CPVulkan/ImageSampler.cpp (the texture sampler) — compiled in
+place into oracle/_ref/formats_check and oracle/_ref/sampler_check (oracle/Makefile, oracle/ref_*_check.cpp). Run in the build container (needs /root/reference):
 
     make -C oracle ref && python tests/golden/make_ref_golden.py
 
@@ -40,7 +40,57 @@ def tohalf_inputs():
     return np.unique(pats)
 
 
+SAMPLER_CHECK = os.path.join(os.path.dirname(CHECK), "sampler_check")
+
+
+def sampler_inputs():
+    """A 3-level RGBA32F mip chain (8x4, 4x2, 2x1) of awkward floats, sampler configurations covering every address mode,
+    both filters on the magnification and minification paths, both mipmap modes, fractional LODs, three border colours and
+    mixed U/V modes, and coordinates that include negatives, exact 0 / 1, texel centres and edges."""
+    rng = np.random.RandomState(20261017)
+    levels = []
+    for w, h in ((8, 4), (4, 2), (2, 1)):
+        t = (rng.uniform(-4.0, 4.0, size=(h, w, 4)) * rng.choice([1.0, 1e-3, 257.0], size=(h, w, 4))).astype(np.float32)
+        levels.append(t)
+    NEAREST, LINEAR = 0, 1
+    cfg = []
+    for mode in range(5):
+        for filt in (NEAREST, LINEAR):
+            for border in ((0, 2, 4) if mode == 3 else (0,)):
+                cfg.append((filt, filt, 0, mode, mode, border, 0.0))            # lod <= 0: magnification filter, level 0
+    for u_mode, v_mode in ((0, 2), (1, 3), (4, 0), (3, 1)):
+        cfg.append((LINEAR, NEAREST, 0, u_mode, v_mode, 2, 0.0))
+    for lod in (0.25, 0.5, 1.0, 1.5, 2.0, 3.7):
+        for mip in (0, 1):
+            for filt in (NEAREST, LINEAR):
+                for mode in (0, 1, 2):
+                    cfg.append((1 - filt, filt, mip, mode, mode, 0, lod))       # lod > 0: minification filter, mip selection
+    cfg = np.array(cfg, dtype=[("mag", "<u4"), ("min", "<u4"), ("mipmap", "<u4"), ("au", "<u4"), ("av", "<u4"), ("border", "<u4"), ("lod", "<f4")])
+    us = np.array([-1.25, -0.5 / 8, 0.0, 0.5 / 8, 0.37, 1 - 1e-7, 1.0, 2.3], dtype=np.float32)
+    grid = np.array([[u, v] for u in us for v in us], dtype=np.float32)
+    coords = np.concatenate([grid, rng.uniform(-2.0, 3.0, size=(64, 2)).astype(np.float32)])
+    return levels, cfg, coords
+
+
+def sampler_golden():
+    import tempfile
+    levels, cfg, coords = sampler_inputs()
+    with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+        f.write(np.array([len(levels), len(cfg), len(coords)], dtype="<u4").tobytes())
+        for t in levels:
+            f.write(np.array([t.shape[1], t.shape[0]], dtype="<u4").tobytes())
+            f.write(t.tobytes())
+        f.write(cfg.tobytes())
+        f.write(coords.tobytes())
+        f.flush()
+        out = subprocess.run([SAMPLER_CHECK, f.name], stdout=subprocess.PIPE, text=True, check=True).stdout
+    bits = np.array([[int(x) for x in l.split()] for l in out.splitlines()], dtype=np.uint32).reshape(len(cfg), len(coords), 4)
+    np.savez_compressed(os.path.join(HERE, "ref_sampler.npz"), level0=levels[0], level1=levels[1], level2=levels[2], configs=cfg, coords=coords, result_bits=bits)
+    print("sampler: %d configurations x %d coordinates" % (len(cfg), len(coords)))
+
+
 def main():
+    sampler_golden()
     open(os.path.join(HERE, "ref_formats.txt"), "w").write(run("formats"))
     open(os.path.join(HERE, "ref_layout.txt"), "w").write(run("layout"))
     half = np.array([int(l.split()[2]) for l in run("half").splitlines()], dtype=np.uint32)

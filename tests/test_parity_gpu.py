@@ -415,3 +415,22 @@ def test_degenerate_line_covers_like_the_reference(dev):
     vb[1, 0:2] = vb[0, 0:2]  # same x, y; different z
     sc.buffers["vb"] = vb.reshape(-1).view(np.uint8)
     compare(dev, sc)
+
+
+# Sampler state matrix (ImageSampler.cpp:12-38, :461-673): the oracle's sampler is pinned bit for bit to the reference's own
+# compiled ImageSampler.cpp (tests/test_reference_sampler.py); here the CUDA sampler is held to the oracle over the same state
+# space — every address mode (mixed per axis), both filters on the magnification and minification paths, both mipmap modes
+# with fractional LODs over a 3-level chain, border colours — for an 8-bit UNORM and a raw float texture.
+SAMPLER_STATES = [dict(address=(a, a), mag=f, min_=f) for a in range(5) for f in (scenes.NEAREST, scenes.LINEAR)]
+SAMPLER_STATES += [dict(address=(3, 3), mag=scenes.LINEAR, min_=scenes.LINEAR, border=b) for b in (2, 4)]
+SAMPLER_STATES += [dict(address=(0, 2), mag=scenes.LINEAR, min_=scenes.NEAREST), dict(address=(1, 3), mag=scenes.NEAREST, min_=scenes.LINEAR, border=4),
+                   dict(address=(4, 0), mag=scenes.LINEAR, min_=scenes.LINEAR)]
+SAMPLER_STATES += [dict(address=(a, a), mag=1 - f, min_=f, mipmap=m, min_lod=lod)
+                   for a, f, m, lod in ((0, 1, 0, 0.25), (0, 1, 0, 0.5), (2, 1, 0, 1.5), (1, 0, 0, 2.0), (0, 1, 1, 0.25), (2, 1, 1, 1.0),
+                                        (1, 1, 1, 1.5), (0, 0, 1, 0.75), (3, 1, 1, 3.7), (4, 1, 1, 1.25))]
+
+
+@pytest.mark.parametrize("state", SAMPLER_STATES, ids=lambda s: "-".join("%s" % (v,) for v in s.values()).replace(" ", ""))
+@pytest.mark.parametrize("tex_fmt", [scenes.R8G8B8A8_UNORM, scenes.R32G32B32A32_SFLOAT])
+def test_sampler_state_matrix(dev, state, tex_fmt):
+    compare(dev, scenes.sampler_matrix(tex_fmt=tex_fmt, **state))
