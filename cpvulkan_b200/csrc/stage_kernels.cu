@@ -285,6 +285,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     cpvk_u8* sHit = cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + warp * CPVK_CHUNK; // [warps][CPVK_CHUNK] chunk-local ids
     unsigned short* sFrag = reinterpret_cast<unsigned short*>(cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * CPVK_CHUNK)
                             + warp * CPVK_FRAG_CAP;                                                  // [warps][CPVK_FRAG_CAP]
+    cpvk_u8* sMask = cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * (CPVK_CHUNK + CPVK_FRAG_CAP * 2); // [CPVK_CHUNK] warp regions a bbox meets
 
     // ---- the fragment wrapper epilogue (PipelineCompiler.cpp:1061-1080) on the shared tile; returns "colour written" ----
     auto rop = [&](int px, int py, float fragDepth, bool front, const CpvkFragOut& out) -> bool {
@@ -577,7 +578,17 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             const uint4* sp = reinterpret_cast<const uint4*>(p.setups + stagedPrim);
             #pragma unroll
             for (int j = 0; j < 6; j++) sQ[j * CPVK_CHUNK + threadIdx.x] = __ldg(sp + j);
-            sBB[threadIdx.x] = __ldg(reinterpret_cast<const uint2*>(p.bboxes + stagedPrim));
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(p.bboxes + stagedPrim));
+            sBB[threadIdx.x] = b;
+            // which of the eight 16x8 warp regions the bbox meets (bit = warp index), worked out once per triangle here
+            // instead of once per triangle per warp in the compaction scan below
+            const int bx0 = (short)(b.x & 0xFFFFu), by0 = (short)(b.x >> 16), bx1 = (short)(b.y & 0xFFFFu), by1 = (short)(b.y >> 16);
+            cpvk_u32 xb = 0, m = 0;
+            #pragma unroll
+            for (int wx = 0; wx < 2; wx++) { const int a = tileX0 + wx * 16; if (bx0 < min(a + 16, x1) && bx1 > a) xb |= 1u << wx; }
+            #pragma unroll
+            for (int wy = 0; wy < 4; wy++) { const int a = tileY0 + wy * 8; if (by0 < min(a + 8, y1) && by1 > a) m |= xb << (2 * wy); }
+            sMask[threadIdx.x] = (cpvk_u8)m;
         }
         __syncthreads();
         if (regionLive) {
@@ -586,12 +597,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             #pragma unroll 1
             for (int base = 0; base < n; base += 32) {
                 const int li = base + lane;
-                bool hit = false;
-                if (li < n) {
-                    const uint2 b = sBB[li];
-                    const int bx0 = (short)(b.x & 0xFFFFu), by0 = (short)(b.x >> 16), bx1 = (short)(b.y & 0xFFFFu), by1 = (short)(b.y >> 16);
-                    hit = bx0 < rx1 && bx1 > rx0 && by0 < ry1 && by1 > ry0;
-                }
+                const bool hit = li < n && ((sMask[li] >> warp) & 1u) != 0u;
                 const cpvk_u32 m = __ballot_sync(0xFFFFFFFFu, hit);
                 if (hit) sHit[nHits + __popc(m & ((1u << lane) - 1u))] = (cpvk_u8)li;
                 nHits += __popc(m);
@@ -632,19 +638,27 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                     const int bx = small ? cx0 - tileX0 : 0, by = small ? cy0 - tileY0 : 0;
                     if (maxW * maxH * 5 <= maxCand * 8) {
                         // similar rectangles across the lanes: all lanes walk one maxW x maxH window in lockstep, which
-                        // hoists the row terms out of the pixel loop (candidate numbering stays row-major per lane)
-                        int c = 0;
+                        // hoists the row terms out of the pixel loop. A row's results are collected at the warp-uniform bit
+                        // xx, trimmed to the lane's own width and appended at yy * cw, so candidate numbering stays
+                        // row-major per lane.
+                        const cpvk_u32 rowMask = small ? ((1u << cw) - 1u) : 0u; // cw <= 16
+                        const int rows = small ? ch : 0;
+                        int shift = 0;
                         #pragma unroll 1
                         for (int yy = 0; yy < maxH; yy++) {
-                            const bool rowIn = small && yy < ch;
+                            const bool rowIn = yy < rows;
                             const float yf = sYf[by + (rowIn ? yy : 0)];
                             const float b0 = (yf - e0ay) * e0dx, b1 = (yf - e1ay) * e1dx, b2 = (yf - e2ay) * e2dx;
-                            #pragma unroll 1
-                            for (int xx = 0; xx < maxW; xx++) {
-                                const float xf = sXf[bx + xx]; // bx + xx <= 46: stays inside the xf/yf/lut block
+                            cpvk_u32 rowCov = 0, bit = 1u;
+                            const float* xp = sXf + bx; // bx + xx <= 46: stays inside the xf/yf/lut block
+                            const float* const xe = xp + maxW;
+                            #pragma unroll 2
+                            for (; xp != xe; xp++, bit <<= 1) {
+                                const float xf = *xp;
                                 const bool out = (xf - e0ax) * e0dy < b0 || (xf - e1ax) * e1dy < b1 || (xf - e2ax) * e2dy < b2;
-                                if (rowIn && xx < cw) { cov |= (out ? 0u : 1u) << c; c++; }
+                                if (!out) rowCov |= bit;
                             }
+                            if (rowIn) { cov |= (rowCov & rowMask) << shift; shift += cw; }
                         }
                     } else {
                         int xx = 0, yy = 0;
@@ -660,8 +674,31 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                         }
                     }
                 }
-                const cpvk_u32 largeMask = __ballot_sync(0xFFFFFFFFu, valid && !small);
-                cpvk_u32 todo = __ballot_sync(0xFFFFFFFFu, valid);
+                // A large triangle whose three edge functions cannot all be >= 0 anywhere in its candidate rectangle is dropped
+                // before the warp walks it (a full-screen quad's second triangle misses half of the regions its bbox meets).
+                // Exact, not conservative-by-epsilon: w = fl(A(x) - B(y)) with A(x) = fl(fl(xf - ax) * dy), B(y) = fl(fl(yf - ay)
+                // * dx); xf, yf are monotone in x, y and every rounded operation is monotone, so over the rectangle w is at
+                // most fl(max(A(x_first), A(x_last)) - min(B(y_first), B(y_last))) — if that is < 0, every pixel fails this
+                // edge's `w < 0` test. Only taken when the edge constants are finite and small enough that no product can
+                // overflow (otherwise an inf * 0 = NaN in the interior, which the reference accepts, could hide from the corners).
+                bool large = valid && !small;
+                if (__any_sync(0xFFFFFFFFu, large)) {
+                    if (large) {
+                        const float xa = sXf[cx0 - tileX0], xb = sXf[cx0 + cw - 1 - tileX0], ya = sYf[cy0 - tileY0], yb = sYf[cy0 + ch - 1 - tileY0];
+                        bool reject = false;
+                        #pragma unroll
+                        for (int e = 0; e < 3; e++) {
+                            const uint4 q = sQ[e * CPVK_CHUNK + kt];
+                            const float ax = __uint_as_float(q.x), ay = __uint_as_float(q.y), dy = __uint_as_float(q.z), dx = __uint_as_float(q.w);
+                            const bool bounded = fabsf(ax) <= 1e15f && fabsf(ay) <= 1e15f && fabsf(dy) <= 1e15f && fabsf(dx) <= 1e15f;
+                            const float aMax = fmaxf((xa - ax) * dy, (xb - ax) * dy), bMin = fminf((ya - ay) * dx, (yb - ay) * dx);
+                            reject = reject || (bounded && aMax < bMin);
+                        }
+                        large = !reject;
+                    }
+                }
+                const cpvk_u32 largeMask = __ballot_sync(0xFFFFFFFFu, large);
+                cpvk_u32 todo = __ballot_sync(0xFFFFFFFFu, small || large);
                 // Covered candidates of the small triangles are written, triangle after triangle (= API order), to this
                 // warp's fragment list in shared memory: 16 bits each = chunk-local triangle | x, y inside the warp region.
                 // The list is then shaded 32 fragments at a time. A large triangle ends the segment and is rasterised by

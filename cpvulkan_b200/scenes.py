@@ -539,6 +539,38 @@ def random_triangles(width=256, height=192, tris=200, seed=1, depth_fmt=D32_SFLO
     return s
 
 
+def large_triangles(width=200, height=136, tris=60, seed=1, scale="mixed", blend=True):
+    """Large triangles (bbox far beyond a 16x8 warp region) whose edges cut through regions at every angle: slivers, screen-
+    sized triangles with one vertex far outside, both windings, and — with scale="extreme" — vertices at 1e6 .. 1e30, +-inf
+    and NaN, where the raster kernel's whole-region rejection must step aside (oracle semantics: NaN edge values pass the
+    `w < 0` test, Draw.cpp:879-903). Blended so that every covered fragment changes the result."""
+    # extreme vertices give NaN colours, whose payload bits differ between x86 and the GPU: an UNORM target packs them to 0
+    s = random_triangles(width=width, height=height, tris=tris, seed=seed, depth_fmt=None,
+                         color_fmt=R8G8B8A8_UNORM if scale == "extreme" else R32G32B32A32_SFLOAT)
+    s.name = "large_triangles_%s" % scale
+    rng = np.random.RandomState(seed + 100)
+    n = 3 * tris
+    xy = rng.uniform(-1.6, 1.6, size=(n, 2)).astype(np.float32)
+    k = np.arange(tris)
+    far = rng.choice([1.0, 1.0, 3.0, 40.0, 1e3], size=tris).astype(np.float32)          # push one vertex of some triangles far out
+    xy[3 * k] *= far[:, None]
+    sliver = k % 5 == 0
+    xy[3 * k[sliver] + 1] = xy[3 * k[sliver]] * np.float32(-1.0) + rng.uniform(-0.02, 0.02, size=(sliver.sum(), 2)).astype(np.float32)
+    if scale == "extreme":
+        big = rng.choice([1e6, 1e12, 1e20, 1e30, np.inf, -np.inf, np.nan], size=tris)
+        pick = rng.randint(0, 3, size=tris)
+        axis = rng.randint(0, 2, size=tris)
+        sel = k % 2 == 0
+        xy[3 * k[sel] + pick[sel], axis[sel]] = big[sel].astype(np.float32)
+    z = rng.uniform(0.0, 1.0, size=(n, 1)).astype(np.float32)
+    pos = np.concatenate([xy, z, np.ones((n, 1), dtype=np.float32)], axis=1).astype(np.float32)
+    col = rng.uniform(0.05, 0.9, size=(n, 4)).astype(np.float32)
+    s.buffers["vb"] = np.concatenate([pos, col], axis=1).astype(np.float32).view(np.uint8).reshape(-1)
+    if blend:
+        s.blend = dict(src=BF_SRC_ALPHA, dst=BF_ONE_MINUS_SRC_ALPHA, op=BO_ADD)
+    return s
+
+
 # ---------------------------------------------------------------------------------------------------
 # export for the Vulkan loader-harness (cpvulkan_b200/icd/cpvk_harness.cpp)
 

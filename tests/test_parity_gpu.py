@@ -434,3 +434,14 @@ SAMPLER_STATES += [dict(address=(a, a), mag=1 - f, min_=f, mipmap=m, min_lod=lod
 @pytest.mark.parametrize("tex_fmt", [scenes.R8G8B8A8_UNORM, scenes.R32G32B32A32_SFLOAT])
 def test_sampler_state_matrix(dev, state, tex_fmt):
     compare(dev, scenes.sampler_matrix(tex_fmt=tex_fmt, **state))
+
+
+# Whole-region rejection of large triangles (k_raster): must never drop a fragment the reference's per-pixel test accepts.
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("scale", ["mixed", "extreme"])
+def test_large_triangle_region_rejection_is_exact(dev, seed, scale):
+    compare(dev, scenes.large_triangles(seed=seed, scale=scale))
+
+
+def test_large_triangles_many_tiles(dev):
+    compare(dev, scenes.large_triangles(width=517, height=389, tris=40, seed=7, scale="extreme"))
