@@ -192,7 +192,15 @@ __global__ void __launch_bounds__(1024) k_bin_scan(CpvkBinArgs a) {
     const cpvk_u32 begin = min(threadIdx.x * per, tiles), end = min(begin + per, tiles);
     if (threadIdx.x == 0) maxShared = 0;
     cpvk_u32 sum = 0, localMax = 0;
-    for (cpvk_u32 i = begin; i < end; i++) { const cpvk_u32 v = a.counts[i]; sum += v; localMax = max(localMax, v); }
+    // runs start at a multiple of `per`: when that is a multiple of four the counts come as 16-byte vectors (a 4K frame is
+    // two loads per thread instead of a chain of eight)
+    const bool vec = (per & 3u) == 0u && (reinterpret_cast<cpvk_u64>(a.counts) & 15u) == 0u;
+    for (cpvk_u32 i = begin; i < end;) {
+        if (vec && i + 4 <= end) {
+            const uint4 v = *reinterpret_cast<const uint4*>(a.counts + i);
+            sum += (v.x + v.y) + (v.z + v.w); localMax = max(max(localMax, max(v.x, v.y)), max(v.z, v.w)); i += 4;
+        } else { const cpvk_u32 v = a.counts[i]; sum += v; localMax = max(localMax, v); i++; }
+    }
     cpvk_u32 x = sum;
     #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const cpvk_u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
@@ -208,7 +216,14 @@ __global__ void __launch_bounds__(1024) k_bin_scan(CpvkBinArgs a) {
     if ((threadIdx.x & 31) == 0) atomicMax(&maxShared, localMax);
     __syncthreads();
     cpvk_u32 run = ((threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u) + x - sum; // exclusive prefix of this thread's run
-    for (cpvk_u32 i = begin; i < end; i++) { a.offsets[i] = run; a.cursors[i] = run; run += a.counts[i]; }
+    for (cpvk_u32 i = begin; i < end;) {
+        if (vec && i + 4 <= end && ((reinterpret_cast<cpvk_u64>(a.offsets) | reinterpret_cast<cpvk_u64>(a.cursors)) & 15u) == 0u) {
+            const uint4 v = *reinterpret_cast<const uint4*>(a.counts + i);
+            const uint4 o = make_uint4(run, run + v.x, run + v.x + v.y, run + v.x + v.y + v.z);
+            *reinterpret_cast<uint4*>(a.offsets + i) = o; *reinterpret_cast<uint4*>(a.cursors + i) = o;
+            run = o.w + v.w; i += 4;
+        } else { a.offsets[i] = run; a.cursors[i] = run; run += a.counts[i]; i++; }
+    }
     if (threadIdx.x == 0) {
         const cpvk_u32 total = warpSums[31], longest = maxShared;
         a.offsets[tiles] = total; a.meta[0] = total; a.meta[1] = longest;

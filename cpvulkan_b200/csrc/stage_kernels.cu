@@ -139,9 +139,17 @@ __device__ __forceinline__ void cpvk_apply_blend(const float s[4], const float d
 
 // Copy `bytes` (a multiple of the texel size) between a global row segment and shared memory, all threads of
 // the CTA cooperating over `rows` rows; 16-byte vectors when both sides allow, else 4-byte words, else bytes.
-__device__ __forceinline__ void cpvk_tile_copy(cpvk_u8* dst, cpvk_u32 dstPitch, const cpvk_u8* src, cpvk_u32 srcPitch, cpvk_u32 bytes, cpvk_u32 rows) {
+// `fullBytes` = bytes of a full-width tile row (a link-time constant per pipeline): when the row is full and everything is
+// 16-byte aligned — every interior tile — the row/column split is a shift instead of a 32-bit division per vector.
+__device__ __forceinline__ void cpvk_tile_copy(cpvk_u8* dst, cpvk_u32 dstPitch, const cpvk_u8* src, cpvk_u32 srcPitch, cpvk_u32 bytes, cpvk_u32 rows, cpvk_u32 fullBytes) {
     const cpvk_u64 align = ((cpvk_u64)dst | (cpvk_u64)src | dstPitch | srcPitch | bytes);
-    if ((align & 15) == 0) {
+    if ((align & 15) == 0 && bytes == fullBytes && (fullBytes & (fullBytes - 1u)) == 0u) {
+        const cpvk_u32 per = fullBytes >> 4; // power of two
+        for (cpvk_u32 i = threadIdx.x; i < per * rows; i += blockDim.x) {
+            const cpvk_u32 r = i / per, c = i & (per - 1u);
+            reinterpret_cast<uint4*>(dst + (cpvk_u64)r * dstPitch)[c] = reinterpret_cast<const uint4*>(src + (cpvk_u64)r * srcPitch)[c];
+        }
+    } else if ((align & 15) == 0) {
         const cpvk_u32 per = bytes >> 4;
         for (cpvk_u32 i = threadIdx.x; i < per * rows; i += blockDim.x) {
             const cpvk_u32 r = i / per, c = i - r * per;
@@ -247,6 +255,12 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
         sYf[j] = ((float)(tileY0 + j) / H + hp) * 2.0f - 1.0f;
     }
     sLut[threadIdx.x] = (float)threadIdx.x / 255.0f; // CPVK_RASTER_THREADS == 256
+    // Unsorted lists always fit one chunk (the host sorts otherwise): fetch this tile's ids now so the load overlaps tile
+    // staging, and park them where the ranking pass below expects them — the staging barrier then covers both.
+    cpvk_u32 firstKey = 0xFFFFFFFFu;
+    if (triangles && !listsSorted) {
+        if (threadIdx.x < listEnd - listBegin) firstKey = __ldg(p.tileLists + listBegin + threadIdx.x);
+    }
     // ---- stage the tile: HBM -> shared, or the packed clear value when a deferred clear is folded into this draw ----
     if (dsUsed) {
         if (lazyMask & 0x100u) {
@@ -255,7 +269,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             cpvk_tile_fill(sDepth, dsTexel, one);
         } else
             cpvk_tile_copy(sDepth, dsPitch, reinterpret_cast<const cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel,
-                           p.ds.rowPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th);
+                           p.ds.rowPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th, dsPitch);
     }
     #pragma unroll
     for (int a = 0; a < CPVK_MAX_COLOR; a++)
@@ -268,10 +282,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                 cpvk_tile_fill(sColor[a], cTexel[a], one);
             } else
                 cpvk_tile_copy(sColor[a], cTexel[a] * CPVK_TILE_W, reinterpret_cast<const cpvk_u8*>(p.color[a].address) + (cpvk_u64)tileY0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a],
-                               p.color[a].rowPitch, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th);
+                               p.color[a].rowPitch, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th, cTexel[a] * CPVK_TILE_W);
         }
-    __syncthreads();
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // warp region (16 wide, 8 tall) clipped to the tile extent
     const int rx0 = tileX0 + (warp & 1) * 16, ry0 = tileY0 + (warp >> 1) * 8;
@@ -285,7 +297,10 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     cpvk_u8* sHit = cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + warp * CPVK_CHUNK; // [warps][CPVK_CHUNK] chunk-local ids
     unsigned short* sFrag = reinterpret_cast<unsigned short*>(cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * CPVK_CHUNK)
                             + warp * CPVK_FRAG_CAP;                                                  // [warps][CPVK_FRAG_CAP]
+    cpvk_u32* sSorted = reinterpret_cast<cpvk_u32*>(cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * CPVK_CHUNK); // [CPVK_CHUNK], aliases sFrag (idle until the chunk is staged)
     cpvk_u8* sMask = cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * (CPVK_CHUNK + CPVK_FRAG_CAP * 2); // [CPVK_CHUNK] warp regions a bbox meets
+    if (triangles && !listsSorted) reinterpret_cast<cpvk_u32*>(sBB)[threadIdx.x] = firstKey; // sKeys of the ranking pass
+    __syncthreads(); // tile, pixel centres, lut and the unsorted ids are staged
 
     // ---- the fragment wrapper epilogue (PipelineCompiler.cpp:1061-1080) on the shared tile; returns "colour written" ----
     auto rop = [&](int px, int py, float fragDepth, bool front, const CpvkFragOut& out) -> bool {
@@ -554,11 +569,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             // one chunk the host skips k_bin_sort and the tile orders its own list here: ids are unique, so each id's
             // rank (number of smaller ids) is its position in API order. Broadcast shared-memory reads, no barriers
             // inside the loop.
-            cpvk_u32* sKeys = reinterpret_cast<cpvk_u32*>(sBB);          // reused before the bboxes are staged
-            cpvk_u32* sSorted = reinterpret_cast<cpvk_u32*>(sQ);         // reused before the records are staged
-            const cpvk_u32 key = (int)threadIdx.x < n ? __ldg(p.tileLists + chunkBase + threadIdx.x) : 0xFFFFFFFFu;
-            sKeys[threadIdx.x] = key;
-            __syncthreads();
+            const cpvk_u32* sKeys = reinterpret_cast<const cpvk_u32*>(sBB);  // staged before the first barrier; reused before the bboxes are staged
+            const cpvk_u32 key = firstKey;
             if ((int)threadIdx.x < n) {
                 cpvk_u32 rank = 0xFFFFFFFFu;
                 const uint4* k4 = reinterpret_cast<const uint4*>(sKeys);
@@ -572,8 +584,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             __syncthreads();
         }
         cpvk_u32 stagedPrim = 0;
-        if ((int)threadIdx.x < n) stagedPrim = listsSorted ? __ldg(p.tileLists + chunkBase + threadIdx.x) : reinterpret_cast<const cpvk_u32*>(sQ)[threadIdx.x];
-        if (!listsSorted) __syncthreads(); // every thread has read its sorted id before the planes are overwritten
+        if ((int)threadIdx.x < n) stagedPrim = listsSorted ? __ldg(p.tileLists + chunkBase + threadIdx.x) : sSorted[threadIdx.x];
         if ((int)threadIdx.x < n) { // CPVK_CHUNK == blockDim.x: one record per thread, 16-byte coalesced pieces
             const uint4* sp = reinterpret_cast<const uint4*>(p.setups + stagedPrim);
             #pragma unroll
@@ -766,25 +777,25 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                 }
             }
         }
-        __syncthreads();
+        if (chunkBase + CPVK_CHUNK < listEnd) __syncthreads(); // the staged chunk is free for the next one (after the last chunk the barrier below does it)
     }
     __syncthreads();
     // ---- write the tile back: shared -> HBM, row segments are contiguous in the linear image ----
     if (dsUsed && ((depthTest && depthWrite) || stencilOn || (lazyMask & 0x100u)))
         cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel, p.ds.rowPitch,
-                       sDepth, dsPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th);
+                       sDepth, dsPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th, dsPitch);
     #pragma unroll
     for (int a = 0; a < CPVK_MAX_COLOR; a++)
         if (sColor[a])
             cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.color[a].address) + (cpvk_u64)tileY0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a], p.color[a].rowPitch,
-                           sColor[a], cTexel[a] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th);
+                           sColor[a], cTexel[a] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th, cTexel[a] * CPVK_TILE_W);
     // ---- the fused gather: the band's rows of this tile go to every peer's copy of colour attachment 0 ----
     if (p.mirrorCount && sColor[0]) {
         const int my0 = max(tileY0, p.clipY0);
         if (my0 < y1)
             for (cpvk_u32 m = 0; m < p.mirrorCount; m++)
                 cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.mirror[m]) + (cpvk_u64)my0 * p.color[0].rowPitch + (cpvk_u64)tileX0 * cTexel[0], p.color[0].rowPitch,
-                               sColor[0] + (cpvk_u32)(my0 - tileY0) * cTexel[0] * CPVK_TILE_W, cTexel[0] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[0], (cpvk_u32)(y1 - my0));
+                               sColor[0] + (cpvk_u32)(my0 - tileY0) * cTexel[0] * CPVK_TILE_W, cTexel[0] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[0], (cpvk_u32)(y1 - my0), cTexel[0] * CPVK_TILE_W);
     }
     if (p.stats && lane == 0 && (nCov | nPass)) {
         atomicAdd(p.stats + 0, (cpvk_u64)nCov);
