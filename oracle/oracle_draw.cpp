@@ -3,9 +3,12 @@
 // TEST INFRASTRUCTURE ONLY. May be used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs — as the checker, never as the thing shipped. The product path (libcpvk_cuda.so)
 // never links or calls this.
-// PARITY UNPINNED: the reference has no tests, golden vectors or published outputs for this path
-//  and cannot be built in this image (needs LLVM-8, Vulkan SDK, GSL, glm: SURVEY F10),
-// so this restatement is pinned only by the reference source it follows and by the KATs in tests/.
+// PARITY: the reference has no tests, golden vectors or published outputs for this path and the ICD
+// cannot be built in this image (LLVM-8, Vulkan SDK, GSL, glm: SURVEY F10). What the reference CAN execute here — its
+// format table / image layout / half codec, its texture sampler and its SPIR-V reader, compiled in place into
+// oracle/_ref/ — pins oracle_formats.h and oracle_sampler.h bit for bit (tests/test_reference_*.py, tests/golden/).
+// The draw control flow in THIS file (IA, setup, coverage, interpolation, late depth/stencil, blend) remains PARITY
+// UNPINNED: it is held only by the reference source it follows and by the independent KATs in tests/test_oracle_kats.py.
 //
 // Follows, in execution order:
 //   CPVulkan/CommandBuffer.Draw.cpp:675-760  ProcessInputAssembler[Indexed]          (IA)

@@ -2,8 +2,11 @@
 //
 // TEST INFRASTRUCTURE ONLY. Nothing under oracle/ is part of the product path; it may be used only by
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
-// PARITY UNPINNED: the reference ships no golden vectors or tests for this path; this
-// file follows the reference *source* line by line and is cross-checked only by the KATs in tests/.
+// PARITY: GetFormatInformation, the image layout and FloatToHalf / HalfToFloat are PINNED against the reference's own
+// CPVulkanBase/Formats.cpp and FloatFormat.h compiled in place (oracle/_ref/formats_check; tests/test_reference_formats.py,
+// tests/golden/ref_formats.txt, ref_layout.txt, ref_half.npz). The pack / unpack arithmetic (UNORM / SNORM / sRGB / depth)
+// is PARITY UNPINNED: the reference emits it as LLVM IR (ImageCompiler.cpp), which cannot run here; it follows the
+// source line by line and is cross-checked by the numpy KATs in tests/test_oracle_kats.py.
 //
 // Follows:
 //   CPVulkanBase/Formats.cpp:210-443 (table), :455-483 (GetNormalImageSize), :583-587 (GetImagePixelOffset)

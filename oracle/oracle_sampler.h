@@ -1,5 +1,9 @@
 // oracle_sampler.h — CPU restatement of the reference's texel fetch and filtering.
-// TEST INFRASTRUCTURE ONLY (see oracle_formats.h). PARITY UNPINNED by reference tests.
+// TEST INFRASTRUCTURE ONLY (see oracle_formats.h).
+// PARITY: SampleImage / SampleImageOfLevel / wrap / lerp are PINNED bit for bit against the reference's own
+// CPVulkan/ImageSampler.cpp compiled in place (oracle/_ref/sampler_check; tests/test_reference_sampler.py,
+// tests/golden/ref_sampler.npz: 90 sampler states x 128 coordinates). The GlslFunctions.cpp wrapper (LOD bias / clamp,
+// swizzle, texel fetch) is PARITY UNPINNED (needs the whole ICD to compile).
 //
 // Follows:
 //   CPVulkan/ImageSampler.cpp:12-38 (wrap), :40-55 (frac, lerp in double), :83-145 (GetPixel + border),
