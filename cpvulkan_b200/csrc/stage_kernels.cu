@@ -655,21 +655,32 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                         const cpvk_u32 rowMask = small ? ((1u << cw) - 1u) : 0u; // cw <= 16
                         const int rows = small ? ch : 0;
                         int shift = 0;
+                        // Two rows per pass: A_k(x) = (xf - ax_k) * dy_k does not depend on the row and B_k(y) = (yf - ay_k) *
+                        // dx_k not on the column, so a column's three A terms are compared against both rows' B terms
+                        // (same operations on the same operands as the per-pixel expression: identical bits).
+                        const float* yp = sYf + by; // by + yy + 1 <= 40: stays inside the xf/yf/lut block, masked by `rows`
                         #pragma unroll 1
-                        for (int yy = 0; yy < maxH; yy++) {
-                            const bool rowIn = yy < rows;
-                            const float yf = sYf[by + (rowIn ? yy : 0)];
-                            const float b0 = (yf - e0ay) * e0dx, b1 = (yf - e1ay) * e1dx, b2 = (yf - e2ay) * e2dx;
-                            cpvk_u32 rowCov = 0, bit = 1u;
+                        for (int yy = 0; yy < maxH; yy += 2) {
+                            const float yf0 = yp[yy], yf1 = yp[yy + 1];
+                            const float b00 = (yf0 - e0ay) * e0dx, b01 = (yf0 - e1ay) * e1dx, b02 = (yf0 - e2ay) * e2dx;
+                            const float b10 = (yf1 - e0ay) * e0dx, b11 = (yf1 - e1ay) * e1dx, b12 = (yf1 - e2ay) * e2dx;
+                            cpvk_u32 r0 = 0, r1 = 0, bit = 1u;
                             const float* xp = sXf + bx; // bx + xx <= 46: stays inside the xf/yf/lut block
                             const float* const xe = xp + maxW;
-                            #pragma unroll 2
+                            #pragma unroll 1
                             for (; xp != xe; xp++, bit <<= 1) {
                                 const float xf = *xp;
-                                const bool out = (xf - e0ax) * e0dy < b0 || (xf - e1ax) * e1dy < b1 || (xf - e2ax) * e2dy < b2;
-                                if (!out) rowCov |= bit;
+                                const float a0 = (xf - e0ax) * e0dy, a1 = (xf - e1ax) * e1dy, a2 = (xf - e2ax) * e2dy;
+                                // inside = !(a0 < b0 || a1 < b1 || a2 < b2) = (a0 >=u b0) && (a1 >=u b1) && (a2 >=u b2), "u" = or unordered:
+                                // three chained predicate compares and one predicated OR per pixel
+                                #define CPVK_COVER(r, x0, x1, x2) asm("{ .reg .pred q; setp.geu.f32 q, %1, %2; setp.geu.and.f32 q, %3, %4, q; setp.geu.and.f32 q, %5, %6, q; @q or.b32 %0, %0, %7; }" \
+                                                                     : "+r"(r) : "f"(a0), "f"(x0), "f"(a1), "f"(x1), "f"(a2), "f"(x2), "r"(bit))
+                                CPVK_COVER(r0, b00, b01, b02);
+                                CPVK_COVER(r1, b10, b11, b12);
+                                #undef CPVK_COVER
                             }
-                            if (rowIn) { cov |= (rowCov & rowMask) << shift; shift += cw; }
+                            if (yy < rows) { cov |= (r0 & rowMask) << shift; shift += cw; }
+                            if (yy + 1 < rows) { cov |= (r1 & rowMask) << shift; shift += cw; }
                         }
                     } else {
                         int xx = 0, yy = 0;
