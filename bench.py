@@ -130,7 +130,7 @@ def run_reference(args):
                                    "oracle omits the reference's JIT/indirect-call overhead (optimistic stand-in)" % (st.fragmentsCovered, model, ncpu)},
         "e2e": {"value": val, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def run_ours(args):
@@ -377,7 +377,7 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def raster_traffic():
@@ -444,6 +444,9 @@ def secondary_configs(dev, torch):
     return out
 
 
+_RESULT_OUT = sys.stdout
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -454,6 +457,12 @@ def main():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU exchange: peer stores from k_raster (default) or an NCCL all-gather after the draw")
     ap.add_argument("--no-extras", action="store_true", help="skip the short C4 / C5 measurements reported under other_configs")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: whatever libraries print to file descriptor 1 on the way (NCCL's
+    # version banner under torchrun, for one) is sent to stderr instead
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -19,7 +19,7 @@ MAX_PUSH_CONSTANT_BYTES = 128
 MAX_SPEC_ENTRIES = 16
 
 E_UNSUPPORTED, E_SPIRV, E_COMPILE, E_ARGUMENT, E_NO_DEVICE = -1, -2, -3, -4, -5
-DESC_NONE, DESC_BUFFER, DESC_IMAGE, DESC_TEXEL_BUFFER = 0, 1, 2, 3
+DESC_NONE, DESC_BUFFER, DESC_IMAGE, DESC_TEXEL_BUFFER, DESC_SAMPLER = 0, 1, 2, 3, 4
 
 u32, i32, u64, f32 = C.c_uint32, C.c_int32, C.c_uint64, C.c_float
 

@@ -263,6 +263,12 @@ private:
     std::vector<std::string> arrays;
     std::map<std::pair<int, uint32_t>, Ptr> ptrs;
     std::map<std::pair<int, uint32_t>, std::string> handles;
+    std::map<std::pair<int, uint32_t>, std::string> samplerOf; // OpSampledImage results: the descriptor that supplies the sampler state
+    void CopyHandle(std::pair<int, uint32_t> dst, std::pair<int, uint32_t> src) {
+        handles[dst] = handles.at(src);
+        auto s = samplerOf.find(src);
+        if (s != samplerOf.end()) samplerOf[dst] = s->second; else samplerOf.erase(dst);
+    }
     int ctxCounter = 0, tmpCounter = 0;
     uint32_t perVertexVar = 0, positionVar = 0, pointSizeVar = 0;
 
@@ -702,7 +708,7 @@ private:
                 const uint32_t pid = callee.params[a], aid = in.ops[1 + a];
                 const Type& pt = T(TypeOf(pid));
                 if (pt.kind == Type::Pointer) ptrs[{nctx, pid}] = VarPtr(ctx, aid);
-                else if (pt.kind == Type::Image || pt.kind == Type::SampledImage || pt.kind == Type::Sampler) handles[{nctx, pid}] = handles.at({ctx, aid});
+                else if (pt.kind == Type::Image || pt.kind == Type::SampledImage || pt.kind == Type::Sampler) CopyHandle({nctx, pid}, {ctx, aid});
                 else for (uint32_t k = 0; k < pt.words; k++) body << "  " << Name(nctx, pid, k, pt.leaves[k]) << " = " << W(ctx, aid, k) << ";\n";
             }
             EmitFunction(in.ops[0], nctx, {}, in.result, ctx, in.type);
@@ -726,7 +732,7 @@ private:
             body << "  default: {\n"; Goto(ctx, f, b.label, in.ops[1]); body << "  }\n  }\n"; break;
         case OpCopyObject:
             if (T(in.type).kind == Type::Pointer) ptrs[{ctx, in.result}] = VarPtr(ctx, in.ops[0]);
-            else if (handles.count({ctx, in.ops[0]})) handles[{ctx, in.result}] = handles[{ctx, in.ops[0]}];
+            else if (handles.count({ctx, in.ops[0]})) CopyHandle({ctx, in.result}, {ctx, in.ops[0]});
             else Comp(ctx, in, [&](uint32_t k) { return W(ctx, in.ops[0], k); });
             break;
         case OpVectorShuffle: {
@@ -850,7 +856,10 @@ private:
         case OpBitwiseAnd: Bin(ctx, in, "(", " & ", ")"); break;
         case OpNot: Comp(ctx, in, [&](uint32_t k) { return "~" + W(ctx, in.ops[0], k); }); break;
         case OpExtInst: EmitExt(ctx, in); break;
-        case OpSampledImage: throw Unsupported("separate image/sampler objects (OpSampledImage) are not built yet");
+        case OpSampledImage: { // @Image.Combine (GlslFunctions.cpp:812-820): the image's data with the sampler object's state
+            auto hi = handles.find({ctx, in.ops[0]}), hs = handles.find({ctx, in.ops[1]});
+            if (hi == handles.end() || hs == handles.end()) throw Malformed("OpSampledImage operands are not loaded handles");
+            handles[{ctx, in.result}] = hi->second; samplerOf[{ctx, in.result}] = hs->second; break; }
         case OpImage: handles[{ctx, in.result}] = handles.at({ctx, in.ops[0]}); break;
         case OpImageSampleImplicitLod: case OpImageSampleExplicitLod: {
             auto h = handles.find({ctx, in.ops[0]}); if (h == handles.end()) throw Malformed("sampled image operand is not a loaded handle");
@@ -863,7 +872,8 @@ private:
             if (model == 4) layout.fsSamplesImages = true;
             int dimsHint = 0; // OpTypeImage Dim: 1D, 2D, 3D -> 1, 2, 3
             { const Type& st = T(TypeOf(in.ops[0])); const Type& it = st.kind == Type::SampledImage ? T(st.elem) : st; if (it.kind == Type::Image && it.count <= 2) dimsHint = (int)it.count + 1; }
-            body << "  " << t << " = cpvk_image_sample(" << h->second << ", " << W(ctx, in.ops[1], 0) << ", " << (cn > 1 ? W(ctx, in.ops[1], 1) : "0.0f") << ", "
+            const auto so = samplerOf.find({ctx, in.ops[0]});
+            body << "  " << t << " = cpvk_image_sample(" << h->second << ", " << (so != samplerOf.end() ? so->second : h->second) << ", " << W(ctx, in.ops[1], 0) << ", " << (cn > 1 ? W(ctx, in.ops[1], 1) : "0.0f") << ", "
                  << (cn > 2 ? W(ctx, in.ops[1], 2) : "0.0f") << ", " << lod << ", lut_, " << dimsHint << ");\n";
             if (T(T(in.type).kind == Type::Vector ? T(in.type).elem : in.type).kind != Type::Float) throw Unsupported("integer image sampling");
             Comp(ctx, in, [&](uint32_t k) { return t + ".v[" + std::to_string(k) + "]"; });

@@ -76,11 +76,12 @@ struct ImageView { Image* image = nullptr; VkFormat format = VK_FORMAT_UNDEFINED
 struct BufferView { Buffer* buffer = nullptr; VkFormat format = VK_FORMAT_UNDEFINED; VkDeviceSize offset = 0, range = 0; };
 struct Sampler { CpvkSampler s{}; };
 struct ShaderModule { std::vector<uint32_t> code; };
-struct DescriptorSetLayout { std::vector<VkDescriptorSetLayoutBinding> bindings; };
+// pImmutableSamplers are copied at creation (DescriptorSetLayout.cpp:44-58): the application's array need not outlive the call
+struct DescriptorSetLayout { std::vector<VkDescriptorSetLayoutBinding> bindings; std::map<uint32_t, std::vector<Sampler*>> immutableSamplers; };
 struct PipelineLayout { int unused = 0; };
 struct DescriptorPool { int unused = 0; };
 struct DescriptorValue { VkDescriptorType type = VK_DESCRIPTOR_TYPE_MAX_ENUM; Buffer* buffer = nullptr; VkDeviceSize offset = 0, range = 0; ImageView* view = nullptr; Sampler* sampler = nullptr; BufferView* bufferView = nullptr; };
-struct DescriptorSet { DescriptorSetLayout* layout = nullptr; std::map<uint32_t, std::vector<DescriptorValue>> bindings; };
+struct DescriptorSet { DescriptorSetLayout* layout = nullptr; std::map<uint32_t, std::vector<DescriptorValue>> bindings; std::map<uint32_t, bool> immutable; };
 struct Subpass { std::vector<VkAttachmentReference> color; VkAttachmentReference depthStencil{VK_ATTACHMENT_UNUSED, VK_IMAGE_LAYOUT_UNDEFINED}; };
 struct RenderPass { std::vector<VkAttachmentDescription> attachments; std::vector<Subpass> subpasses; };
 struct Framebuffer { std::vector<ImageView*> views; uint32_t width = 0, height = 0; };
@@ -205,6 +206,10 @@ void FillDescriptor(CpvkDescriptor& out, uint32_t set, uint32_t binding, uint32_
         out.swizzle[0] = iv->components.r; out.swizzle[1] = iv->components.g; out.swizzle[2] = iv->components.b; out.swizzle[3] = iv->components.a;
         if (v.sampler) out.sampler = v.sampler->s;
         break; }
+    case VK_DESCRIPTOR_TYPE_SAMPLER: // combined with a SAMPLED_IMAGE by OpSampledImage in the shader (Samples/separate_image_sampler)
+        out.type = CPVK_DESC_SAMPLER;
+        if (v.sampler) out.sampler = v.sampler->s;
+        break;
     default: Fatal("descriptor type not built");
     }
 }
@@ -233,7 +238,6 @@ void ExecDraw(Device& d, uint32_t count, uint32_t instanceCount, uint32_t first,
                 if (v.type == VK_DESCRIPTOR_TYPE_MAX_ENUM) continue;
                 uint32_t dynOff = 0;
                 if (v.type == VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC || v.type == VK_DESCRIPTOR_TYPE_STORAGE_BUFFER_DYNAMIC) dynOff = dyn < s.dynamicOffsets[set].size() ? s.dynamicOffsets[set][dyn++] : 0;
-                if (v.type == VK_DESCRIPTOR_TYPE_SAMPLER) continue;
                 if (nd >= CPVK_MAX_DESCRIPTORS) Fatal("too many descriptors bound");
                 FillDescriptor(st->descriptors[nd++], set, kv.first, e, v, dynOff);
             }
@@ -450,7 +454,15 @@ VKFN(VkResult) CreateShaderModule(VkDevice, const VkShaderModuleCreateInfo* info
 }
 VKFN(void) DestroyShaderModule(VkDevice, VkShaderModule m, const VkAllocationCallbacks*) { delete reinterpret_cast<ShaderModule*>(m); }
 VKFN(VkResult) CreateDescriptorSetLayout(VkDevice, const VkDescriptorSetLayoutCreateInfo* info, const VkAllocationCallbacks*, VkDescriptorSetLayout* pLayout) {
-    auto* l = new DescriptorSetLayout(); l->bindings.assign(info->pBindings, info->pBindings + info->bindingCount); *pLayout = reinterpret_cast<VkDescriptorSetLayout>(l); return VK_SUCCESS;
+    auto* l = new DescriptorSetLayout(); l->bindings.assign(info->pBindings, info->pBindings + info->bindingCount);
+    for (auto& b : l->bindings) {
+        if ((b.descriptorType == VK_DESCRIPTOR_TYPE_SAMPLER || b.descriptorType == VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER) && b.pImmutableSamplers) {
+            auto& v = l->immutableSamplers[b.binding];
+            for (uint32_t i = 0; i < b.descriptorCount; i++) v.push_back(reinterpret_cast<Sampler*>(b.pImmutableSamplers[i]));
+        }
+        b.pImmutableSamplers = nullptr;
+    }
+    *pLayout = reinterpret_cast<VkDescriptorSetLayout>(l); return VK_SUCCESS;
 }
 VKFN(void) DestroyDescriptorSetLayout(VkDevice, VkDescriptorSetLayout l, const VkAllocationCallbacks*) { delete reinterpret_cast<DescriptorSetLayout*>(l); }
 VKFN(VkResult) CreatePipelineLayout(VkDevice, const VkPipelineLayoutCreateInfo*, const VkAllocationCallbacks*, VkPipelineLayout* p) { *p = reinterpret_cast<VkPipelineLayout>(new PipelineLayout()); return VK_SUCCESS; }
@@ -460,7 +472,14 @@ VKFN(void) DestroyDescriptorPool(VkDevice, VkDescriptorPool p, const VkAllocatio
 VKFN(VkResult) AllocateDescriptorSets(VkDevice, const VkDescriptorSetAllocateInfo* info, VkDescriptorSet* pSets) {
     for (uint32_t i = 0; i < info->descriptorSetCount; i++) {
         auto* s = new DescriptorSet(); s->layout = reinterpret_cast<DescriptorSetLayout*>(info->pSetLayouts[i]);
-        for (auto& b : s->layout->bindings) s->bindings[b.binding].resize(b.descriptorCount);
+        for (auto& b : s->layout->bindings) {
+            auto& vec = s->bindings[b.binding]; vec.resize(b.descriptorCount);
+            auto im = s->layout->immutableSamplers.find(b.binding); // DescriptorSet.cpp:38-48: the set starts out holding them
+            if (im != s->layout->immutableSamplers.end()) {
+                s->immutable[b.binding] = true;
+                for (uint32_t e = 0; e < b.descriptorCount && e < im->second.size(); e++) { vec[e].sampler = im->second[e]; if (b.descriptorType == VK_DESCRIPTOR_TYPE_SAMPLER) vec[e].type = VK_DESCRIPTOR_TYPE_SAMPLER; }
+            }
+        }
         pSets[i] = reinterpret_cast<VkDescriptorSet>(s);
     }
     return VK_SUCCESS;
@@ -475,6 +494,8 @@ VKFN(void) UpdateDescriptorSets(VkDevice, uint32_t writeCount, const VkWriteDesc
         if (vec.size() < wr.dstArrayElement + wr.descriptorCount) vec.resize(wr.dstArrayElement + wr.descriptorCount);
         for (uint32_t k = 0; k < wr.descriptorCount; k++) {
             DescriptorValue& v = vec[wr.dstArrayElement + k];
+            const bool immutable = set->immutable.count(wr.dstBinding) != 0; // the layout's sampler survives every write (DescriptorSet.cpp:79-101)
+            Sampler* const keep = immutable ? v.sampler : nullptr;
             v = DescriptorValue(); v.type = wr.descriptorType;
             switch (wr.descriptorType) {
             case VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER: case VK_DESCRIPTOR_TYPE_STORAGE_BUFFER: case VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC: case VK_DESCRIPTOR_TYPE_STORAGE_BUFFER_DYNAMIC:
@@ -482,7 +503,9 @@ VKFN(void) UpdateDescriptorSets(VkDevice, uint32_t writeCount, const VkWriteDesc
             case VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER: case VK_DESCRIPTOR_TYPE_STORAGE_TEXEL_BUFFER:
                 v.bufferView = reinterpret_cast<BufferView*>(wr.pTexelBufferView[k]); break;
             default:
-                v.view = reinterpret_cast<ImageView*>(wr.pImageInfo[k].imageView); v.sampler = reinterpret_cast<Sampler*>(wr.pImageInfo[k].sampler); break;
+                v.view = reinterpret_cast<ImageView*>(wr.pImageInfo[k].imageView);
+                v.sampler = immutable ? keep : (wr.descriptorType == VK_DESCRIPTOR_TYPE_SAMPLED_IMAGE || wr.descriptorType == VK_DESCRIPTOR_TYPE_STORAGE_IMAGE) ? nullptr : reinterpret_cast<Sampler*>(wr.pImageInfo[k].sampler);
+                break;
             }
         }
     }

@@ -62,8 +62,13 @@ class Image:
 
 
 class Texture:
-    def __init__(self, binding, image, filt=NEAREST, address=CLAMP_TO_EDGE, set_=0):
+    """sampler_binding: None = combined image sampler; an int = texture2D at `binding` + sampler object at `sampler_binding`
+    (OpSampledImage in the shader, Samples/separate_image_sampler). immutable: through the ICD the sampler is given in the
+    set layout's pImmutableSamplers and the descriptor write carries none (Samples/immutable_sampler)."""
+
+    def __init__(self, binding, image, filt=NEAREST, address=CLAMP_TO_EDGE, set_=0, sampler_binding=None, immutable=False):
         self.set, self.binding, self.image, self.filter, self.address = set_, binding, image, filt, address
+        self.sampler_binding, self.immutable = sampler_binding, immutable
 
 
 class Scene:
@@ -166,10 +171,16 @@ def materialize(scene, alloc):
         ds.set, ds.binding, ds.type = t.set, t.binding, capi.DESC_IMAGE
         ds.format, ds.dimensions, ds.levelCount = img.format, 2, 1
         ds.levels[0] = capi.MipLevel(addr, img.width, img.height, 1, 0)
+        if t.sampler_binding is not None:  # the image descriptor carries no sampler; a CPVK_DESC_SAMPLER record follows
+            nd += 1
+            ds = s.descriptors[nd]
+            ds.set, ds.binding, ds.type = t.set, t.sampler_binding, capi.DESC_SAMPLER
         sm = ds.sampler
         sm.magFilter = sm.minFilter = t.filter
         sm.addressModeU = sm.addressModeV = sm.addressModeW = t.address
         sm.minLod, sm.maxLod = 0.0, 0.0
+        if t.sampler_binding is not None or t.immutable:
+            sm.borderColor = 4  # the harness' vkCreateSampler state (FLOAT_OPAQUE_WHITE); never sampled with CLAMP_TO_BORDER here
         nd += 1
     for set_, binding, name, fmt in scene.texel_buffers:
         ds = s.descriptors[nd]
@@ -332,6 +343,26 @@ def draw_textured_cube(width=500, height=500, filt=NEAREST):
     s.depth_test = s.depth_write = True
     s.count = 36
     _render_targets(s, width, height, B8G8R8A8_UNORM, D16_UNORM, (0.2, 0.2, 0.2, 0.2))
+    return s
+
+
+def separate_image_sampler(width=500, height=500, filt=LINEAR, immutable=False):
+    """Samples/separate_image_sampler: the textured cube with `texture2D tex` at binding 1 and `sampler samp` at binding 2,
+    combined in the shader by OpSampledImage (sampler2D(tex, samp)); the fragment shader also darkens a 1 % border."""
+    s = draw_textured_cube(width, height, filt)
+    s.name = "separate_image_sampler_%d%s" % (filt, "_immutable" if immutable else "")
+    s.fs = "sepsampler.frag"
+    t = s.textures[0]
+    s.textures = [Texture(1, t.image, filt, CLAMP_TO_EDGE, sampler_binding=2, immutable=immutable)]
+    return s
+
+
+def immutable_sampler(width=500, height=500, filt=LINEAR):
+    """Samples/immutable_sampler: draw_textured_cube with the sampler baked into the descriptor set layout."""
+    s = draw_textured_cube(width, height, filt)
+    s.name = "immutable_sampler_%d" % filt
+    t = s.textures[0]
+    s.textures = [Texture(1, t.image, filt, CLAMP_TO_EDGE, immutable=True)]
     return s
 
 
@@ -607,7 +638,8 @@ def export_scene(scene, directory):
     for t in scene.textures:
         fn = "tex_%d.bin" % t.binding
         np.ascontiguousarray(t.image.data).tofile(os.path.join(directory, fn))
-        lines.append("texture %d %d %d %d %d %d %d %s" % (t.set, t.binding, t.image.format, t.image.width, t.image.height, t.filter, t.address, fn))
+        lines.append("texture %d %d %d %d %d %d %d %s %d %d" % (t.set, t.binding, t.image.format, t.image.width, t.image.height, t.filter, t.address, fn,
+                                                                -1 if t.sampler_binding is None else t.sampler_binding, int(t.immutable)))
     cc = scene.color.clear[1] if scene.color.clear else (0, 0, 0, 0)
     lines.append("color %d %d %d %r %r %r %r" % ((scene.color.format, scene.color.width, scene.color.height) + tuple(float(np.float32(c)) for c in cc)))
     if scene.depth:

@@ -159,7 +159,9 @@ enum {
     CPVK_DESC_NONE = 0,
     CPVK_DESC_BUFFER = 1,        /* uniform / storage buffer (LoadUniforms, Draw.cpp:379-396) */
     CPVK_DESC_IMAGE = 2,         /* ImageDescriptorType::Image (+ sampler when combined)      */
-    CPVK_DESC_TEXEL_BUFFER = 3   /* ImageDescriptorType::Buffer                                */
+    CPVK_DESC_TEXEL_BUFFER = 3,  /* ImageDescriptorType::Buffer                                */
+    CPVK_DESC_SAMPLER = 4        /* a sampler object on its own (VK_DESCRIPTOR_TYPE_SAMPLER): only `sampler` is read; OpSampledImage
+                                    combines it with a CPVK_DESC_IMAGE (ImageCombine, GlslFunctions.cpp:812-820) */
 };
 
 typedef struct CpvkDescriptor {

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -321,6 +322,17 @@ struct Interp {
         frames.resize(64); // fixed: references into `frames` must stay valid across nested calls
     }
 
+    // OpSampledImage = @Image.Combine (GlslFunctions.cpp:812-820): the image descriptor's data with the sampler object's state.
+    // One combined record per (image, sampler) pair, kept for the interpreter's lifetime.
+    std::deque<CpvkDescriptor> combined;
+    std::map<std::pair<const CpvkDescriptor*, const CpvkDescriptor*>, const CpvkDescriptor*> combinedOf;
+    const CpvkDescriptor* Combine(const CpvkDescriptor* image, const CpvkDescriptor* sampler) {
+        auto it = combinedOf.find({image, sampler});
+        if (it != combinedOf.end()) return it->second;
+        combined.push_back(*image);
+        combined.back().sampler = sampler->sampler;
+        return combinedOf[{image, sampler}] = &combined.back();
+    }
     const CpvkDescriptor* FindDescriptor(uint32_t set, uint32_t binding, uint32_t element) const {
         for (uint32_t i = 0; i < env.descriptorCount; i++) {
             const CpvkDescriptor& d = env.descriptors[i];
@@ -664,7 +676,11 @@ inline bool Interp::Exec(Function& f, std::vector<uint32_t>& fr, const Inst& in,
     case OpBitwiseAnd: BIN_U(x & y)
     case OpNot: { const uint32_t* a = V(in.ops[0]); for (uint32_t i = 0; i < n; i++) r[i] = ~a[i]; return false; }
     case OpExtInst: ExtInst(f, fr, in); return false;
-    case OpSampledImage: std::memcpy(r, V(in.ops[0]), 8); return false; // combined descriptors only
+    case OpSampledImage: {
+        uint64_t hi, hs; std::memcpy(&hi, V(in.ops[0]), 8); std::memcpy(&hs, V(in.ops[1]), 8);
+        if (!hi || !hs) Fail("OpSampledImage on an unbound image or sampler");
+        const uint64_t h = (uint64_t)(uintptr_t)Combine(reinterpret_cast<const CpvkDescriptor*>((uintptr_t)hi), reinterpret_cast<const CpvkDescriptor*>((uintptr_t)hs));
+        std::memcpy(r, &h, 8); return false; }
     case OpImage: std::memcpy(r, V(in.ops[0]), 8); return false;
     case OpImageSampleImplicitLod: case OpImageSampleExplicitLod: {
         uint64_t h; std::memcpy(&h, V(in.ops[0]), 8);

@@ -102,3 +102,17 @@ def test_icd_clear_attachments_rectangle(built, tmp_path):
 @pytest.mark.parametrize("topology", [scenes.POINT_LIST, scenes.LINE_LIST, scenes.LINE_STRIP])
 def test_icd_points_and_lines(built, tmp_path, topology):
     check(scenes.random_points_lines(topology=topology, count=50, seed=9, line_width=2.5), tmp_path)
+
+
+@pytest.mark.parametrize("filt", [scenes.NEAREST, scenes.LINEAR])
+@pytest.mark.parametrize("immutable", [False, True])
+def test_icd_separate_image_sampler(built, tmp_path, filt, immutable):
+    # Samples/separate_image_sampler: SAMPLED_IMAGE + SAMPLER descriptors combined by OpSampledImage in the shader
+    # (ImageCombine, GlslFunctions.cpp:812-820); with immutable=True the sampler comes from the set layout instead of a write
+    check(scenes.separate_image_sampler(200, 160, filt, immutable), tmp_path)
+
+
+@pytest.mark.parametrize("filt", [scenes.NEAREST, scenes.LINEAR])
+def test_icd_immutable_sampler(built, tmp_path, filt):
+    # Samples/immutable_sampler: pImmutableSamplers in the layout, image_info.sampler = 0 in the write (DescriptorSet.cpp:38-48, :79-101)
+    check(scenes.immutable_sampler(200, 160, filt), tmp_path)

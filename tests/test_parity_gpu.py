@@ -445,3 +445,9 @@ def test_large_triangle_region_rejection_is_exact(dev, seed, scale):
 
 def test_large_triangles_many_tiles(dev):
     compare(dev, scenes.large_triangles(width=517, height=389, tris=40, seed=7, scale="extreme"))
+
+
+@pytest.mark.parametrize("filt", [scenes.NEAREST, scenes.LINEAR])
+def test_separate_image_and_sampler(dev, filt):
+    # OpSampledImage: image data from one descriptor, sampler state from another (Samples/separate_image_sampler)
+    compare(dev, scenes.separate_image_sampler(300, 220, filt))
