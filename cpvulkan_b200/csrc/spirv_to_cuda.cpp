@@ -35,7 +35,7 @@ enum : uint16_t {
     OpFunction = 54, OpFunctionParameter, OpFunctionEnd, OpFunctionCall, OpVariable = 59, OpLoad = 61, OpStore,
     OpAccessChain = 65, OpInBoundsAccessChain, OpDecorate = 71, OpMemberDecorate, OpVectorExtractDynamic = 77,
     OpVectorInsertDynamic, OpVectorShuffle, OpCompositeConstruct, OpCompositeExtract, OpCompositeInsert, OpCopyObject,
-    OpTranspose, OpSampledImage = 86, OpImageSampleImplicitLod, OpImageSampleExplicitLod, OpImageFetch = 95,
+    OpTranspose, OpSampledImage = 86, OpImageSampleImplicitLod, OpImageSampleExplicitLod, OpImageFetch = 95, OpImageRead = 98,
     OpImage = 100, OpConvertFToU = 109, OpConvertFToS, OpConvertSToF, OpConvertUToF, OpBitcast = 124,
     OpSNegate = 126, OpFNegate, OpIAdd, OpFAdd, OpISub, OpFSub, OpIMul, OpFMul, OpUDiv, OpSDiv, OpFDiv, OpUMod, OpSRem,
     OpSMod, OpFRem, OpFMod, OpVectorTimesScalar, OpMatrixTimesScalar, OpVectorTimesMatrix, OpMatrixTimesVector,
@@ -878,9 +878,12 @@ private:
             if (T(T(in.type).kind == Type::Vector ? T(in.type).elem : in.type).kind != Type::Float) throw Unsupported("integer image sampling");
             Comp(ctx, in, [&](uint32_t k) { return t + ".v[" + std::to_string(k) + "]"; });
             break; }
-        case OpImageFetch: {
+        // OpImageRead is @Image.Read = ImageFetch with the coordinate as written (GlslFunctions.cpp:739-743) — for
+        // subpassLoad() glslang writes ivec2(0, 0), so the reference reads texel (0, 0) of the input attachment for every
+        // fragment; kept as is for parity.
+        case OpImageFetch: case OpImageRead: {
             auto h = handles.find({ctx, in.ops[0]}); if (h == handles.end()) throw Malformed("image operand is not a loaded handle");
-            if (in.nops > 2) throw Unsupported("image operands on OpImageFetch");
+            if (in.nops > 2) throw Unsupported("image operands on OpImageFetch / OpImageRead (TODO_ERROR, SPIRVCompiler.cpp:1660-1663)");
             const uint32_t cn = T(TypeOf(in.ops[1])).words;
             const std::string t = "s" + std::to_string(tmpCounter++);
             declV.insert(t);

@@ -152,7 +152,7 @@ struct SceneDesc {
     struct Uni { uint32_t set, binding; std::string name; }; std::vector<Uni> uniforms;
     // samplerBinding >= 0: texture2D + sampler bound separately (Samples/separate_image_sampler); immutableSampler: the sampler
     // lives in the set layout and the descriptor write carries none (Samples/immutable_sampler)
-    struct Tex { uint32_t set, binding, format, w, h, filter, address; std::string file; int samplerBinding = -1; int immutableSampler = 0; }; std::vector<Tex> textures;
+    struct Tex { uint32_t set, binding, format, w, h, filter, address; std::string file; int samplerBinding = -1; int immutableSampler = 0; int inputAttachment = 0; }; std::vector<Tex> textures;
     struct TexelBuf { uint32_t set, binding, format; std::string name; }; std::vector<TexelBuf> texelBuffers;
     uint32_t colorFormat = 0, width = 0, height = 0; float clearColor[4] = {};
     uint32_t depthFormat = 0; float clearDepth = 1; uint32_t clearStencil = 0;
@@ -180,7 +180,7 @@ static SceneDesc ParseScene(const std::string& dir) {
         else if (key == "index_buffer") is >> s.indexBuffer >> s.indexStride;
         else if (key == "uniform") { SceneDesc::Uni u; is >> u.set >> u.binding >> u.name; s.uniforms.push_back(u); }
         else if (key == "texel_buffer") { SceneDesc::TexelBuf t; is >> t.set >> t.binding >> t.name >> t.format; s.texelBuffers.push_back(t); }
-        else if (key == "texture") { SceneDesc::Tex t; is >> t.set >> t.binding >> t.format >> t.w >> t.h >> t.filter >> t.address >> t.file; if (!(is >> t.samplerBinding)) t.samplerBinding = -1; if (!(is >> t.immutableSampler)) t.immutableSampler = 0; s.textures.push_back(t); }
+        else if (key == "texture") { SceneDesc::Tex t; is >> t.set >> t.binding >> t.format >> t.w >> t.h >> t.filter >> t.address >> t.file; if (!(is >> t.samplerBinding)) t.samplerBinding = -1; if (!(is >> t.immutableSampler)) t.immutableSampler = 0; if (!(is >> t.inputAttachment)) t.inputAttachment = 0; s.textures.push_back(t); }
         else if (key == "color") { is >> s.colorFormat >> s.width >> s.height; for (auto& c : s.clearColor) is >> c; }
         else if (key == "depth") is >> s.depthFormat >> s.clearDepth >> s.clearStencil;
         else if (key == "viewport") for (auto& v : s.viewport) is >> v;
@@ -298,7 +298,8 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < sc.textures.size(); i++) {
         auto& t = sc.textures[i];
         const VkSampler* immutable = t.immutableSampler ? &texObjs[i].sampler : nullptr;
-        if (t.samplerBinding < 0) lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 1, VK_SHADER_STAGE_FRAGMENT_BIT, immutable});
+        if (t.inputAttachment) lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_INPUT_ATTACHMENT, 1, VK_SHADER_STAGE_FRAGMENT_BIT, nullptr}); // input_attachment.cpp:194-201
+        else if (t.samplerBinding < 0) lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 1, VK_SHADER_STAGE_FRAGMENT_BIT, immutable});
         else {
             lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_SAMPLED_IMAGE, 1, VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
             lb.push_back({(uint32_t)t.samplerBinding, VK_DESCRIPTOR_TYPE_SAMPLER, 1, VK_SHADER_STAGE_FRAGMENT_BIT, immutable});
@@ -323,9 +324,9 @@ int main(int argc, char** argv) {
     VkFramebufferCreateInfo fbi{VK_STRUCTURE_TYPE_FRAMEBUFFER_CREATE_INFO, nullptr, 0, renderPass, (uint32_t)atts.size(), fbViews, sc.width, sc.height, 1};
     VkFramebuffer framebuffer; VK(vkCreateFramebuffer(app.device, &fbi, nullptr, &framebuffer));
     // init_descriptor_pool / init_descriptor_set
-    VkDescriptorPoolSize ps[5] = {{VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 8}, {VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 8}, {VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, 8},
-                                  {VK_DESCRIPTOR_TYPE_SAMPLED_IMAGE, 8}, {VK_DESCRIPTOR_TYPE_SAMPLER, 8}};
-    VkDescriptorPoolCreateInfo dpi{VK_STRUCTURE_TYPE_DESCRIPTOR_POOL_CREATE_INFO, nullptr, 0, 1, 5, ps};
+    VkDescriptorPoolSize ps[6] = {{VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 8}, {VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 8}, {VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, 8},
+                                  {VK_DESCRIPTOR_TYPE_SAMPLED_IMAGE, 8}, {VK_DESCRIPTOR_TYPE_SAMPLER, 8}, {VK_DESCRIPTOR_TYPE_INPUT_ATTACHMENT, 8}};
+    VkDescriptorPoolCreateInfo dpi{VK_STRUCTURE_TYPE_DESCRIPTOR_POOL_CREATE_INFO, nullptr, 0, 1, 6, ps};
     VkDescriptorPool dpool; VK(vkCreateDescriptorPool(app.device, &dpi, nullptr, &dpool));
     VkDescriptorSetAllocateInfo dsa{VK_STRUCTURE_TYPE_DESCRIPTOR_SET_ALLOCATE_INFO, nullptr, dpool, 1, &setLayout};
     VkDescriptorSet dset; VK(vkAllocateDescriptorSets(app.device, &dsa, &dset));
@@ -337,7 +338,10 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < sc.textures.size(); i++) {
         auto& t = sc.textures[i];
         const VkSampler written = t.immutableSampler ? VkSampler(VK_NULL_HANDLE) : texObjs[i].sampler; // immutable: image_info.sampler = 0 (immutable_sampler.cpp:106)
-        if (t.samplerBinding < 0) {
+        if (t.inputAttachment) {
+            iinfos[2 * i] = {VK_NULL_HANDLE, texObjs[i].view, VK_IMAGE_LAYOUT_SHADER_READ_ONLY_OPTIMAL};
+            writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, t.binding, 0, 1, VK_DESCRIPTOR_TYPE_INPUT_ATTACHMENT, &iinfos[2 * i], nullptr, nullptr});
+        } else if (t.samplerBinding < 0) {
             iinfos[2 * i] = {written, texObjs[i].view, VK_IMAGE_LAYOUT_SHADER_READ_ONLY_OPTIMAL};
             writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, t.binding, 0, 1, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, &iinfos[2 * i], nullptr, nullptr});
         } else { // separate_image_sampler.cpp:114-125: image_info.sampler = 0 for the texture, a second info for the sampler

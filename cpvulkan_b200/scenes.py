@@ -66,9 +66,10 @@ class Texture:
     (OpSampledImage in the shader, Samples/separate_image_sampler). immutable: through the ICD the sampler is given in the
     set layout's pImmutableSamplers and the descriptor write carries none (Samples/immutable_sampler)."""
 
-    def __init__(self, binding, image, filt=NEAREST, address=CLAMP_TO_EDGE, set_=0, sampler_binding=None, immutable=False):
+    def __init__(self, binding, image, filt=NEAREST, address=CLAMP_TO_EDGE, set_=0, sampler_binding=None, immutable=False, input_attachment=False):
         self.set, self.binding, self.image, self.filter, self.address = set_, binding, image, filt, address
         self.sampler_binding, self.immutable = sampler_binding, immutable
+        self.input_attachment = input_attachment  # bound as VK_DESCRIPTOR_TYPE_INPUT_ATTACHMENT (no sampler), read with subpassLoad
 
 
 class Scene:
@@ -357,6 +358,18 @@ def separate_image_sampler(width=500, height=500, filt=LINEAR, immutable=False):
     return s
 
 
+def input_attachment(width=500, height=500):
+    """Samples/input_attachment: the fragment shader returns subpassLoad() of an image bound as an input attachment. The
+    reference reads the coordinate glslang writes — ivec2(0, 0) — so every fragment gets texel (0, 0); the cube geometry of
+    C2 stands in for the sample's full-screen triangle so that coverage and depth are exercised too."""
+    s = draw_textured_cube(width, height, NEAREST)
+    s.name = "input_attachment"
+    s.fs = "subpass.frag"
+    t = s.textures[0]
+    s.textures = [Texture(1, t.image, NEAREST, CLAMP_TO_EDGE, input_attachment=True)]
+    return s
+
+
 def immutable_sampler(width=500, height=500, filt=LINEAR):
     """Samples/immutable_sampler: draw_textured_cube with the sampler baked into the descriptor set layout."""
     s = draw_textured_cube(width, height, filt)
@@ -638,8 +651,8 @@ def export_scene(scene, directory):
     for t in scene.textures:
         fn = "tex_%d.bin" % t.binding
         np.ascontiguousarray(t.image.data).tofile(os.path.join(directory, fn))
-        lines.append("texture %d %d %d %d %d %d %d %s %d %d" % (t.set, t.binding, t.image.format, t.image.width, t.image.height, t.filter, t.address, fn,
-                                                                -1 if t.sampler_binding is None else t.sampler_binding, int(t.immutable)))
+        lines.append("texture %d %d %d %d %d %d %d %s %d %d %d" % (t.set, t.binding, t.image.format, t.image.width, t.image.height, t.filter, t.address, fn,
+                                                                   -1 if t.sampler_binding is None else t.sampler_binding, int(t.immutable), int(t.input_attachment)))
     cc = scene.color.clear[1] if scene.color.clear else (0, 0, 0, 0)
     lines.append("color %d %d %d %r %r %r %r" % ((scene.color.format, scene.color.width, scene.color.height) + tuple(float(np.float32(c)) for c in cc)))
     if scene.depth:

@@ -33,6 +33,7 @@ OPS = {
     "CompositeConstruct": (80, 1, 1), "CompositeExtract": (81, 1, 1), "CompositeInsert": (82, 1, 1),
     "CopyObject": (83, 1, 1), "Transpose": (84, 1, 1), "SampledImage": (86, 1, 1),
     "ImageSampleImplicitLod": (87, 1, 1), "ImageSampleExplicitLod": (88, 1, 1), "ImageFetch": (95, 1, 1),
+    "ImageRead": (98, 1, 1),
     "Image": (100, 1, 1), "ImageQuerySizeLod": (103, 1, 1), "ImageQuerySize": (104, 1, 1),
     "ConvertFToU": (109, 1, 1), "ConvertFToS": (110, 1, 1), "ConvertSToF": (111, 1, 1), "ConvertUToF": (112, 1, 1),
     "UConvert": (113, 1, 1), "SConvert": (114, 1, 1), "FConvert": (115, 1, 1), "Bitcast": (124, 1, 1),
@@ -65,7 +66,7 @@ DECORATION = {"RelaxedPrecision": 0, "SpecId": 1, "Block": 2, "BufferBlock": 3, 
               "ArrayStride": 6, "MatrixStride": 7, "GLSLShared": 8, "GLSLPacked": 9, "BuiltIn": 11,
               "NoPerspective": 13, "Flat": 14, "Centroid": 16, "Invariant": 18, "NonWritable": 24,
               "NonReadable": 25, "Location": 30, "Component": 31, "Index": 32, "Binding": 33, "DescriptorSet": 34,
-              "Offset": 35}
+              "Offset": 35, "InputAttachmentIndex": 43}
 BUILTIN = {"Position": 0, "PointSize": 1, "ClipDistance": 3, "CullDistance": 4, "VertexId": 5, "InstanceId": 6,
            "PrimitiveId": 7, "FragCoord": 15, "PointCoord": 16, "FrontFacing": 17, "FragDepth": 22,
            "VertexIndex": 42, "InstanceIndex": 43}
@@ -77,7 +78,7 @@ MISC = {
     # ExecutionMode
     "OriginUpperLeft": 7, "OriginLowerLeft": 8, "EarlyFragmentTests": 9, "DepthReplacing": 12,
     # Capability
-    "Matrix": 0, "Shader": 1, "SampledBuffer": 46, "ImageBuffer": 47,
+    "Matrix": 0, "Shader": 1, "InputAttachment": 40, "SampledBuffer": 46, "ImageBuffer": 47,
     # Dim
     "1D": 0, "2D": 1, "3D": 2, "Cube": 3, "Rect": 4, "Buffer": 5, "SubpassData": 6,
     # ImageFormat

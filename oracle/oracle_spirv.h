@@ -42,7 +42,7 @@ enum Op : uint16_t {
     OpMemberDecorate = 72, OpVectorExtractDynamic = 77, OpVectorInsertDynamic = 78, OpVectorShuffle = 79,
     OpCompositeConstruct = 80, OpCompositeExtract = 81, OpCompositeInsert = 82, OpCopyObject = 83,
     OpTranspose = 84, OpSampledImage = 86, OpImageSampleImplicitLod = 87, OpImageSampleExplicitLod = 88,
-    OpImageFetch = 95, OpImage = 100, OpConvertFToU = 109, OpConvertFToS = 110, OpConvertSToF = 111,
+    OpImageFetch = 95, OpImageRead = 98, OpImage = 100, OpConvertFToU = 109, OpConvertFToS = 110, OpConvertSToF = 111,
     OpConvertUToF = 112, OpBitcast = 124, OpSNegate = 126, OpFNegate = 127, OpIAdd = 128, OpFAdd = 129,
     OpISub = 130, OpFSub = 131, OpIMul = 132, OpFMul = 133, OpUDiv = 134, OpSDiv = 135, OpFDiv = 136,
     OpUMod = 137, OpSRem = 138, OpSMod = 139, OpFRem = 140, OpFMod = 141, OpVectorTimesScalar = 142,
@@ -695,7 +695,7 @@ inline bool Interp::Exec(Function& f, std::vector<uint32_t>& fr, const Inst& in,
         const Vec4f s = ImageSampleExplicitLod(*d, coord, lod);
         for (uint32_t i = 0; i < n; i++) r[i] = U(s.v[i]);
         return false; }
-    case OpImageFetch: {
+    case OpImageFetch: case OpImageRead: { // @Image.Read = ImageFetch, coordinate as written (GlslFunctions.cpp:739-743)
         uint64_t h; std::memcpy(&h, V(in.ops[0]), 8);
         const CpvkDescriptor* d = reinterpret_cast<const CpvkDescriptor*>((uintptr_t)h);
         if (!d) Fail("unbound image descriptor");

@@ -116,3 +116,9 @@ def test_icd_separate_image_sampler(built, tmp_path, filt, immutable):
 def test_icd_immutable_sampler(built, tmp_path, filt):
     # Samples/immutable_sampler: pImmutableSamplers in the layout, image_info.sampler = 0 in the write (DescriptorSet.cpp:38-48, :79-101)
     check(scenes.immutable_sampler(200, 160, filt), tmp_path)
+
+
+def test_icd_input_attachment(built, tmp_path):
+    # Samples/input_attachment: INPUT_ATTACHMENT descriptor read with subpassLoad (OpImageRead -> @Image.Read = ImageFetch at the
+    # coordinate as written, GlslFunctions.cpp:739-743)
+    check(scenes.input_attachment(200, 160), tmp_path)

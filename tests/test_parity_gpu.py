@@ -451,3 +451,7 @@ def test_large_triangles_many_tiles(dev):
 def test_separate_image_and_sampler(dev, filt):
     # OpSampledImage: image data from one descriptor, sampler state from another (Samples/separate_image_sampler)
     compare(dev, scenes.separate_image_sampler(300, 220, filt))
+
+
+def test_input_attachment_read(dev):
+    compare(dev, scenes.input_attachment(300, 220))

@@ -20,6 +20,7 @@ EXPECTED = {  # (storage class, Location) in module order; storage: 0 UniformCon
     "texelbuf.vert": (0, [(6, -1), (0, -1), (6, -1), (6, -1), (3, 0), (6, -1), (3, -1), (1, -1)]),  # 6 = Private
     "complex.frag": (4, [(9, -1), (1, 0), (3, 0)]),                                                  # 9 = PushConstant
     "sepsampler.frag": (4, [(3, 0), (0, -1), (0, -1), (1, 0)]),                                      # texture2D + sampler
+    "subpass.frag": (4, [(3, 0), (0, -1)]),                                                          # subpassInput
 }
 
 
