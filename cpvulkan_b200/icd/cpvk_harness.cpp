@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <algorithm>
 #include <map>
 #include <sstream>
 #include <string>
@@ -74,6 +75,7 @@ DECL(vkCmdBeginRenderPass, void, VkCommandBuffer, const VkRenderPassBeginInfo*, 
 DECL(vkCmdEndRenderPass, void, VkCommandBuffer)
 DECL(vkCmdBindPipeline, void, VkCommandBuffer, VkPipelineBindPoint, VkPipeline)
 DECL(vkCmdBindDescriptorSets, void, VkCommandBuffer, VkPipelineBindPoint, VkPipelineLayout, uint32_t, uint32_t, const VkDescriptorSet*, uint32_t, const uint32_t*)
+DECL(vkCmdPushConstants, void, VkCommandBuffer, VkPipelineLayout, VkShaderStageFlags, uint32_t, uint32_t, const void*)
 DECL(vkCmdBindVertexBuffers, void, VkCommandBuffer, uint32_t, uint32_t, const VkBuffer*, const VkDeviceSize*)
 DECL(vkCmdBindIndexBuffer, void, VkCommandBuffer, VkBuffer, VkDeviceSize, VkIndexType)
 DECL(vkCmdSetViewport, void, VkCommandBuffer, uint32_t, uint32_t, const VkViewport*)
@@ -122,7 +124,7 @@ static void LoadIcd() {
     GET(vkGetImageSubresourceLayout) GET(vkCreateImageView) GET(vkCreateSampler) GET(vkCreateBufferView) GET(vkCreateShaderModule) GET(vkCreateDescriptorSetLayout) GET(vkCreatePipelineLayout)
     GET(vkCreateDescriptorPool) GET(vkAllocateDescriptorSets) GET(vkUpdateDescriptorSets) GET(vkCreateRenderPass) GET(vkCreateFramebuffer) GET(vkCreateGraphicsPipelines)
     GET(vkCreateCommandPool) GET(vkAllocateCommandBuffers) GET(vkBeginCommandBuffer) GET(vkEndCommandBuffer) GET(vkCmdBeginRenderPass) GET(vkCmdEndRenderPass)
-    GET(vkCmdBindPipeline) GET(vkCmdBindDescriptorSets) GET(vkCmdBindVertexBuffers) GET(vkCmdBindIndexBuffer) GET(vkCmdSetViewport) GET(vkCmdSetScissor) GET(vkCmdDraw)
+    GET(vkCmdBindPipeline) GET(vkCmdBindDescriptorSets) GET(vkCmdPushConstants) GET(vkCmdBindVertexBuffers) GET(vkCmdBindIndexBuffer) GET(vkCmdSetViewport) GET(vkCmdSetScissor) GET(vkCmdDraw)
     GET(vkCmdDrawIndexed) GET(vkCmdCopyImageToBuffer) GET(vkCmdBlitImage) GET(vkCmdCopyImage) GET(vkCmdDrawIndirect) GET(vkCmdDrawIndexedIndirect) GET(vkCmdDrawIndirectCount) GET(vkCmdDrawIndexedIndirectCount) GET(vkCmdExecuteCommands) GET(vkCmdUpdateBuffer) GET(vkCmdFillBuffer) GET(vkCmdClearAttachments) GET(vkCreateFence) GET(vkResetFences) GET(vkWaitForFences) GET(vkQueueSubmit) GET(vkDeviceWaitIdle)
 }
 
@@ -149,7 +151,10 @@ struct SceneDesc {
     struct Buf { std::string file; uint64_t size; }; std::map<std::string, Buf> buffers;
     std::map<uint32_t, std::string> vertexBuffers;
     std::string indexBuffer; uint32_t indexStride = 0;
-    struct Uni { uint32_t set, binding; std::string name; }; std::vector<Uni> uniforms;
+    // dynRange != 0: bound as UNIFORM_BUFFER_DYNAMIC over [0, dynRange) with dynOffset passed to vkCmdBindDescriptorSets (Samples/dynamic_uniform)
+    struct Uni { uint32_t set, binding; std::string name; uint32_t dynOffset = 0, dynRange = 0; }; std::vector<Uni> uniforms;
+    std::vector<uint8_t> pushConstants;                                        // vkCmdPushConstants (Samples/push_constants)
+    struct Spec { uint32_t stage, id, value; }; std::vector<Spec> specs;       // VkSpecializationInfo (Samples/spirv_specialization)
     // samplerBinding >= 0: texture2D + sampler bound separately (Samples/separate_image_sampler); immutableSampler: the sampler
     // lives in the set layout and the descriptor write carries none (Samples/immutable_sampler)
     struct Tex { uint32_t set, binding, format, w, h, filter, address; std::string file; int samplerBinding = -1; int immutableSampler = 0; int inputAttachment = 0; }; std::vector<Tex> textures;
@@ -178,7 +183,9 @@ static SceneDesc ParseScene(const std::string& dir) {
         else if (key == "buffer") { std::string n; SceneDesc::Buf b; is >> n >> b.file >> b.size; s.buffers[n] = b; }
         else if (key == "vertex_buffer") { uint32_t b; std::string n; is >> b >> n; s.vertexBuffers[b] = n; }
         else if (key == "index_buffer") is >> s.indexBuffer >> s.indexStride;
-        else if (key == "uniform") { SceneDesc::Uni u; is >> u.set >> u.binding >> u.name; s.uniforms.push_back(u); }
+        else if (key == "uniform") { SceneDesc::Uni u; is >> u.set >> u.binding >> u.name; if (!(is >> u.dynOffset >> u.dynRange)) { u.dynOffset = 0; u.dynRange = 0; } s.uniforms.push_back(u); }
+        else if (key == "push_constants") { size_t n; std::string hex; is >> n >> hex; for (size_t i = 0; i + 1 < hex.size() && i / 2 < n; i += 2) s.pushConstants.push_back((uint8_t)std::stoul(hex.substr(i, 2), nullptr, 16)); }
+        else if (key == "spec") { SceneDesc::Spec sp; is >> sp.stage >> sp.id >> sp.value; s.specs.push_back(sp); }
         else if (key == "texel_buffer") { SceneDesc::TexelBuf t; is >> t.set >> t.binding >> t.name >> t.format; s.texelBuffers.push_back(t); }
         else if (key == "texture") { SceneDesc::Tex t; is >> t.set >> t.binding >> t.format >> t.w >> t.h >> t.filter >> t.address >> t.file; if (!(is >> t.samplerBinding)) t.samplerBinding = -1; if (!(is >> t.immutableSampler)) t.immutableSampler = 0; if (!(is >> t.inputAttachment)) t.inputAttachment = 0; s.textures.push_back(t); }
         else if (key == "color") { is >> s.colorFormat >> s.width >> s.height; for (auto& c : s.clearColor) is >> c; }
@@ -294,7 +301,7 @@ int main(int argc, char** argv) {
     }
     // init_descriptor_and_pipeline_layouts
     std::vector<VkDescriptorSetLayoutBinding> lb;
-    for (auto& u : sc.uniforms) lb.push_back({u.binding, VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
+    for (auto& u : sc.uniforms) lb.push_back({u.binding, u.dynRange ? VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC : VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
     for (size_t i = 0; i < sc.textures.size(); i++) {
         auto& t = sc.textures[i];
         const VkSampler* immutable = t.immutableSampler ? &texObjs[i].sampler : nullptr;
@@ -308,7 +315,8 @@ int main(int argc, char** argv) {
     for (auto& t : sc.texelBuffers) lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
     VkDescriptorSetLayoutCreateInfo li{VK_STRUCTURE_TYPE_DESCRIPTOR_SET_LAYOUT_CREATE_INFO, nullptr, 0, (uint32_t)lb.size(), lb.data()};
     VkDescriptorSetLayout setLayout; VK(vkCreateDescriptorSetLayout(app.device, &li, nullptr, &setLayout));
-    VkPipelineLayoutCreateInfo pli{VK_STRUCTURE_TYPE_PIPELINE_LAYOUT_CREATE_INFO, nullptr, 0, 1, &setLayout, 0, nullptr};
+    VkPushConstantRange pcr{VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, 0, (uint32_t)sc.pushConstants.size()};
+    VkPipelineLayoutCreateInfo pli{VK_STRUCTURE_TYPE_PIPELINE_LAYOUT_CREATE_INFO, nullptr, 0, 1, &setLayout, sc.pushConstants.empty() ? 0u : 1u, sc.pushConstants.empty() ? nullptr : &pcr};
     VkPipelineLayout pipeLayout; VK(vkCreatePipelineLayout(app.device, &pli, nullptr, &pipeLayout));
     // init_renderpass (loadOp CLEAR / storeOp STORE) + init_framebuffers
     std::vector<VkAttachmentDescription> atts;
@@ -332,8 +340,9 @@ int main(int argc, char** argv) {
     VkDescriptorSet dset; VK(vkAllocateDescriptorSets(app.device, &dsa, &dset));
     std::vector<VkDescriptorBufferInfo> binfos(sc.uniforms.size()); std::vector<VkDescriptorImageInfo> iinfos(sc.textures.size() * 2); std::vector<VkWriteDescriptorSet> writes;
     for (size_t i = 0; i < sc.uniforms.size(); i++) {
-        binfos[i] = {bufs.at(sc.uniforms[i].name), 0, sc.buffers.at(sc.uniforms[i].name).size};
-        writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, sc.uniforms[i].binding, 0, 1, VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, nullptr, &binfos[i], nullptr});
+        const bool dyn = sc.uniforms[i].dynRange != 0; // dynamic_uniform.cpp:196-215: the descriptor covers one element, the offset picks it at bind time
+        binfos[i] = {bufs.at(sc.uniforms[i].name), 0, dyn ? (VkDeviceSize)sc.uniforms[i].dynRange : sc.buffers.at(sc.uniforms[i].name).size};
+        writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, sc.uniforms[i].binding, 0, 1, dyn ? VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC : VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, nullptr, &binfos[i], nullptr});
     }
     for (size_t i = 0; i < sc.textures.size(); i++) {
         auto& t = sc.textures[i];
@@ -366,8 +375,12 @@ int main(int argc, char** argv) {
     VkShaderModuleCreateInfo smi{VK_STRUCTURE_TYPE_SHADER_MODULE_CREATE_INFO, nullptr, 0, vsb.size(), (const uint32_t*)vsb.data()};
     VkShaderModule vsm, fsm; VK(vkCreateShaderModule(app.device, &smi, nullptr, &vsm));
     smi.codeSize = fsb.size(); smi.pCode = (const uint32_t*)fsb.data(); VK(vkCreateShaderModule(app.device, &smi, nullptr, &fsm));
-    VkPipelineShaderStageCreateInfo stages[2] = {{VK_STRUCTURE_TYPE_PIPELINE_SHADER_STAGE_CREATE_INFO, nullptr, 0, VK_SHADER_STAGE_VERTEX_BIT, vsm, "main", nullptr},
-                                                 {VK_STRUCTURE_TYPE_PIPELINE_SHADER_STAGE_CREATE_INFO, nullptr, 0, VK_SHADER_STAGE_FRAGMENT_BIT, fsm, "main", nullptr}};
+    // spirv_specialization.cpp: one 32-bit value per constant id, packed back to back
+    VkSpecializationInfo specInfo[2] = {}; std::vector<VkSpecializationMapEntry> specEntries[2]; std::vector<uint32_t> specData[2];
+    for (auto& sp : sc.specs) { const uint32_t st = sp.stage ? 1u : 0u; specEntries[st].push_back({sp.id, (uint32_t)(specData[st].size() * 4), 4}); specData[st].push_back(sp.value); }
+    for (int st = 0; st < 2; st++) specInfo[st] = {(uint32_t)specEntries[st].size(), specEntries[st].data(), specData[st].size() * 4, specData[st].data()};
+    VkPipelineShaderStageCreateInfo stages[2] = {{VK_STRUCTURE_TYPE_PIPELINE_SHADER_STAGE_CREATE_INFO, nullptr, 0, VK_SHADER_STAGE_VERTEX_BIT, vsm, "main", specEntries[0].empty() ? nullptr : &specInfo[0]},
+                                                 {VK_STRUCTURE_TYPE_PIPELINE_SHADER_STAGE_CREATE_INFO, nullptr, 0, VK_SHADER_STAGE_FRAGMENT_BIT, fsm, "main", specEntries[1].empty() ? nullptr : &specInfo[1]}};
     VkPipelineVertexInputStateCreateInfo vis{VK_STRUCTURE_TYPE_PIPELINE_VERTEX_INPUT_STATE_CREATE_INFO, nullptr, 0, (uint32_t)sc.bindings.size(), sc.bindings.data(), (uint32_t)sc.attributes.size(), sc.attributes.data()};
     VkPipelineInputAssemblyStateCreateInfo ias{VK_STRUCTURE_TYPE_PIPELINE_INPUT_ASSEMBLY_STATE_CREATE_INFO, nullptr, 0, (VkPrimitiveTopology)sc.topology, VK_FALSE};
     VkPipelineViewportStateCreateInfo vps{VK_STRUCTURE_TYPE_PIPELINE_VIEWPORT_STATE_CREATE_INFO, nullptr, 0, 1, nullptr, 1, nullptr};
@@ -425,7 +438,11 @@ int main(int argc, char** argv) {
         VK(vkBeginCommandBuffer(rec, &sbeg));
     }
     vkCmdBindPipeline(rec, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeline);
-    vkCmdBindDescriptorSets(rec, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeLayout, 0, 1, &dset, 0, nullptr);
+    std::vector<uint32_t> dynOffsets; // in binding order, as the API defines for dynamic descriptors of one set
+    { std::vector<std::pair<uint32_t, uint32_t>> byBinding; for (auto& u : sc.uniforms) if (u.dynRange) byBinding.push_back({u.binding, u.dynOffset});
+      std::sort(byBinding.begin(), byBinding.end()); for (auto& kv : byBinding) dynOffsets.push_back(kv.second); }
+    vkCmdBindDescriptorSets(rec, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeLayout, 0, 1, &dset, (uint32_t)dynOffsets.size(), dynOffsets.empty() ? nullptr : dynOffsets.data());
+    if (!sc.pushConstants.empty()) vkCmdPushConstants(rec, pipeLayout, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, 0, (uint32_t)sc.pushConstants.size(), sc.pushConstants.data());
     for (auto& kv : sc.vertexBuffers) { VkDeviceSize off = 0; VkBuffer b = bufs.at(kv.second); vkCmdBindVertexBuffers(rec, kv.first, 1, &b, &off); }
     VkViewport vp{sc.viewport[0], sc.viewport[1], sc.viewport[2], sc.viewport[3], sc.viewport[4], sc.viewport[5]};
     vkCmdSetViewport(rec, 0, 1, &vp);

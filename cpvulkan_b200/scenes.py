@@ -95,6 +95,8 @@ class Scene:
         self.viewport = None                     # (x, y, w, h, minDepth, maxDepth)
         self.count, self.instances, self.first, self.vertex_offset, self.first_instance = 0, 1, 0, 0, 0
         self.push_constants = b""
+        self.spec_constants = {"vertex": [], "fragment": []}   # per stage: (constantId, 32-bit value as u32)
+        self.uniform_dynamic = {}                # uniform buffer name -> (dynamic offset, range): bound as UNIFORM_BUFFER_DYNAMIC
         self.line_width = 1.0
         self.mutate = None                       # optional callable(Materialized): last-minute edits of the PODs, applied on every backend
 
@@ -163,7 +165,14 @@ def materialize(scene, alloc):
         ds = s.descriptors[nd]
         ds.set, ds.binding, ds.type = set_, binding, capi.DESC_BUFFER
         ds.address, ds.range = m.addr[name], scene.buffers[name].nbytes
+        if name in scene.uniform_dynamic:  # LoadUniforms adds the dynamic offset to the descriptor's own (Draw.cpp:379-396)
+            off, rng = scene.uniform_dynamic[name]
+            ds.address, ds.range = m.addr[name] + off, rng
         nd += 1
+    for stage, target in (("vertex", m.desc.vertex), ("fragment", m.desc.fragment)):
+        target.specCount = len(scene.spec_constants[stage])
+        for i, (cid, value) in enumerate(scene.spec_constants[stage]):
+            target.spec[i].constantId, target.spec[i].value = cid, value
     for t in scene.textures:
         ds = s.descriptors[nd]
         img = t.image
@@ -636,6 +645,11 @@ def export_scene(scene, directory):
     if scene.blend:
         bl = scene.blend
         lines.append("blend %d %d %d %d %d %d" % (bl["src"], bl["dst"], bl["op"], bl.get("srcA", bl["src"]), bl.get("dstA", bl["dst"]), bl.get("opA", bl["op"])))
+    if scene.push_constants:
+        lines.append("push_constants %d %s" % (len(scene.push_constants), bytes(scene.push_constants).hex()))
+    for stage, tag in (("vertex", 0), ("fragment", 1)):
+        for cid, value in scene.spec_constants[stage]:
+            lines.append("spec %d %d %d" % (tag, cid, value))
     for name, data in scene.buffers.items():
         fn = "buf_%s.bin" % name
         np.ascontiguousarray(data).tofile(os.path.join(directory, fn))
@@ -645,7 +659,8 @@ def export_scene(scene, directory):
     if scene.index_buffer:
         lines.append("index_buffer %s %d" % (scene.index_buffer, scene.index_stride))
     for set_, binding, name in scene.uniforms:
-        lines.append("uniform %d %d %s" % (set_, binding, name))
+        dyn = scene.uniform_dynamic.get(name)
+        lines.append("uniform %d %d %s" % (set_, binding, name) + (" %d %d" % dyn if dyn else ""))
     for set_, binding, name, fmt in scene.texel_buffers:
         lines.append("texel_buffer %d %d %s %d" % (set_, binding, name, fmt))
     for t in scene.textures:

@@ -122,3 +122,30 @@ def test_icd_input_attachment(built, tmp_path):
     # Samples/input_attachment: INPUT_ATTACHMENT descriptor read with subpassLoad (OpImageRead -> @Image.Read = ImageFetch at the
     # coordinate as written, GlslFunctions.cpp:739-743)
     check(scenes.input_attachment(200, 160), tmp_path)
+
+
+@pytest.mark.parametrize("iterations,threshold,scale", [(4, 0.9, None), (9, 100.0, 1.25)])
+def test_icd_push_constants_and_specialization(built, tmp_path, iterations, threshold, scale):
+    # Samples/push_constants + Samples/spirv_specialization: vkCmdPushConstants (CommandBuffer.cpp:552-556) and
+    # VkSpecializationInfo on the fragment stage, feeding the loop / function-call / OpKill shader of the front-end breadth test
+    import struct
+    sc = scenes.random_triangles(width=64, height=48, tris=120, seed=81)
+    sc.fs = "complex.frag"
+    sc.push_constants = struct.pack("<4fif", 0.3, 0.1, 0.2, 0.05, iterations, threshold)
+    if scale is not None:
+        sc.spec_constants["fragment"] = [(3, struct.unpack("<I", struct.pack("<f", scale))[0])]
+    check(sc, tmp_path)
+
+
+def test_icd_dynamic_uniform_offset(built, tmp_path):
+    # Samples/dynamic_uniform: UNIFORM_BUFFER_DYNAMIC whose offset arrives with vkCmdBindDescriptorSets (Binding.cpp:58-80); the
+    # matrix the draw must use sits 256 bytes into the buffer, behind a decoy
+    sc = scenes.draw_cube(200, 160)
+    mvp = sc.buffers["ubo"]
+    decoy = np.zeros(256, dtype=np.uint8)
+    sc.buffers["ubo"] = np.concatenate([decoy, mvp, np.zeros(192, dtype=np.uint8)])
+    sc.uniform_dynamic["ubo"] = (256, 64)
+    info = check(sc, tmp_path)
+    oc, _, _ = scenes.run_oracle(scenes.draw_cube(200, 160))
+    gc, _, _ = scenes.run_icd(sc, str(tmp_path))
+    assert np.array_equal(oc, gc), "the dynamic offset must select the same matrix the plain cube uses"
