@@ -455,3 +455,49 @@ def test_separate_image_and_sampler(dev, filt):
 
 def test_input_attachment_read(dev):
     compare(dev, scenes.input_attachment(300, 220))
+
+
+# ---- empty and ragged inputs (CalculatePrimitives, Draw.cpp:567-673: count / 3 triangles, the remainder is dropped) ----
+
+@pytest.mark.parametrize("count", [0, 1, 2, 3, 4, 5, 7])
+@pytest.mark.parametrize("topology", [scenes.TRIANGLE_LIST, scenes.TRIANGLE_STRIP, scenes.TRIANGLE_FAN])
+def test_empty_and_ragged_vertex_counts(dev, count, topology):
+    sc = scenes.random_triangles(width=64, height=48, tris=8, seed=91, topology=topology)  # at least 10 vertices in the buffer
+    sc.count = count
+    st = compare(dev, sc)
+    assert st.primitives == (count // 3 if topology == scenes.TRIANGLE_LIST else max(count - 2, 0))
+
+
+@pytest.mark.parametrize("count", [0, 2, 4, 11])
+@pytest.mark.parametrize("stride", [1, 2, 4])
+def test_ragged_index_counts(dev, count, stride):
+    sc = scenes.random_triangles(width=64, height=48, tris=6, seed=92, indexed=stride)
+    sc.count = count
+    compare(dev, sc)
+
+
+def test_zero_instances_draw_nothing(dev):
+    sc = scenes.random_triangles(width=64, height=48, tris=20, seed=93)
+    sc.instances = 0
+    st = compare(dev, sc)
+    assert st.fragmentsCovered == 0
+
+
+def test_everything_culled_or_off_screen(dev):
+    sc = scenes.random_triangles(width=64, height=48, tris=50, seed=94, cull=3)  # FRONT_AND_BACK
+    assert compare(dev, sc).fragmentsCovered == 0
+    sc = scenes.random_triangles(width=64, height=48, tris=50, seed=95)
+    vb = sc.buffers["vb"].view(np.float32).reshape(-1, 8).copy()
+    vb[:, 0] += 5.0  # all of it to the right of the viewport (w == 1 .. 3: still outside after the divide)
+    vb[:, 0] *= 4.0
+    sc.buffers["vb"] = vb.view(np.uint8).reshape(-1)
+    assert compare(dev, sc).fragmentsCovered == 0
+
+
+def test_back_to_back_empty_and_full_draws_share_the_device(dev):
+    # an empty draw must leave the device's speculative launch plan and scratch in a usable state for the next draw
+    empty = scenes.random_triangles(width=64, height=48, tris=4, seed=96); empty.count = 0
+    compare(dev, empty)
+    compare(dev, scenes.random_triangles(width=200, height=150, tris=400, seed=97))
+    compare(dev, empty)
+    compare(dev, scenes.draw_cube(128, 128))
