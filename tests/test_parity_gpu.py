@@ -501,3 +501,19 @@ def test_back_to_back_empty_and_full_draws_share_the_device(dev):
     compare(dev, scenes.random_triangles(width=200, height=150, tris=400, seed=97))
     compare(dev, empty)
     compare(dev, scenes.draw_cube(128, 128))
+
+
+# ---- maximum sizes ----
+
+def test_widest_and_tallest_render_targets(dev):
+    """The bbox records hold 16-bit pixel coordinates: 32767 is the largest extent the path takes (larger is refused, below)."""
+    compare(dev, scenes.random_triangles(width=32767, height=3, tris=6, seed=98, depth_fmt=scenes.D16_UNORM))
+    compare(dev, scenes.random_triangles(width=5, height=32767, tris=6, seed=99, depth_fmt=None))
+
+
+def test_render_targets_beyond_the_limit_are_refused(dev):
+    from cpvulkan_b200.device import CpvkError
+    with pytest.raises(CpvkError) as e:
+        run_cuda(dev, scenes.random_triangles(width=32768, height=2, tris=2, seed=1, depth_fmt=None))
+    assert "32767" in str(e.value)
+    compare(dev, scenes.draw_cube(64, 64))  # the device is still usable

@@ -204,3 +204,41 @@ def test_misaligned_images_are_refused(dev):
     with pytest.raises(CpvkError):
         dev.blit(capi.Blit(bad, img.att("dev"), 0, 0, 8, 8, 0, 0, 8, 8, 0))
     img.free()
+
+
+# ---- empty and degenerate regions ----
+
+def test_empty_copies_and_blits_change_nothing(dev):
+    """Zero rows, zero row bytes, and blit rectangles with no area (the reference's loops simply do not execute,
+    CommandBuffer.cpp:75-226, CommandBuffer.Copy.cpp): the destination keeps every byte."""
+    lib = capi.load_oracle()
+    src = Image(dev, R8G8B8A8_UNORM, 16, 16, 0, seed=21)
+    dst = Image(dev, R8G8B8A8_UNORM, 16, 16, 0, seed=22)
+    dev.copy_rows(dst.addr, dst.pitch, src.addr, src.pitch, 0, 16)
+    dev.copy_rows(dst.addr, dst.pitch, src.addr, src.pitch, 64, 0)
+    for rect in ((4, 4, 4, 12), (4, 4, 12, 4), (0, 0, 0, 0)):
+        hb = capi.Blit(src.att("host"), dst.att("host"), 0, 0, 16, 16, rect[0], rect[1], rect[2], rect[3], 1)
+        db = capi.Blit(src.att("dev"), dst.att("dev"), 0, 0, 16, 16, rect[0], rect[1], rect[2], rect[3], 1)
+        assert lib.cpvk_oracle_blit(C.byref(hb)) == 0
+        dev.blit(db)
+    dst.check()
+    src.free(); dst.free()
+
+
+@pytest.mark.parametrize("filt", [0, 1])
+def test_one_texel_images(dev, filt):
+    lib = capi.load_oracle()
+    src = Image(dev, R8G8B8A8_UNORM, 1, 1, 0, seed=23)
+    dst = Image(dev, R16G16B16A16_SFLOAT, 7, 5, 0, seed=24)
+    hb = capi.Blit(src.att("host"), dst.att("host"), 0, 0, 1, 1, 0, 0, 7, 5, filt)
+    db = capi.Blit(src.att("dev"), dst.att("dev"), 0, 0, 1, 1, 0, 0, 7, 5, filt)
+    assert lib.cpvk_oracle_blit(C.byref(hb)) == 0
+    dev.blit(db)
+    dst.check()
+    back = Image(dev, R8G8B8A8_UNORM, 1, 1, 0, seed=25)
+    hb = capi.Blit(dst.att("host"), back.att("host"), 0, 0, 7, 5, 0, 0, 1, 1, filt)
+    db = capi.Blit(dst.att("dev"), back.att("dev"), 0, 0, 7, 5, 0, 0, 1, 1, filt)
+    assert lib.cpvk_oracle_blit(C.byref(hb)) == 0
+    dev.blit(db)
+    back.check()
+    src.free(); dst.free(); back.free()
