@@ -36,10 +36,38 @@ FunctionPointer CompileSetPixelU32(CPJit*, const FormatInformation*) { return Un
 
 struct Config { uint32_t mag, min, mipmap, addressU, addressV, border; float lod; };
 
+// "3d" mode — the overload vkCmdBlitImage uses (CommandBuffer.cpp:75-226): SampleImage(state, format, data, uvec3 range, fvec3
+// coordinates, filter) = lod 1, CLAMP_TO_EDGE, so the MINIFICATION filter on the single level, eight taps when LINEAR.
+// input: u32 w, h, d, nCoords; w*h*d*4 floats; coords (u, v, w). Output: for filter NEAREST then LINEAR, nCoords lines.
+static int Main3D(const char* path) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) return 2;
+    uint32_t hdr[4];
+    in.read(reinterpret_cast<char*>(hdr), 16);
+    std::vector<float> texels((size_t)hdr[0] * hdr[1] * hdr[2] * 4);
+    in.read(reinterpret_cast<char*>(texels.data()), texels.size() * 4);
+    std::vector<float> coords((size_t)hdr[3] * 3);
+    in.read(reinterpret_cast<char*>(coords.data()), coords.size() * 4);
+    if (!in) return 2;
+    auto state = std::make_unique<DeviceState>();
+    state->jit = nullptr;
+    gsl::span<uint8_t> data(reinterpret_cast<uint8_t*>(texels.data()), (std::ptrdiff_t)(texels.size() * 4));
+    for (VkFilter filter : {VK_FILTER_NEAREST, VK_FILTER_LINEAR})
+        for (uint32_t i = 0; i < hdr[3]; i++) {
+            const glm::fvec4 r = SampleImage<glm::fvec4>(state.get(), VK_FORMAT_R32G32B32A32_SFLOAT, data, glm::uvec3(hdr[0], hdr[1], hdr[2]),
+                                                         glm::fvec3(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2]), filter);
+            uint32_t b[4];
+            std::memcpy(b, &r.x, 16);
+            std::printf("%u %u %u %u\n", b[0], b[1], b[2], b[3]);
+        }
+    return 0;
+}
+
 // input file (little endian): u32 levels, nConfigs, nCoords; per level u32 w, h then w*h*4 floats; configs; coords (u, v)
 // output on stdout: nConfigs * nCoords lines of four float bit patterns
 int main(int argc, char** argv) {
-    if (argc < 2) { std::fprintf(stderr, "usage: sampler_check input.bin\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: sampler_check input.bin | sampler_check 3d input.bin\n"); return 2; }
+    if (argc > 2 && !std::strcmp(argv[1], "3d")) return Main3D(argv[2]);
     std::ifstream in(argv[1], std::ios::binary);
     if (!in) return 2;
     uint32_t hdr[3];

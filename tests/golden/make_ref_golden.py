@@ -89,8 +89,27 @@ def sampler_golden():
     print("sampler: %d configurations x %d coordinates" % (len(cfg), len(coords)))
 
 
+def sampler3d_golden():
+    """The 3-D SampleImage overload vkCmdBlitImage goes through, on a 6x5x1 image (what a 2-D blit source is) and a 4x3x2 one."""
+    import tempfile
+    rng = np.random.RandomState(77)
+    out = {}
+    for tag, (w, h, d) in (("a", (6, 5, 1)), ("b", (4, 3, 2))):
+        tex = rng.uniform(-3.0, 3.0, size=(d, h, w, 4)).astype(np.float32)
+        us = np.array([-0.3, 0.0, 0.5 / w, 0.37, 0.5, 1 - 1e-7, 1.0, 1.4], dtype=np.float32)
+        coords = np.array([[u, v, z] for u in us for v in us[1:6] for z in (0.0, 0.25, 0.5, 0.75, 1.0)], dtype=np.float32)
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            f.write(np.array([w, h, d, len(coords)], dtype="<u4").tobytes()); f.write(tex.tobytes()); f.write(coords.tobytes()); f.flush()
+            lines = subprocess.run([SAMPLER_CHECK, "3d", f.name], stdout=subprocess.PIPE, text=True, check=True).stdout.splitlines()
+        bits = np.array([[int(x) for x in l.split()] for l in lines], dtype=np.uint32).reshape(2, len(coords), 4)
+        out["tex_" + tag], out["coords_" + tag], out["bits_" + tag] = tex, coords, bits
+    np.savez_compressed(os.path.join(HERE, "ref_sampler3d.npz"), **out)
+    print("sampler 3d: %d + %d coordinates x 2 filters" % (len(out["coords_a"]), len(out["coords_b"])))
+
+
 def main():
     sampler_golden()
+    sampler3d_golden()
     open(os.path.join(HERE, "ref_formats.txt"), "w").write(run("formats"))
     open(os.path.join(HERE, "ref_layout.txt"), "w").write(run("layout"))
     half = np.array([int(l.split()[2]) for l in run("half").splitlines()], dtype=np.uint32)

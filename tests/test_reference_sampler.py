@@ -67,3 +67,36 @@ def test_golden_file_is_what_the_reference_returns(tmp_path):
     out = subprocess.run([CHECK, str(path)], stdout=subprocess.PIPE, text=True, check=True).stdout
     bits = np.array([[int(x) for x in l.split()] for l in out.splitlines()], dtype=np.uint32).reshape(g["result_bits"].shape)
     assert np.array_equal(bits, g["result_bits"])
+    g3 = np.load(os.path.join(ROOT, "tests", "golden", "ref_sampler3d.npz"))
+    for tag in ("a", "b"):
+        tex, coords = g3["tex_" + tag], g3["coords_" + tag]
+        path3 = tmp_path / ("in3d_%s.bin" % tag)
+        with open(path3, "wb") as f:
+            f.write(np.array([tex.shape[2], tex.shape[1], tex.shape[0], len(coords)], dtype="<u4").tobytes())
+            f.write(np.ascontiguousarray(tex).tobytes()); f.write(np.ascontiguousarray(coords).tobytes())
+        out = subprocess.run([CHECK, "3d", str(path3)], stdout=subprocess.PIPE, text=True, check=True).stdout
+        bits = np.array([[int(x) for x in l.split()] for l in out.splitlines()], dtype=np.uint32).reshape(g3["bits_" + tag].shape)
+        assert np.array_equal(bits, g3["bits_" + tag])
+
+
+def test_oracle_3d_sampling_as_used_by_blit_matches_reference(oracle):
+    """SampleImage(state, format, data, uvec3 range, fvec3 coordinates, filter) — the overload vkCmdBlitImage calls
+    (CommandBuffer.cpp:75-226): lod 1, CLAMP_TO_EDGE on all axes, the minification filter on the only level, eight taps and
+    seven double lerps when LINEAR. tests/golden/ref_sampler3d.npz holds the reference binary's results."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_sampler3d.npz"))
+    for tag in ("a", "b"):
+        tex = np.ascontiguousarray(g["tex_" + tag]); coords = np.ascontiguousarray(g["coords_" + tag])
+        depth, h, w, _ = tex.shape
+        for filt in (0, 1):
+            d = capi.Descriptor()
+            d.type, d.format, d.dimensions, d.levelCount = capi.DESC_IMAGE, RGBA32F, 3, 1
+            d.levels[0] = capi.MipLevel(tex.ctypes.data, w, h, depth, 0)
+            s = d.sampler
+            s.magFilter = s.minFilter = filt
+            s.addressModeU = s.addressModeV = s.addressModeW = 2  # CLAMP_TO_EDGE
+            s.mipLodBias, s.minLod, s.maxLod = 0.0, 0.0, 1000.0
+            got = np.zeros((len(coords), 4), dtype=np.float32)
+            oracle.cpvk_oracle_sample(C.byref(d), coords.ctypes.data_as(C.c_void_p), len(coords), C.c_float(1.0), got.ctypes.data_as(C.c_void_p))
+            bad = np.nonzero(np.any(got.view(np.uint32) != g["bits_" + tag][filt], axis=1))[0]
+            assert len(bad) == 0, "image %s filter %d coordinate %s: oracle %s reference %s" % (
+                tag, filt, coords[bad[0]], got[bad[0]], g["bits_" + tag][filt][bad[0]].view(np.float32))
