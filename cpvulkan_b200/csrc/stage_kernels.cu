@@ -192,6 +192,12 @@ extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 // the ordering the reference gets from its nested loops (Draw.cpp:1526-1593). Colour and depth live in shared
 // memory in their *storage* format for the whole tile lifetime: every ROP is the reference's get/set-pixel
 // round trip (GlslFunctions.cpp:842-928) on shared memory, and HBM sees one read and one write per tile byte.
+#ifndef CPVK_COVER_ROWS
+#define CPVK_COVER_ROWS 5   /* rows of the coverage window evaluated per pass over its columns (measured on C3/M1: 2 -> 242 us, 4 -> 235, 5 -> 228, 6 -> 231, 8 -> 249 with spills) */
+#endif
+#ifndef CPVK_COVER_UNROLL
+#define CPVK_COVER_UNROLL 1
+#endif
 #ifndef CPVK_RASTER_MIN_CTAS
 #define CPVK_RASTER_MIN_CTAS 4 /* resident CTAs per SM the register allocation aims for; build.py builds 4, 3 and 2 */
 #endif
@@ -655,32 +661,37 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                         const cpvk_u32 rowMask = small ? ((1u << cw) - 1u) : 0u; // cw <= 16
                         const int rows = small ? ch : 0;
                         int shift = 0;
-                        // Two rows per pass: A_k(x) = (xf - ax_k) * dy_k does not depend on the row and B_k(y) = (yf - ay_k) *
+                        // CPVK_COVER_ROWS rows per pass: A_k(x) = (xf - ax_k) * dy_k does not depend on the row and B_k(y) = (yf - ay_k) *
                         // dx_k not on the column, so a column's three A terms are compared against both rows' B terms
                         // (same operations on the same operands as the per-pixel expression: identical bits).
-                        const float* yp = sYf + by; // by + yy + 1 <= 40: stays inside the xf/yf/lut block, masked by `rows`
+                        const float* yp = sYf + by; // by + yy + CPVK_COVER_ROWS - 1 < 48: stays inside the xf/yf/lut block, masked by `rows`
                         #pragma unroll 1
-                        for (int yy = 0; yy < maxH; yy += 2) {
-                            const float yf0 = yp[yy], yf1 = yp[yy + 1];
-                            const float b00 = (yf0 - e0ay) * e0dx, b01 = (yf0 - e1ay) * e1dx, b02 = (yf0 - e2ay) * e2dx;
-                            const float b10 = (yf1 - e0ay) * e0dx, b11 = (yf1 - e1ay) * e1dx, b12 = (yf1 - e2ay) * e2dx;
-                            cpvk_u32 r0 = 0, r1 = 0, bit = 1u;
+                        for (int yy = 0; yy < maxH; yy += CPVK_COVER_ROWS) {
+                            float b0[CPVK_COVER_ROWS], b1[CPVK_COVER_ROWS], b2[CPVK_COVER_ROWS];
+                            cpvk_u32 r[CPVK_COVER_ROWS];
+                            #pragma unroll
+                            for (int k = 0; k < CPVK_COVER_ROWS; k++) {
+                                const float yf = yp[yy + k];
+                                b0[k] = (yf - e0ay) * e0dx; b1[k] = (yf - e1ay) * e1dx; b2[k] = (yf - e2ay) * e2dx; r[k] = 0;
+                            }
+                            cpvk_u32 bit = 1u;
                             const float* xp = sXf + bx; // bx + xx <= 46: stays inside the xf/yf/lut block
                             const float* const xe = xp + maxW;
-                            #pragma unroll 1
+                            constexpr int kCoverUnroll = CPVK_COVER_UNROLL;
+                            #pragma unroll kCoverUnroll
                             for (; xp != xe; xp++, bit <<= 1) {
                                 const float xf = *xp;
                                 const float a0 = (xf - e0ax) * e0dy, a1 = (xf - e1ax) * e1dy, a2 = (xf - e2ax) * e2dy;
                                 // inside = !(a0 < b0 || a1 < b1 || a2 < b2) = (a0 >=u b0) && (a1 >=u b1) && (a2 >=u b2), "u" = or unordered:
                                 // three chained predicate compares and one predicated OR per pixel
-                                #define CPVK_COVER(r, x0, x1, x2) asm("{ .reg .pred q; setp.geu.f32 q, %1, %2; setp.geu.and.f32 q, %3, %4, q; setp.geu.and.f32 q, %5, %6, q; @q or.b32 %0, %0, %7; }" \
-                                                                     : "+r"(r) : "f"(a0), "f"(x0), "f"(a1), "f"(x1), "f"(a2), "f"(x2), "r"(bit))
-                                CPVK_COVER(r0, b00, b01, b02);
-                                CPVK_COVER(r1, b10, b11, b12);
-                                #undef CPVK_COVER
+                                #pragma unroll
+                                for (int k = 0; k < CPVK_COVER_ROWS; k++)
+                                    asm("{ .reg .pred q; setp.geu.f32 q, %1, %2; setp.geu.and.f32 q, %3, %4, q; setp.geu.and.f32 q, %5, %6, q; @q or.b32 %0, %0, %7; }"
+                                        : "+r"(r[k]) : "f"(a0), "f"(b0[k]), "f"(a1), "f"(b1[k]), "f"(a2), "f"(b2[k]), "r"(bit));
                             }
-                            if (yy < rows) { cov |= (r0 & rowMask) << shift; shift += cw; }
-                            if (yy + 1 < rows) { cov |= (r1 & rowMask) << shift; shift += cw; }
+                            #pragma unroll
+                            for (int k = 0; k < CPVK_COVER_ROWS; k++)
+                                if (yy + k < rows) { cov |= (r[k] & rowMask) << shift; shift += cw; }
                         }
                     } else {
                         int xx = 0, yy = 0;
