@@ -312,13 +312,74 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     achieved = b_alg / (ms_raster * 1e-3) / 1e9 if ms_raster > 0 else 0.0
 
+    # e2e on N > 1 GPUs (every rank takes part): each frame, every rank uploads the (replicated) geometry from its own pinned
+    # buffers over its own PCIe link, renders its band — the fused gather and its barrier stay in the frame — and reads ITS band
+    # back into pinned host memory: the host ends up with the whole frame, one band per process, 1/N of the read-back per link.
+    # The read-back of frame k overlaps the upload and rendering of frame k+1: the finished band is copied to one of two
+    # staging buffers on the draw stream (16 MB, device to device) and a second device object, on its own stream, carries
+    # it to the host; events order the two streams in both directions.
+    e2e_multi = None
+    if world > 1:
+        names = ["vb", "ib", "ubo"]
+        staged = {}
+        for nme in names:
+            data = scene.buffers[nme]
+            a = dev.alloc(data.nbytes, host_shadow=True)
+            dev.shadow(a)[:data.nbytes] = data
+            staged[nme] = (a, data.nbytes)
+        stream2 = torch.cuda.Stream()
+        dev2 = Device(local, stream=stream2.cuda_stream, stats=False)
+        band_addr = color_t.data_ptr() + rank * band_bytes
+        slots = []
+        for _ in range(2):
+            staging = torch.empty(band_bytes, dtype=torch.uint8, device="cuda")
+            out_dev = dev2.alloc(band_bytes, host_shadow=True)  # only its pinned shadow is used, as the read-back target
+            slots.append({"staging": staging, "host": dev2.allocs[out_dev][1], "copied": torch.cuda.Event(), "read": torch.cuda.Event()})
+            slots[-1]["read"].record(stream2)
+
+        def e2e_frame(k):
+            sl = slots[k % 2]
+            for nme in names:
+                src_alloc, nbytes = staged[nme]
+                dev.upload_async(sod.m.addr[nme], dev.allocs[src_alloc][1], nbytes)
+            frame()
+            stream.wait_event(sl["read"])                       # the staging buffer's previous contents have reached the host
+            dev.copy_rows(sl["staging"].data_ptr(), band_bytes, band_addr, band_bytes, band_bytes, 1)
+            sl["copied"].record(stream)
+            stream2.wait_event(sl["copied"])
+            dev2.download_into_async(sl["host"], sl["staging"].data_ptr(), band_bytes)
+            sl["read"].record(stream2)
+
+        for k in range(4):
+            e2e_frame(k)
+        torch.cuda.synchronize()
+        want = color_t[rank * band_bytes:(rank + 1) * band_bytes].cpu()
+        for sl in slots:
+            got = torch.from_numpy(np.ctypeslib.as_array(C.cast(sl["host"], C.POINTER(C.c_uint8)), shape=(band_bytes,)).copy())
+            if not torch.equal(got, want):
+                raise SystemExit("e2e read-back of rank %d's band differs from the resident frame" % rank)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            e2e_frame(k)
+        barrier()  # torch.cuda.synchronize() inside: both streams have drained
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+        e2e_multi = {"value": prims / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": world * sum(v[1] for v in staged.values()),
+                     "d2h_bytes_per_step": world * band_bytes, "ms_per_step": e2e_ms,
+                     "through": "C ABI on every rank (cpvk_cuda_mem_upload of the replicated geometry / clear / draw with the fused gather / copy_rows of "
+                                "the rank's band to a staging buffer / mem_download_async on a second device object), pinned host buffers, "
+                                "read-back of frame k overlapped with frame k+1; max over ranks"}
+        dev2.close()
+
     line = None
     if rank == 0:
         # e2e through the C ABI with HOST buffers: every frame uploads its inputs (vertices, indices, uniforms) from pinned
         # host memory, clears, draws and reads the colour result back into pinned host memory. Like a double-buffered
         # application, two device objects (each with its own stream, scratch and frame) alternate frames, so the read-back of
         # frame k overlaps the upload and rendering of frame k+1; a frame's buffers are reused only after its read-back is done.
-        e2e = None
+        e2e = e2e_multi
         if world == 1:
             names = ["vb", "ib", "ubo"]
             lanes = []
