@@ -382,3 +382,77 @@ def test_blend_against_scalar_model(oracle, blend):
     # the source colour reaches the blender through perspective interpolation, (w0*c + w1*c + w2*c) / (w0 + w1 + w2), which is c only
     # to the last bit or two and differs per pixel — so this KAT pins factor / op selection and operand order to 1e-5, not the bits
     assert np.allclose(got, np.broadcast_to(d, got.shape), rtol=1e-5, atol=1e-6), (got[0], d)
+
+
+# ---- points and lines: the oracle's coverage against independent numpy restatements of Draw.cpp:1315-1508 ----
+
+def cvtt(v):  # static_cast<int32_t>(float) on x86: truncation, INT_MIN when out of range or NaN
+    v = np.float32(v)
+    return -2**31 if (np.isnan(v) or v >= np.float32(2**31) or v < np.float32(-2**31)) else int(np.trunc(v))
+
+
+def numpy_point_coverage(scene):
+    vb = scene.buffers["vb"].view(np.float32).reshape(-1, 9)
+    W, H = np.float32(scene.color.width), np.float32(scene.color.height)
+    n = 0
+    for v in vb[:scene.count]:
+        w = v[3]
+        X, Y = np.float32(v[0] / w), np.float32(v[1] / w)
+        sx = cvtt(np.float32(np.float32(np.float32(X + np.float32(1)) * np.float32(0.5)) * np.float32(W - np.float32(1))))
+        sy = cvtt(np.float32(np.float32(np.float32(Y + np.float32(1)) * np.float32(0.5)) * np.float32(H - np.float32(1))))
+        size = np.float32(v[8])
+        half = cvtt(np.ceil(np.float32(size / np.float32(2))))
+        x0, y0 = max(0, sx - half), max(0, sy - half)
+        x1, y1 = min(int(W), sx + half + 1), min(int(H), sy + half + 1)
+        if x1 <= x0 or y1 <= y0:
+            continue
+        xs = np.arange(x0, x1, dtype=np.int64); ys = np.arange(y0, y1, dtype=np.int64)
+        s = np.float32(0.5) + ((xs - sx).astype(np.float32) / size).astype(np.float32)
+        t = np.float32(0.5) + ((ys - sy).astype(np.float32) / size).astype(np.float32)
+        n += int(np.count_nonzero((s >= 0) & (s <= 1))) * int(np.count_nonzero((t >= 0) & (t <= 1)))
+    return n
+
+
+def numpy_line_coverage(scene):
+    vb = scene.buffers["vb"].view(np.float32).reshape(-1, 9)[:scene.count]
+    W, H = np.float32(scene.color.width), np.float32(scene.color.height)
+    f = np.float32
+    xs = ((np.arange(int(W), dtype=np.float32) / W + (f(1) / W) * f(0.5)) * f(2) - f(1)).astype(np.float32)
+    ys = ((np.arange(int(H), dtype=np.float32) / H + (f(1) / H) * f(0.5)) * f(2) - f(1)).astype(np.float32)
+    X, Y = np.meshgrid(xs, ys)
+    pairs = [(2 * i, 2 * i + 1) for i in range(len(vb) // 2)] if scene.topology == F.LINE_LIST else [(i, i + 1) for i in range(len(vb) - 1)]
+    lw = np.array([f(scene.line_width) / W, f(scene.line_width) / H], dtype=np.float32)
+
+    def E(a, b):  # EdgeFunction(a, b, p) = (p.x - a.x) * (b.y - a.y) - (p.y - a.y) * (b.x - a.x), one rounding per operator
+        return ((X - a[0]) * f(b[1] - a[1])).astype(np.float32) - ((Y - a[1]) * f(b[0] - a[0])).astype(np.float32)
+
+    n = 0
+    for i0, i1 in pairs:
+        P0 = np.array([vb[i0][0] / vb[i0][3], vb[i0][1] / vb[i0][3], vb[i0][2] / vb[i0][3], vb[i0][3]], dtype=np.float32)
+        P1 = np.array([vb[i1][0] / vb[i1][3], vb[i1][1] / vb[i1][3], vb[i1][2] / vb[i1][3], vb[i1][3]], dtype=np.float32)
+        d = (P1 - P0).astype(np.float32)                        # glm::normalize(vec4): x * inversesqrt(dot(x, x)), all four components
+        sq = f(f(f(d[0] * d[0]) + f(d[1] * d[1])) + f(d[2] * d[2])) + f(d[3] * d[3])
+        inv = f(1) / np.sqrt(f(sq), dtype=np.float32)
+        dirx, diry = f(d[0] * inv), f(d[1] * inv)
+        perp = np.array([diry, -dirx], dtype=np.float32) * lw
+        p00, p01 = (P0[:2] + perp).astype(np.float32), (P0[:2] - perp).astype(np.float32)
+        p10, p11 = (P1[:2] + perp).astype(np.float32), (P1[:2] - perp).astype(np.float32)
+        inside = (E(p00, p01) >= 0) & (E(p11, p10) >= 0) & (E(p10, p00) >= 0) & (E(p01, p11) >= 0)
+        n += int(np.count_nonzero(inside))
+    return n
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("perspective", [True, False])
+def test_point_coverage_against_numpy(oracle, seed, perspective):
+    sc = scenes.random_points_lines(count=80, seed=seed, topology=F.POINT_LIST, depth_fmt=None, perspective=perspective)
+    _, _, st = scenes.run_oracle(sc)
+    assert st.primitives == 80 and st.fragmentsCovered == numpy_point_coverage(sc)
+
+
+@pytest.mark.parametrize("topology", [F.LINE_LIST, F.LINE_STRIP])
+@pytest.mark.parametrize("width", [1.0, 4.5])
+def test_line_coverage_against_numpy(oracle, topology, width):
+    sc = scenes.random_points_lines(count=30, seed=5, topology=topology, line_width=width, depth_fmt=None, perspective=True)
+    _, _, st = scenes.run_oracle(sc)
+    assert st.fragmentsCovered == numpy_line_coverage(sc)
