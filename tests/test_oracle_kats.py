@@ -456,3 +456,123 @@ def test_line_coverage_against_numpy(oracle, topology, width):
     sc = scenes.random_points_lines(count=30, seed=5, topology=topology, line_width=width, depth_fmt=None, perspective=True)
     _, _, st = scenes.run_oracle(sc)
     assert st.fragmentsCovered == numpy_line_coverage(sc)
+
+
+# ---- interpolation and depth: GetFragmentInput / SetDatum (Draw.cpp:816-954) on one triangle, value by value ----
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("perspective", [True, False])
+def test_interpolated_colour_and_depth_against_numpy(oracle, seed, perspective):
+    """Every covered pixel of a single triangle: weights w_i = E_i / area, depth = z0*w0 + z1*w1 + z2*w2, and each colour
+    component numerator / denominator with numerator = ((0 + w0*v0/pw0) + w1*v1/pw1) + w2*v2/pw2 and the matching denominator —
+    float32, one rounding per operator, in the reference's order; RGBA32F colour and D32 depth compared bit for bit."""
+    f = np.float32
+    sc = scenes.random_triangles(width=40, height=28, tris=1, seed=seed, perspective=perspective, color_fmt=F.R32G32B32A32_SFLOAT,
+                                 depth_fmt=F.D32_SFLOAT, depth_op=F.ALWAYS)
+    color, depth, st = scenes.run_oracle(sc)
+    W, H = 40, 28
+    vb = sc.buffers["vb"].view(np.float32).reshape(-1, 8)[:3]
+    P = [np.array([v[0] / v[3], v[1] / v[3], v[2] / v[3], v[3]], dtype=np.float32) for v in vb]
+    xs = ((np.arange(W, dtype=np.float32) / f(W) + (f(1) / f(W)) * f(0.5)) * f(2) - f(1)).astype(np.float32)
+    ys = ((np.arange(H, dtype=np.float32) / f(H) + (f(1) / f(H)) * f(0.5)) * f(2) - f(1)).astype(np.float32)
+    X, Y = np.meshgrid(xs, ys)
+
+    def E(a, b, cx, cy):
+        return ((cx - a[0]) * f(b[1] - a[1])).astype(np.float32) - ((cy - a[1]) * f(b[0] - a[0])).astype(np.float32)
+
+    area = f(f((P[2][0] - P[0][0]) * f(P[1][1] - P[0][1])) - f((P[2][1] - P[0][1]) * f(P[1][0] - P[0][0])))
+    if area < 0:
+        area = -area
+        w = [E(P[2], P[1], X, Y), E(P[0], P[2], X, Y), E(P[1], P[0], X, Y)]
+    else:
+        w = [E(P[1], P[2], X, Y), E(P[2], P[0], X, Y), E(P[0], P[1], X, Y)]
+    inside = ~((w[0] < 0) | (w[1] < 0) | (w[2] < 0))
+    # the integer bounding box of the reference's pixel loop (Draw.cpp:1548-1569) also limits coverage
+    sx = [int(np.trunc(f(f(f(p[0] + f(1)) * f(0.5)) * f(W)))) for p in P]; sy = [int(np.trunc(f(f(f(p[1] + f(1)) * f(0.5)) * f(H)))) for p in P]
+    box = np.zeros((H, W), dtype=bool)
+    box[max(0, min(sy)):min(H, max(sy) + 1), max(0, min(sx)):min(W, max(sx) + 1)] = True
+    inside &= box
+    assert st.fragmentsCovered == int(np.count_nonzero(inside))
+    with np.errstate(all="ignore"):
+        w = [(wi / area).astype(np.float32) for wi in w]
+        z = ((P[0][2] * w[0]).astype(np.float32) + (P[1][2] * w[1]).astype(np.float32)).astype(np.float32) + (P[2][2] * w[2]).astype(np.float32)
+        den = np.zeros_like(X)
+        for i in range(3):
+            den = (den + (w[i] / P[i][3]).astype(np.float32)).astype(np.float32)
+        want = np.zeros((H, W, 4), dtype=np.float32)
+        for c in range(4):
+            num = np.zeros_like(X)
+            for i in range(3):
+                num = (num + ((w[i] * vb[i][4 + c]).astype(np.float32) / P[i][3]).astype(np.float32)).astype(np.float32)
+            want[:, :, c] = (num / den).astype(np.float32)
+    got_c = color.view(np.float32).reshape(H, W, 4); got_z = depth.view(np.float32).reshape(H, W)
+    assert np.array_equal(got_c[inside].view(np.uint32), want[inside].view(np.uint32))
+    assert np.array_equal(got_z[inside].view(np.uint32), z.astype(np.float32)[inside].view(np.uint32))
+    assert np.all(got_z[~inside] == f(1.0)) and np.all(got_c[~inside] == np.array((0.1, 0.2, 0.3, 1.0), dtype=np.float32))
+
+
+# ---- more codecs: SNORM, 16-bit UNORM / SNORM, BGRA ordering, A2B10G10R10 (ImageCompiler.cpp:15-53, :160-301, :1077-1348) ----
+
+def pack_raw(oracle, fmt, texel, values):
+    v = np.ascontiguousarray(values, dtype=np.float32).reshape(-1, 4)
+    out = np.zeros(len(v) * texel, dtype=np.uint8)
+    oracle.cpvk_oracle_pack_f32(fmt, v.ctypes.data_as(C.c_void_p), len(v), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def unpack_raw(oracle, fmt, texel, raw):
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    n = len(raw) // texel
+    out = np.zeros((n, 4), dtype=np.float32)
+    oracle.cpvk_oracle_unpack_f32(fmt, raw.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def probe_values(scale):
+    """Inputs around every kind of boundary for a normalised format with `scale` = 2^n - 1 or 2^(n-1) - 1."""
+    rng = np.random.RandomState(int(scale) & 0xFFFF)
+    k = rng.randint(0, int(scale) + 1, size=400).astype(np.float64)
+    core = np.concatenate([k / scale, (k + 0.5) / scale, (k + 0.5) / scale * (1 + 2e-7), (k + 0.5) / scale * (1 - 2e-7)])
+    v = np.concatenate([core, -core, [0.0, -0.0, 1.0, -1.0, 1.5, -1.5, 1e30, -1e30, np.inf, -np.inf, np.nan]]).astype(np.float32)
+    pad = (-len(v)) % 4
+    return np.concatenate([v, np.zeros(pad, dtype=np.float32)]).reshape(-1, 4)
+
+
+def model_norm(v, lo, scale):  # minnum(maxnum(v, lo), 1) * scale, llvm.round, fptoui / fptosi
+    c = np.where(np.isnan(v), np.float32(lo), v)
+    c = np.minimum(np.maximum(c, np.float32(lo)), np.float32(1)).astype(np.float32)
+    return round_half_away((c * np.float32(scale)).astype(np.float32)).astype(np.int64)
+
+
+@pytest.mark.parametrize("fmt,dtype,texel,lo,scale", [(38, np.int8, 4, -1.0, 127.0), (91, np.uint16, 8, 0.0, 65535.0), (92, np.int16, 8, -1.0, 32767.0)],
+                         ids=["R8G8B8A8_SNORM", "R16G16B16A16_UNORM", "R16G16B16A16_SNORM"])
+def test_normalised_pack_and_unpack_against_numpy(oracle, fmt, dtype, texel, lo, scale):
+    v = probe_values(scale)
+    raw = pack_raw(oracle, fmt, texel, v)
+    want = model_norm(v.reshape(-1), lo, scale).astype(dtype)
+    assert np.array_equal(raw.view(dtype), want)
+    codes = np.arange(np.iinfo(dtype).min, np.iinfo(dtype).max + 1, dtype=np.int64)
+    codes = np.concatenate([codes, np.zeros((-len(codes)) % 4, dtype=np.int64)]).astype(dtype)
+    back = unpack_raw(oracle, fmt, texel, codes.view(np.uint8))
+    # sitofp / uitofp, then a true divide by the same constant (ImageCompiler.cpp:41-53): -128 / 127 < -1 is NOT clamped
+    assert np.array_equal(back.reshape(-1), (codes.astype(np.float32) / np.float32(scale)).astype(np.float32))
+
+
+def test_bgra8_component_order(oracle):
+    v = np.array([[0.0, 1.0 / 255, 2.0 / 255, 3.0 / 255], [1.0, 0.5, 0.25, 0.125]], dtype=np.float32)
+    rgba, bgra = pack_raw(oracle, 37, 4, v).reshape(-1, 4), pack_raw(oracle, 44, 4, v).reshape(-1, 4)
+    assert np.array_equal(bgra, rgba[:, [2, 1, 0, 3]])  # B8G8R8A8: blue in byte 0 (Formats.cpp table: RedOffset 2, BlueOffset 0)
+    assert np.array_equal(unpack_raw(oracle, 44, 4, bgra.reshape(-1)), unpack_raw(oracle, 37, 4, rgba.reshape(-1)))
+
+
+def test_a2b10g10r10_pack_and_unpack_against_numpy(oracle):
+    rng = np.random.RandomState(9)
+    v = np.concatenate([rng.uniform(-0.2, 1.2, size=(500, 4)), [[0, 0, 0, 0], [1, 1, 1, 1], [0.5 / 1023, 1.5 / 1023, 1022.5 / 1023, 0.5 / 3]]]).astype(np.float32)
+    raw = pack_raw(oracle, 64, 4, v).view(np.uint32)
+    r, g, b = (model_norm(v[:, i], 0.0, 1023.0) for i in range(3))
+    a = model_norm(v[:, 3], 0.0, 3.0)
+    assert np.array_equal(raw, (r | (g << 10) | (b << 20) | (a << 30)).astype(np.uint32))  # A2B10G10R10: red in the low bits
+    back = unpack_raw(oracle, 64, 4, raw.view(np.uint8))
+    want = np.stack([r.astype(np.float32) / np.float32(1023), g.astype(np.float32) / np.float32(1023), b.astype(np.float32) / np.float32(1023),
+                     a.astype(np.float32) / np.float32(3)], axis=1).astype(np.float32)
+    assert np.array_equal(back, want)
