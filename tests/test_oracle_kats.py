@@ -576,3 +576,44 @@ def test_a2b10g10r10_pack_and_unpack_against_numpy(oracle):
     want = np.stack([r.astype(np.float32) / np.float32(1023), g.astype(np.float32) / np.float32(1023), b.astype(np.float32) / np.float32(1023),
                      a.astype(np.float32) / np.float32(3)], axis=1).astype(np.float32)
     assert np.array_equal(back, want)
+
+
+# ---- vkCmdBlitImage coordinate arithmetic (CommandBuffer.cpp:186-226) with NEAREST taps, RGBA32F to RGBA32F ----
+
+@pytest.mark.parametrize("case", [((12, 9), (12, 9), (0, 0, 12, 9), (0, 0, 12, 9)),          # 1:1
+                                  ((12, 9), (30, 20), (0, 0, 12, 9), (0, 0, 30, 20)),        # magnify
+                                  ((31, 17), (10, 6), (0, 0, 31, 17), (0, 0, 10, 6)),        # minify
+                                  ((16, 16), (20, 20), (3, 2, 13, 11), (4, 5, 17, 19)),      # sub-rectangles
+                                  ((16, 16), (16, 16), (0, 0, 16, 16), (16, 16, 0, 0)),      # destination mirrored in x and y
+                                  ((16, 16), (16, 16), (16, 0, 0, 16), (0, 0, 16, 16))],     # source mirrored in x
+                         ids=["same", "magnify", "minify", "subrect", "dst-mirror", "src-mirror"])
+def test_blit_nearest_against_numpy(oracle, case):
+    """u = (dstX + 0.5f - dst0.x) * (float(src1.x - src0.x) / (dst1.x - dst0.x)) + src0.x, the coordinate handed to the sampler
+    is u / width, and NEAREST takes floor(coordinate * width) clamped to the edge — float32, in that order. A mirrored
+    destination walks x + dst1.x (the reference's negativeWidth branch). Texels are raw floats, so the copy must be exact."""
+    f = np.float32
+    (sw, sh), (dw, dh), (sx0, sy0, sx1, sy1), (dx0, dy0, dx1, dy1) = case
+    rng = np.random.RandomState(sw * 31 + dw)
+    src = rng.uniform(-4, 4, size=(sh, sw, 4)).astype(np.float32)
+    dst = rng.uniform(-4, 4, size=(dh, dw, 4)).astype(np.float32)
+    want = dst.copy()
+
+    def axis(d0, d1, s0, s1, size_src):
+        n = abs(d1 - d0)
+        out = []
+        for i in range(n):
+            d = i + (d1 if d1 - d0 < 0 else d0)
+            scale = f(f(s1 - s0) / f(d1 - d0))
+            u = f(f(f(f(d) + f(0.5)) - f(d0)) * scale) + f(s0)
+            t = int(np.floor(f(f(u / f(size_src)) * f(size_src))))
+            out.append((d, min(max(t, 0), size_src - 1)))
+        return out
+
+    for dy, ty in axis(dy0, dy1, sy0, sy1, sh):
+        for dx, tx in axis(dx0, dx1, sx0, sx1, sw):
+            if 0 <= dx < dw and 0 <= dy < dh:
+                want[dy, dx] = src[ty, tx]
+    b = capi.Blit(capi.Attachment(src.ctypes.data, sw, sh, sw * 16, 109), capi.Attachment(dst.ctypes.data, dw, dh, dw * 16, 109),
+                  sx0, sy0, sx1, sy1, dx0, dy0, dx1, dy1, 0)
+    assert oracle.cpvk_oracle_blit(C.byref(b)) == 0
+    assert np.array_equal(dst.view(np.uint32), want.view(np.uint32))
