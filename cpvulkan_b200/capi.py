@@ -155,6 +155,7 @@ ABI_SYMBOLS = [
     "cpvk_cuda_pipeline_cubin", "cpvk_cuda_pipeline_compile_only", "cpvk_cuda_draw", "cpvk_cuda_last_draw_stats",
     "cpvk_cuda_launch_count", "cpvk_cuda_clear", "cpvk_cuda_copy_rows", "cpvk_cuda_blit",
     "cpvk_cuda_flush", "cpvk_cuda_device_set_lazy_clear", "cpvk_cuda_device_set_speculation", "cpvk_cuda_mem_download_async",
+    "cpvk_cuda_abi_sizeof",
 ]
 
 

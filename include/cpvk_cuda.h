@@ -236,6 +236,9 @@ typedef union CpvkClearValue { /* VkClearValue */
 /* ---- entry points ---- */
 
 int cpvk_cuda_abi_version(void);
+/* sizeof() of an ABI struct by name ("CpvkDrawState", ...), 0 if unknown: lets a binding in another language check its mirror
+   of the PODs above against what this library was compiled with. */
+size_t cpvk_cuda_abi_sizeof(const char* name);
 const char* cpvk_cuda_last_error(void); /* thread-local, human readable */
 
 /* Device bring-up == `new CPJit()` + AddGlslFunctions in Device::Device (CPVulkan/Device.cpp:17-27). */
