@@ -617,3 +617,63 @@ def test_blit_nearest_against_numpy(oracle, case):
                   sx0, sy0, sx1, sy1, dx0, dy0, dx1, dy1, 0)
     assert oracle.cpvk_oracle_blit(C.byref(b)) == 0
     assert np.array_equal(dst.view(np.uint32), want.view(np.uint32))
+
+
+# ---- the sampling wrapper: LOD bias / clamp, mip choice and view swizzle (GlslFunctions.cpp:539-555, :598-654) ----
+
+MAX_BIAS = np.float32(32.0)
+
+
+def level_chain():
+    """Four mip levels (8x8 .. 1x1), RGBA32F, every texel of level L = (L, 10 + L, 20 + L, 30 + L): the sampled value names the level."""
+    return [np.ascontiguousarray(np.broadcast_to(np.array([l, 10 + l, 20 + l, 30 + l], dtype=np.float32), (8 >> l, 8 >> l, 4))) for l in range(4)]
+
+
+def chain_descriptor(levels, mipmap, bias, min_lod, max_lod, swizzle=(0, 0, 0, 0)):
+    d = capi.Descriptor()
+    d.type, d.format, d.dimensions, d.levelCount = capi.DESC_IMAGE, 109, 2, len(levels)
+    for i, t in enumerate(levels):
+        d.levels[i] = capi.MipLevel(t.ctypes.data, t.shape[1], t.shape[0], 1, 0)
+    s = d.sampler
+    s.magFilter = s.minFilter = F.NEAREST
+    s.mipmapMode, s.mipLodBias, s.minLod, s.maxLod = mipmap, bias, min_lod, max_lod
+    for i, c in enumerate(swizzle):
+        d.swizzle[i] = c
+    return d
+
+
+@pytest.mark.parametrize("mipmap", [0, 1], ids=["mip-nearest", "mip-linear"])
+def test_lod_bias_clamp_and_mip_choice_against_numpy(oracle, mipmap):
+    f = np.float32
+    levels = level_chain()
+    coords = np.array([[0.3, 0.6, 0.0]], dtype=np.float32)
+    for lod in (-1.0, 0.0, 0.2, 0.5, 0.75, 1.0, 1.49, 1.5, 2.2, 3.0, 7.0):
+        for bias, lo, hi in ((0.0, 0.0, 1000.0), (0.6, 0.0, 1000.0), (-0.75, 0.0, 1000.0), (50.0, 0.0, 1000.0), (0.0, 1.25, 2.5), (1.0, 0.5, 0.5), (0.0, 0.0, 0.0)):
+            d = chain_descriptor(levels, mipmap, bias, lo, hi)
+            got = np.zeros((1, 4), dtype=np.float32)
+            oracle.cpvk_oracle_sample(C.byref(d), coords.ctypes.data_as(C.c_void_p), 1, C.c_float(lod), got.ctypes.data_as(C.c_void_p))
+            lam = f(f(lod) + min(max(f(f(bias) + f(0)), -MAX_BIAS), MAX_BIAS))  # MAX_SAMPLER_LOD_BIAS = 32 (Config.h:156)
+            lam = min(max(lam, f(lo)), f(hi))                      # std::clamp(lambdaPrime, minLod, maxLod)
+            if lam <= 0:
+                want = f(0)
+            else:
+                m = min(max(lam, f(0)), f(len(levels) - 1))
+                if mipmap == 0:
+                    want = f(int(np.ceil(f(m + f(0.5)))) - 1)      # ceil(l + 0.5) - 1 (ImageSampler.cpp:632-637)
+                else:
+                    l1 = int(np.floor(m)); delta = f(m - f(l1))
+                    want = f(l1) if delta == 0 else f(np.float64(l1) + np.float64(f(f(l1 + 1) - f(l1))) * np.float64(delta))  # double lerp of the two levels
+            assert got[0, 0] == want and got[0, 3] == f(30) + want, (lod, bias, lo, hi, got[0], want)
+
+
+def test_view_swizzle_against_numpy(oracle):
+    levels = level_chain()[:1]
+    coords = np.array([[0.5, 0.5, 0.0]], dtype=np.float32)
+    base = np.array([0, 10, 20, 30], dtype=np.float32)
+    pick = {0: None, 1: 0.0, 2: 1.0, 3: base[0], 4: base[1], 5: base[2], 6: base[3]}  # IDENTITY, ZERO, ONE, R, G, B, A
+    for swz in ((0, 0, 0, 0), (3, 4, 5, 6), (6, 5, 4, 3), (1, 2, 0, 3), (4, 4, 4, 2), (0, 3, 0, 1)):
+        d = chain_descriptor(levels, 0, 0.0, 0.0, 0.0, swz)
+        got = np.zeros((1, 4), dtype=np.float32)
+        oracle.cpvk_oracle_sample(C.byref(d), coords.ctypes.data_as(C.c_void_p), 1, C.c_float(0.0), got.ctypes.data_as(C.c_void_p))
+        want = [base[i] if pick[s] is None else pick[s] for i, s in enumerate(swz)]
+        assert list(got[0]) == want, (swz, got[0], want)
