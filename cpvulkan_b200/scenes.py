@@ -466,7 +466,7 @@ def overdraw_quads(width=7680, height=4320, quads=2000, tex_size=1024, seed=42, 
 
 
 def sampler_matrix(width=96, height=64, tex_fmt=R8G8B8A8_UNORM, address=(REPEAT, REPEAT), mag=LINEAR, min_=LINEAR, mipmap=0,
-                   min_lod=0.0, border=0, tex_size=(8, 4), levels=3, seed=3):
+                   min_lod=0.0, border=0, tex_size=(8, 4), levels=3, seed=3, bias=0.0, max_lod=1000.0, swizzle=None):
     """One opaque full-screen quad whose uv runs from -1.5 to 2.5 over a small mip-mapped texture, written to an RGBA32F
     target so every sampled float is visible. The sampler state (address modes per axis, mag / min filter, mipmap mode,
     border colour) and the mip chain (levels back to back, Formats.cpp:455-483) are patched into the descriptor on every
@@ -506,7 +506,10 @@ def sampler_matrix(width=96, height=64, tex_fmt=R8G8B8A8_UNORM, address=(REPEAT,
             sm.magFilter, sm.minFilter, sm.mipmapMode = mag, min_, mipmap
             sm.addressModeU, sm.addressModeV = address
             sm.borderColor = border
-            sm.minLod, sm.maxLod = min_lod, 1000.0
+            sm.minLod, sm.maxLod, sm.mipLodBias = min_lod, max_lod, bias
+            if swizzle is not None:  # VkComponentSwizzle per channel of the view (GlslFunctions.cpp:539-555, :636-651)
+                for k, c in enumerate(swizzle):
+                    d.swizzle[k] = c
     s.mutate = patch
     return s
 

@@ -517,3 +517,14 @@ def test_render_targets_beyond_the_limit_are_refused(dev):
         run_cuda(dev, scenes.random_triangles(width=32768, height=2, tris=2, seed=1, depth_fmt=None))
     assert "32767" in str(e.value)
     compare(dev, scenes.draw_cube(64, 64))  # the device is still usable
+
+
+# LOD bias / clamp and the view swizzle of the sampling wrapper (GlslFunctions.cpp:539-555, :598-654); the oracle side of these is
+# pinned by tests/test_oracle_kats.py::test_lod_bias_clamp_and_mip_choice_against_numpy and ::test_view_swizzle_against_numpy.
+@pytest.mark.parametrize("state", [dict(bias=0.6, mipmap=1), dict(bias=-0.75, min_lod=1.5, mipmap=1), dict(bias=50.0, mipmap=0), dict(min_lod=0.25, max_lod=0.25, mipmap=1),
+                                   dict(bias=1.0, min_lod=0.5, max_lod=1.25, mipmap=0), dict(swizzle=(6, 5, 4, 3)), dict(swizzle=(1, 2, 0, 3), bias=0.4, mipmap=1),
+                                   dict(swizzle=(4, 4, 4, 2), address=(1, 3), border=4)],
+                         ids=lambda s: "-".join("%s%s" % (k, v) for k, v in s.items()).replace(" ", ""))
+@pytest.mark.parametrize("tex_fmt", [scenes.R8G8B8A8_UNORM, scenes.R32G32B32A32_SFLOAT])
+def test_sampler_lod_bias_clamp_and_swizzle(dev, state, tex_fmt):
+    compare(dev, scenes.sampler_matrix(tex_fmt=tex_fmt, **state))
