@@ -528,3 +528,15 @@ def test_render_targets_beyond_the_limit_are_refused(dev):
 @pytest.mark.parametrize("tex_fmt", [scenes.R8G8B8A8_UNORM, scenes.R32G32B32A32_SFLOAT])
 def test_sampler_lod_bias_clamp_and_swizzle(dev, state, tex_fmt):
     compare(dev, scenes.sampler_matrix(tex_fmt=tex_fmt, **state))
+
+
+# Integer colour attachments: the fragment output is uvec4 and the attachment write goes through @setPixelU32 with the format's
+# clamp (PipelineCompiler.cpp:1528-1653, ImageCompiler.cpp:1130-1160); partial write masks read the destination back as integers.
+@pytest.mark.parametrize("fmt", [41, 95, 107], ids=["R8G8B8A8_UINT", "R16G16B16A16_UINT", "R32G32B32A32_UINT"])
+@pytest.mark.parametrize("mask", [0xF, 0x5])
+def test_unsigned_integer_colour_attachment(dev, fmt, mask):
+    sc = scenes.random_triangles(width=64, height=48, tris=40, seed=61, color_fmt=fmt)
+    sc.fs = "uintout.frag"
+    sc.color.clear = ("color_uint", (1, 2, 3, 4))
+    sc.write_mask = mask
+    compare(dev, sc)

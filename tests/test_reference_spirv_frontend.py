@@ -21,6 +21,7 @@ EXPECTED = {  # (storage class, Location) in module order; storage: 0 UniformCon
     "complex.frag": (4, [(9, -1), (1, 0), (3, 0)]),                                                  # 9 = PushConstant
     "sepsampler.frag": (4, [(3, 0), (0, -1), (0, -1), (1, 0)]),                                      # texture2D + sampler
     "subpass.frag": (4, [(3, 0), (0, -1)]),                                                          # subpassInput
+    "uintout.frag": (4, [(3, 0), (1, 0)]),                                                           # uvec4 output
 }
 
 
