@@ -34,7 +34,7 @@ BF_ZERO, BF_ONE, BF_SRC_COLOR, BF_ONE_MINUS_SRC_COLOR, BF_DST_COLOR, BF_ONE_MINU
     BF_ONE_MINUS_SRC_ALPHA, BF_DST_ALPHA, BF_ONE_MINUS_DST_ALPHA = range(10)
 BO_ADD, BO_SUBTRACT, BO_REVERSE_SUBTRACT, BO_MIN, BO_MAX = range(5)
 
-TEXEL_SIZE = {R8G8B8A8_UNORM: 4, B8G8R8A8_UNORM: 4, R16G16B16A16_SFLOAT: 8, D16_UNORM: 2, D32_SFLOAT: 4, 41: 4, 95: 8, 107: 16,  # ..._UINT: R8G8B8A8, R16G16B16A16, R32G32B32A32
+TEXEL_SIZE = {R8G8B8A8_UNORM: 4, B8G8R8A8_UNORM: 4, R16G16B16A16_SFLOAT: 8, D16_UNORM: 2, D32_SFLOAT: 4, 41: 4, 95: 8, 107: 16, 42: 4, 96: 8, 108: 16,  # ..._UINT / ..._SINT: R8G8B8A8, R16G16B16A16, R32G32B32A32
               D24_UNORM_S8_UINT: 4, R32_SFLOAT: 4, R32G32B32A32_SFLOAT: 16,
               125: 4, 127: 1, 128: 3, 130: 8}  # X8_D24_UNORM_PACK32, S8_UINT, D16_UNORM_S8_UINT, D32_SFLOAT_S8_UINT
 

@@ -540,3 +540,13 @@ def test_unsigned_integer_colour_attachment(dev, fmt, mask):
     sc.color.clear = ("color_uint", (1, 2, 3, 4))
     sc.write_mask = mask
     compare(dev, sc)
+
+
+@pytest.mark.parametrize("fmt", [42, 96, 108], ids=["R8G8B8A8_SINT", "R16G16B16A16_SINT", "R32G32B32A32_SINT"])
+@pytest.mark.parametrize("mask", [0xF, 0xA])
+def test_signed_integer_colour_attachment(dev, fmt, mask):
+    sc = scenes.random_triangles(width=64, height=48, tris=40, seed=62, color_fmt=fmt)
+    sc.fs = "sintout.frag"                                        # ivec4(color * 600 - 300): clamps at both ends of an 8-bit target
+    sc.color.clear = ("color_uint", (0xFFFFFFFF, 2, 3, 4))        # -1, 2, 3, 4 as VkClearColorValue.int32
+    sc.write_mask = mask
+    compare(dev, sc)

@@ -22,6 +22,7 @@ EXPECTED = {  # (storage class, Location) in module order; storage: 0 UniformCon
     "sepsampler.frag": (4, [(3, 0), (0, -1), (0, -1), (1, 0)]),                                      # texture2D + sampler
     "subpass.frag": (4, [(3, 0), (0, -1)]),                                                          # subpassInput
     "uintout.frag": (4, [(3, 0), (1, 0)]),                                                           # uvec4 output
+    "sintout.frag": (4, [(3, 0), (1, 0)]),                                                           # ivec4 output
 }
 
 
