@@ -550,3 +550,38 @@ def test_signed_integer_colour_attachment(dev, fmt, mask):
     sc.color.clear = ("color_uint", (0xFFFFFFFF, 2, 3, 4))        # -1, 2, 3, 4 as VkClearColorValue.int32
     sc.write_mask = mask
     compare(dev, sc)
+
+
+# ---- multiple colour attachments (a10: the output with Location == attachment index feeds that attachment) ----
+
+def two_attachments(fmt1, blend1=None, mask1=0xF, seed=63):
+    """random triangles into two colour attachments: #0 RGBA8 (the scene's own), #1 `fmt1` placed right behind it in the same
+    allocation, so both come back with the colour read-back."""
+    sc = scenes.random_triangles(width=72, height=40, tris=60, seed=seed)
+    sc.fs = "mrt.frag"
+    w, h = sc.color.width, sc.color.height
+    texel1 = scenes.TEXEL_SIZE[fmt1]
+    sc.color.chain_bytes = w * h * 4 + w * h * texel1
+    sc.color.data = np.zeros(sc.color.chain_bytes, dtype=np.uint8)
+    sc.color.data[w * h * 4:] = 0x3C  # attachment 1 is not cleared by the scene: give it a known, non-trivial start
+
+    def edit(m):
+        a0 = m.color_attachment
+        m.desc.colorAttachmentCount = 2
+        m.desc.colorFormats[1] = fmt1
+        b = m.desc.blend[1]
+        b.colorWriteMask = mask1
+        if blend1:
+            b.blendEnable = 1
+            b.srcColorBlendFactor, b.dstColorBlendFactor, b.colorBlendOp = blend1["src"], blend1["dst"], blend1["op"]
+            b.srcAlphaBlendFactor, b.dstAlphaBlendFactor, b.alphaBlendOp = blend1["src"], blend1["dst"], blend1["op"]
+        m.state.color[1] = type(a0)(a0.address + a0.rowPitch * a0.height, w, h, w * texel1, fmt1)
+    sc.mutate = edit
+    return sc
+
+
+@pytest.mark.parametrize("fmt1,blend1,mask1", [(scenes.B8G8R8A8_UNORM, None, 0xF), (scenes.R16G16B16A16_SFLOAT, None, 0xF),
+                                               (scenes.R8G8B8A8_UNORM, dict(src=6, dst=7, op=0), 0xF), (scenes.R32G32B32A32_SFLOAT, None, 0x6)],
+                         ids=["bgra8", "rgba16f", "rgba8-blended", "rgba32f-masked"])
+def test_two_colour_attachments(dev, fmt1, blend1, mask1):
+    compare(dev, two_attachments(fmt1, blend1, mask1))

@@ -23,6 +23,7 @@ EXPECTED = {  # (storage class, Location) in module order; storage: 0 UniformCon
     "subpass.frag": (4, [(3, 0), (0, -1)]),                                                          # subpassInput
     "uintout.frag": (4, [(3, 0), (1, 0)]),                                                           # uvec4 output
     "sintout.frag": (4, [(3, 0), (1, 0)]),                                                           # ivec4 output
+    "mrt.frag": (4, [(3, 1), (3, 0), (1, 0)]),                                                       # two outputs, declared 1 then 0
 }
 
 
