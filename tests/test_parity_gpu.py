@@ -585,3 +585,33 @@ def two_attachments(fmt1, blend1=None, mask1=0xF, seed=63):
                          ids=["bgra8", "rgba16f", "rgba8-blended", "rgba32f-masked"])
 def test_two_colour_attachments(dev, fmt1, blend1, mask1):
     compare(dev, two_attachments(fmt1, blend1, mask1))
+
+
+# ---- interpolation qualifiers and gl_FragCoord (a6, a7) ----
+
+@pytest.mark.parametrize("topology", [scenes.TRIANGLE_LIST, scenes.TRIANGLE_STRIP, scenes.TRIANGLE_FAN])
+def test_flat_inputs_copy_the_provoking_vertex(dev, topology):
+    sc = scenes.random_triangles(width=64, height=48, tris=30, seed=64, color_fmt=scenes.R32G32B32A32_SFLOAT, topology=topology)
+    sc.fs = "flat.frag"  # Draw.cpp:940-943; provoking vertex per CalculatePrimitives (:614-661: list 3i, strip i, fan i + 1)
+    compare(dev, sc)
+
+
+@pytest.mark.parametrize("perspective", [True, False])
+def test_noperspective_inputs(dev, perspective):
+    sc = scenes.random_triangles(width=64, height=48, tris=30, seed=65, color_fmt=scenes.R32G32B32A32_SFLOAT, perspective=perspective)
+    sc.fs = "nopersp.frag"  # SetDatum<false, 3>: w0*v0 + w1*v1 + w2*v2 (Draw.cpp:833-839)
+    compare(dev, sc)
+
+
+@pytest.mark.parametrize("depth_range", [(0.0, 1.0), (0.2, 0.6)])
+def test_frag_coord_is_the_integer_pixel_and_the_viewport_depth(dev, depth_range):
+    sc = scenes.random_triangles(width=64, height=48, tris=30, seed=66, color_fmt=scenes.R32G32B32A32_SFLOAT)
+    sc.fs = "fragcoord.frag"  # fragCoord = (x, y, depth', 1) with integer x, y (Draw.cpp:1300-1313, :1574-1579)
+    sc.viewport = (0.0, 0.0, 64.0, 48.0, depth_range[0], depth_range[1])
+    compare(dev, sc)
+
+
+def test_flat_and_noperspective_on_lines(dev):
+    for fs in ("flat.frag", "nopersp.frag"):
+        sc = scenes.random_points_lines(count=24, seed=8, topology=scenes.LINE_STRIP, line_width=3.0, color_fmt=scenes.R32G32B32A32_SFLOAT, fs=fs)
+        compare(dev, sc)
