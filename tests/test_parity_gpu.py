@@ -615,3 +615,18 @@ def test_flat_and_noperspective_on_lines(dev):
     for fs in ("flat.frag", "nopersp.frag"):
         sc = scenes.random_points_lines(count=24, seed=8, topology=scenes.LINE_STRIP, line_width=3.0, color_fmt=scenes.R32G32B32A32_SFLOAT, fs=fs)
         compare(dev, sc)
+
+
+# ---- depth-only passes: no colour attachment in the subpass (a shadow-map style draw) ----
+
+@pytest.mark.parametrize("depth_fmt", [scenes.D32_SFLOAT, scenes.D16_UNORM, scenes.D24_UNORM_S8_UINT])
+def test_depth_only_pass(dev, depth_fmt):
+    from cpvulkan_b200 import capi
+
+    def edit(m):
+        m.desc.colorAttachmentCount = 0
+        m.desc.colorFormats[0] = 0
+        m.state.color[0] = capi.Attachment()
+    sc = scenes.random_triangles(width=64, height=48, tris=40, seed=67, depth_fmt=depth_fmt)
+    st = compare(dev, _with(sc, edit))  # the colour image keeps its clear value on both sides, the depth attachment is compared
+    assert 0 < st.fragmentsWritten < st.fragmentsCovered
