@@ -630,3 +630,35 @@ def test_depth_only_pass(dev, depth_fmt):
     sc = scenes.random_triangles(width=64, height=48, tris=40, seed=67, depth_fmt=depth_fmt)
     st = compare(dev, _with(sc, edit))  # the colour image keeps its clear value on both sides, the depth attachment is compared
     assert 0 < st.fragmentsWritten < st.fragmentsCovered
+
+
+# ---- vertex fetch conversions (a3, EmitCopyInput, PipelineCompiler.cpp:821-896) and a non-zero first vertex ----
+
+@pytest.mark.parametrize("fmt,texel", [(scenes.R8G8B8A8_UNORM, 4), (scenes.B8G8R8A8_UNORM, 4), (scenes.R16G16B16A16_SFLOAT, 8), (64, 4), (38, 4)],
+                         ids=["rgba8_unorm", "bgra8_unorm", "rgba16f", "a2b10g10r10_unorm", "rgba8_snorm"])
+def test_vertex_attribute_formats(dev, fmt, texel):
+    """The colour attribute arrives in a format other than the shader's vec4: half floats are extended (the "simple format"
+    path), packed / normalised formats go through the pixel decoder (EmitGetPixel)."""
+    sc = scenes.random_triangles(width=64, height=48, tris=30, seed=68, color_fmt=scenes.R32G32B32A32_SFLOAT)
+    vb = sc.buffers["vb"].view(np.float32).reshape(-1, 8)
+    n = len(vb)
+    rng = np.random.RandomState(3)
+    if fmt == scenes.R16G16B16A16_SFLOAT:
+        packed = rng.uniform(-2, 2, size=(n, 4)).astype(np.float16).view(np.uint8).reshape(n, 8)
+    else:
+        packed = rng.randint(0, 256, size=(n, texel), dtype=np.uint8)
+    stride = 16 + texel
+    out = np.zeros((n, stride), dtype=np.uint8)
+    out[:, :16] = np.ascontiguousarray(vb[:, :4]).view(np.uint8).reshape(n, 16)
+    out[:, 16:] = packed
+    sc.buffers["vb"] = out.reshape(-1)
+    sc.bindings = [(0, stride, 0)]
+    sc.attributes = [(0, 0, scenes.R32G32B32A32_SFLOAT, 0), (1, 0, fmt, 16)]
+    compare(dev, sc)
+
+
+def test_first_vertex_of_a_non_indexed_draw(dev):
+    sc = scenes.random_triangles(width=64, height=48, tris=30, seed=69)
+    sc.first, sc.count = 21, 45  # vertexId = firstVertex + i (Draw.cpp:675-688)
+    st = compare(dev, sc)
+    assert st.primitives == 15
