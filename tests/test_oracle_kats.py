@@ -677,3 +677,49 @@ def test_view_swizzle_against_numpy(oracle):
         oracle.cpvk_oracle_sample(C.byref(d), coords.ctypes.data_as(C.c_void_p), 1, C.c_float(0.0), got.ctypes.data_as(C.c_void_p))
         want = [base[i] if pick[s] is None else pick[s] for i, s in enumerate(swz)]
         assert list(got[0]) == want, (swz, got[0], want)
+
+
+# ---- shader runtime math (a14): the reference's GLSL.std.450 subset and OpDot, value by value ----
+
+def test_glsl_std_450_subset_against_numpy(oracle):
+    """glslmath.frag evaluated by the oracle's SPIR-V interpreter against a float32 numpy model that spells each function the
+    way the reference does: std::min / std::max / std::clamp comparison forms, Mix = x*(1-a) + y*a, NMin / NMax / NClamp,
+    glm::normalize = v * (1 / sqrt(dot)), glm::reflect = I - N * dot(N, I) * 2, glm::dot = (x + y) + z resp. (x + y) + (z + w)
+    (GlslFunctions.cpp:19-321, SpirvFunctions.cpp:6-60). The per-pixel input colour is taken from a run of cube.frag on the
+    same scene, which writes the interpolated input unchanged."""
+    f = np.float32
+    sc = scenes.random_triangles(width=48, height=36, tris=20, seed=70, color_fmt=F.R32G32B32A32_SFLOAT, depth_fmt=None)
+    cin, _, st0 = scenes.run_oracle(sc)
+    sc.fs = "glslmath.frag"
+    out, _, st = scenes.run_oracle(sc)
+    assert st.fragmentsCovered == st0.fragmentsCovered > 1000
+    c = cin.view(np.float32).reshape(-1, 4); got = out.view(np.float32).reshape(-1, 4)
+    clear = np.array((0.1, 0.2, 0.3, 1.0), dtype=np.float32)
+    drawn = np.any(c != clear, axis=1)  # last writer wins in both runs (no depth, no blend), so rows correspond pixel by pixel
+    c = c[drawn]; got = got[drawn]
+    mn = lambda x, y: np.where(y < x, y, x); mx = lambda x, y: np.where(x < y, y, x)
+    clampf = lambda v, lo, hi: np.where(v < lo, lo, np.where(hi < v, hi, v))
+    a = ((c * f(4)).astype(np.float32) - f(2)).astype(np.float32)
+    c3q = (c[:, :3] + f(0.25)).astype(np.float32)
+    dd = (((c3q[:, 0] * c3q[:, 0]).astype(np.float32) + (c3q[:, 1] * c3q[:, 1]).astype(np.float32)).astype(np.float32) + (c3q[:, 2] * c3q[:, 2]).astype(np.float32)).astype(np.float32)
+    inv = (f(1) / np.sqrt(dd, dtype=np.float32)).astype(np.float32)
+    n = (c3q * inv[:, None]).astype(np.float32)
+    d = (((n[:, 0] * a[:, 0]).astype(np.float32) + (n[:, 1] * a[:, 1]).astype(np.float32)).astype(np.float32) + (n[:, 2] * a[:, 2]).astype(np.float32)).astype(np.float32)
+    r = (a[:, :3] - ((n * d[:, None]).astype(np.float32) * f(2)).astype(np.float32)).astype(np.float32)
+    f0 = (mn(a[:, 0], a[:, 1]) + mx(a[:, 2], a[:, 3])).astype(np.float32)
+    nclamp = mn(mx(a[:, 0], f(-0.5)), f(0.75))  # no NaN in this scene: NMin / NMax reduce to min / max
+    f1 = ((mn(a[:, 0], a[:, 3]) + mx(a[:, 1], a[:, 2])).astype(np.float32) + nclamp).astype(np.float32)
+    dot4 = (((a[:, 0] * c[:, 0]).astype(np.float32) + (a[:, 1] * c[:, 1]).astype(np.float32)).astype(np.float32) +
+            ((a[:, 2] * c[:, 2]).astype(np.float32) + (a[:, 3] * c[:, 3]).astype(np.float32)).astype(np.float32)).astype(np.float32)
+    f2 = ((clampf(a[:, 1], f(-1), f(0.5)) + np.abs(a[:, 2])).astype(np.float32) + dot4).astype(np.float32)
+    cw = c[:, ::-1]
+    m = ((a * (f(1) - cw).astype(np.float32)).astype(np.float32) + (c * cw).astype(np.float32)).astype(np.float32)
+    i = np.trunc((a * f(100)).astype(np.float32)).astype(np.int64); u = np.trunc((c * f(1000)).astype(np.float32)).astype(np.int64)
+    s = np.abs(i[:, 0]) + np.sign(i[:, 1]) + np.minimum(i[:, 2], i[:, 3]) + np.maximum(i[:, 0], i[:, 2]) + np.clip(i[:, 3], -50, 60)
+    q = np.minimum(u[:, 0], u[:, 1]) + np.maximum(u[:, 2], u[:, 3]) + np.clip(u[:, 0], 100, 700)
+    want = np.stack([((f0 + f1).astype(np.float32) + r[:, 0]).astype(np.float32),
+                     (((f2 + r[:, 1]).astype(np.float32) + m[:, 0]).astype(np.float32) + m[:, 1]).astype(np.float32),
+                     (((r[:, 2] + m[:, 2]).astype(np.float32) + m[:, 3]).astype(np.float32) + s.astype(np.float32)).astype(np.float32),
+                     q.astype(np.float32)], axis=1)
+    bad = np.nonzero(np.any(got.view(np.uint32) != want.view(np.uint32), axis=1))[0]
+    assert len(bad) == 0, "%d of %d pixels differ; first: c=%s oracle=%s model=%s" % (len(bad), len(got), c[bad[0]], got[bad[0]], want[bad[0]])

@@ -662,3 +662,12 @@ def test_first_vertex_of_a_non_indexed_draw(dev):
     sc.first, sc.count = 21, 45  # vertexId = firstVertex + i (Draw.cpp:675-688)
     st = compare(dev, sc)
     assert st.primitives == 15
+
+
+def test_glsl_std_450_subset(dev):
+    """The reference's whole GLSL.std.450 subset + OpDot + integer conversions in one shader (glslmath.frag): translator vs
+    interpreter, bit for bit; the interpreter side is pinned by tests/test_oracle_kats.py::test_glsl_std_450_subset_against_numpy."""
+    for seed, persp in ((70, True), (71, False)):
+        sc = scenes.random_triangles(width=48, height=36, tris=20, seed=seed, color_fmt=scenes.R32G32B32A32_SFLOAT, depth_fmt=None, perspective=persp)
+        sc.fs = "glslmath.frag"
+        compare(dev, sc)

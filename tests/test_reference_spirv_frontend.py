@@ -24,6 +24,7 @@ EXPECTED = {  # (storage class, Location) in module order; storage: 0 UniformCon
     "uintout.frag": (4, [(3, 0), (1, 0)]),                                                           # uvec4 output
     "sintout.frag": (4, [(3, 0), (1, 0)]),                                                           # ivec4 output
     "mrt.frag": (4, [(3, 1), (3, 0), (1, 0)]),                                                       # two outputs, declared 1 then 0
+    "glslmath.frag": (4, [(3, 0), (1, 0)]),
     "flat.frag": (4, [(3, 0), (1, 0)]),
     "nopersp.frag": (4, [(3, 0), (1, 0)]),
     "fragcoord.frag": (4, [(3, 0), (1, 0), (1, -1)]),                                                # gl_FragCoord: Input, no Location
