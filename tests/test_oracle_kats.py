@@ -723,3 +723,60 @@ def test_glsl_std_450_subset_against_numpy(oracle):
                      q.astype(np.float32)], axis=1)
     bad = np.nonzero(np.any(got.view(np.uint32) != want.view(np.uint32), axis=1))[0]
     assert len(bad) == 0, "%d of %d pixels differ; first: c=%s oracle=%s model=%s" % (len(bad), len(got), c[bad[0]], got[bad[0]], want[bad[0]])
+
+
+# ---- matrix arithmetic in shaders (a14, @Matrix.Mult.*, SpirvFunctions.cpp:6-60 -> glm) ----
+
+def matmath_scene(W=40, H=30, seed=12):
+    """A point list, one vertex per pixel of a sparse grid, size-1 points (exactly one pixel each: Draw.cpp:1345-1361), colours
+    produced by matmath.vert: (a * b * k) * inColor + pos * b."""
+    rng = np.random.RandomState(seed)
+    sc = scenes.random_points_lines(width=W, height=H, count=1, seed=seed, topology=F.POINT_LIST, depth_fmt=None, color_fmt=F.R32G32B32A32_SFLOAT, perspective=False)
+    sc.vs = "matmath.vert"
+    pix = [(i, j) for j in range(1, H - 1, 3) for i in range(1, W - 1, 3)]
+    n = len(pix)
+    f = np.float32
+    x = np.array([(i + 0.25) * 2.0 / (W - 1) - 1.0 for i, _ in pix], dtype=np.float32)
+    y = np.array([(j + 0.25) * 2.0 / (H - 1) - 1.0 for _, j in pix], dtype=np.float32)
+    pos = np.stack([x, y, rng.uniform(0, 1, n).astype(np.float32), np.ones(n, dtype=np.float32)], axis=1)
+    col = rng.uniform(-1, 1, size=(n, 4)).astype(np.float32)
+    vb = np.concatenate([pos, col, np.ones((n, 1), dtype=np.float32)], axis=1).astype(np.float32)
+    sc.buffers["vb"] = vb.view(np.uint8).reshape(-1)
+    sc.count = n
+    a = rng.uniform(-1.5, 1.5, size=(4, 4)).astype(np.float32)  # [column][row], as std140 column-major stores it
+    b = rng.uniform(-1.5, 1.5, size=(4, 4)).astype(np.float32)
+    k = f(0.7)
+    ubo = np.zeros(36, dtype=np.float32)
+    ubo[0:16] = a.reshape(-1); ubo[16:32] = b.reshape(-1); ubo[32] = k
+    sc.buffers["ubo"] = ubo.view(np.uint8)
+    sc.uniforms = [(0, 0, "ubo")]
+    return sc, pix, pos, col, a, b, k
+
+
+def test_matrix_products_against_numpy(oracle):
+    """glm 0.9.5's operand order (the copy vendored with the reference's samples, detail/type_mat4x4.inl:620-780):
+    mat*mat column j = ((A0*B[j][0] + A1*B[j][1]) + A2*B[j][2]) + A3*B[j][3]; mat*scalar per element; mat*vec =
+    (m0*v0 + m1*v1) + (m2*v2 + m3*v3); vec*mat component j = ((m[j][0]*v0 + m[j][1]*v1) + m[j][2]*v2) + m[j][3]*v3."""
+    f = np.float32
+    sc, pix, pos, col, a, b, k = matmath_scene()
+    out, _, st = scenes.run_oracle(sc)
+    assert st.fragmentsCovered == len(pix)
+    img = out.view(np.float32).reshape(sc.color.height, sc.color.width, 4)
+    mm = np.zeros((4, 4), dtype=np.float32)
+    for j in range(4):
+        acc = (a[0] * b[j][0]).astype(np.float32)
+        for r in range(1, 4):
+            acc = (acc + (a[r] * b[j][r]).astype(np.float32)).astype(np.float32)
+        mm[j] = acc
+    ms = (mm * k).astype(np.float32)
+    for (i, j), p, c in zip(pix, pos, col):
+        mv = (((ms[0] * c[0]).astype(np.float32) + (ms[1] * c[1]).astype(np.float32)).astype(np.float32) +
+              ((ms[2] * c[2]).astype(np.float32) + (ms[3] * c[3]).astype(np.float32)).astype(np.float32)).astype(np.float32)
+        vm = np.zeros(4, dtype=np.float32)
+        for q in range(4):
+            acc = f(b[q][0] * p[0])
+            for r in range(1, 4):
+                acc = f(acc + f(b[q][r] * p[r]))
+            vm[q] = acc
+        want = (mv + vm).astype(np.float32)
+        assert np.array_equal(img[j, i].view(np.uint32), want.view(np.uint32)), ((i, j), img[j, i], want)

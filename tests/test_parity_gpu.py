@@ -671,3 +671,15 @@ def test_glsl_std_450_subset(dev):
         sc = scenes.random_triangles(width=48, height=36, tris=20, seed=seed, color_fmt=scenes.R32G32B32A32_SFLOAT, depth_fmt=None, perspective=persp)
         sc.fs = "glslmath.frag"
         compare(dev, sc)
+
+
+def test_matrix_products_in_a_vertex_shader(dev):
+    """mat*mat, mat*scalar, mat*vec and vec*mat (matmath.vert) on a point list: translator vs interpreter; the interpreter's
+    operand order is pinned against glm's by tests/test_oracle_kats.py::test_matrix_products_against_numpy."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("kats", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_oracle_kats.py"))
+    kats = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(kats)
+    compare(dev, kats.matmath_scene()[0])
+    compare(dev, kats.matmath_scene(64, 48, seed=13)[0])
