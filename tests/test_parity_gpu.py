@@ -683,3 +683,21 @@ def test_matrix_products_in_a_vertex_shader(dev):
     spec.loader.exec_module(kats)
     compare(dev, kats.matmath_scene()[0])
     compare(dev, kats.matmath_scene(64, 48, seed=13)[0])
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(first=5, count=20), dict(instances=3, first_instance=2), dict(indexed=True)],
+                         ids=["plain", "first-vertex", "instances", "indexed"])
+def test_vertex_and_instance_index_builtins(dev, kw):
+    """gl_VertexIndex (firstVertex + i, or vertexOffset + index) and gl_InstanceIndex (firstInstance + instance) feed the colour and
+    the position of a point list (builtins.vert)."""
+    sc = scenes.random_points_lines(width=96, height=64, count=40, seed=14, topology=scenes.POINT_LIST, perspective=False)
+    sc.vs = "builtins.vert"
+    if "first" in kw:
+        sc.first, sc.count = kw["first"], kw["count"]
+    if "instances" in kw:
+        sc.instances, sc.first_instance = kw["instances"], kw["first_instance"]
+    if kw.get("indexed"):
+        idx = np.random.RandomState(2).permutation(40).astype(np.uint16)
+        sc.buffers["ib"] = idx.view(np.uint8).reshape(-1)
+        sc.index_buffer, sc.index_stride, sc.vertex_offset = "ib", 2, 0
+    compare(dev, sc)

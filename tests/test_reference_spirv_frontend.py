@@ -15,6 +15,7 @@ CHECK = os.path.join(ROOT, "oracle", "_ref", "spirv_check")
 EXPECTED = {  # (storage class, Location) in module order; storage: 0 UniformConstant, 1 Input, 2 Uniform, 3 Output, 6 Private, 9 PushConstant
     "cube.vert": (0, [(3, 0), (1, 1), (3, -1), (2, -1), (1, 0)]),
     "cube.frag": (4, [(3, 0), (1, 0)]),
+    "builtins.vert": (0, [(3, 0), (1, 1), (3, -1), (1, -1), (1, -1), (1, 0), (1, 2)]),               # VertexIndex, InstanceIndex: Inputs without Location
     "matmath.vert": (0, [(3, 0), (1, 1), (3, -1), (2, -1), (1, 0), (1, 2)]),                          # two mat4 + a float in one UBO
     "texcube.vert": (0, [(3, 0), (1, 1), (3, -1), (2, -1), (1, 0)]),
     "texcube.frag": (4, [(3, 0), (0, -1), (1, 0)]),
