@@ -780,3 +780,49 @@ def test_matrix_products_against_numpy(oracle):
             vm[q] = acc
         want = (mv + vm).astype(np.float32)
         assert np.array_equal(img[j, i].view(np.uint32), want.view(np.uint32)), ((i, j), img[j, i], want)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("perspective", [True, False])
+def test_line_interpolation_and_depth_against_numpy(oracle, seed, perspective):
+    """One wide line: t = dot(p - p0, p1 - p0) / (length(p1 - p0) * length(p1 - p0)), colour = SetDatum<true, 2> with weights
+    (1 - t, t), depth = p0.z * t + p1.z * (1 - t) — the weights swapped, as the reference has it (Draw.cpp:1440-1494)."""
+    f = np.float32
+    sc = scenes.random_points_lines(width=40, height=28, count=1, seed=seed, topology=F.LINE_LIST, line_width=5.0, depth_fmt=F.D32_SFLOAT,
+                                    color_fmt=F.R32G32B32A32_SFLOAT, perspective=perspective)
+    sc.depth_op = F.ALWAYS
+    color, depth, st = scenes.run_oracle(sc)
+    W, H = 40, 28
+    vb = sc.buffers["vb"].view(np.float32).reshape(-1, 9)[:2]
+    P = [np.array([v[0] / v[3], v[1] / v[3], v[2] / v[3], v[3]], dtype=np.float32) for v in vb]
+    xs = ((np.arange(W, dtype=np.float32) / f(W) + (f(1) / f(W)) * f(0.5)) * f(2) - f(1)).astype(np.float32)
+    ys = ((np.arange(H, dtype=np.float32) / f(H) + (f(1) / f(H)) * f(0.5)) * f(2) - f(1)).astype(np.float32)
+    X, Y = np.meshgrid(xs, ys)
+    d = (P[1] - P[0]).astype(np.float32)
+    sq = f(f(f(d[0] * d[0]) + f(d[1] * d[1])) + f(d[2] * d[2])) + f(d[3] * d[3])
+    inv = f(1) / np.sqrt(f(sq), dtype=np.float32)
+    perp = np.array([f(d[1] * inv), -f(d[0] * inv)], dtype=np.float32) * np.array([f(5.0) / f(W), f(5.0) / f(H)], dtype=np.float32)
+    p00, p01 = (P[0][:2] + perp).astype(np.float32), (P[0][:2] - perp).astype(np.float32)
+    p10, p11 = (P[1][:2] + perp).astype(np.float32), (P[1][:2] - perp).astype(np.float32)
+    E = lambda a, b: ((X - a[0]) * f(b[1] - a[1])).astype(np.float32) - ((Y - a[1]) * f(b[0] - a[0])).astype(np.float32)
+    inside = (E(p00, p01) >= 0) & (E(p11, p10) >= 0) & (E(p10, p00) >= 0) & (E(p01, p11) >= 0)
+    assert st.fragmentsCovered == int(np.count_nonzero(inside)) > 20
+    dx, dy = f(P[1][0] - P[0][0]), f(P[1][1] - P[0][1])
+    length = np.sqrt(f(f(dx * dx) + f(dy * dy)), dtype=np.float32)
+    with np.errstate(all="ignore"):
+        t = ((((X - P[0][0]).astype(np.float32) * dx).astype(np.float32) + ((Y - P[0][1]).astype(np.float32) * dy).astype(np.float32)).astype(np.float32)
+             / f(length * length)).astype(np.float32)
+        w = [(f(1) - t).astype(np.float32), t]
+        z = ((P[0][2] * t).astype(np.float32) + (P[1][2] * w[0]).astype(np.float32)).astype(np.float32)
+        den = np.zeros_like(X)
+        for i in range(2):
+            den = (den + (w[i] / P[i][3]).astype(np.float32)).astype(np.float32)
+        want = np.zeros((H, W, 4), dtype=np.float32)
+        for c in range(4):
+            num = np.zeros_like(X)
+            for i in range(2):
+                num = (num + ((w[i] * vb[i][4 + c]).astype(np.float32) / P[i][3]).astype(np.float32)).astype(np.float32)
+            want[:, :, c] = (num / den).astype(np.float32)
+    got_c = color.view(np.float32).reshape(H, W, 4); got_z = depth.view(np.float32).reshape(H, W)
+    assert np.array_equal(got_c[inside].view(np.uint32), want[inside].view(np.uint32))
+    assert np.array_equal(got_z[inside].view(np.uint32), z[inside].view(np.uint32))
