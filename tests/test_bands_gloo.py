@@ -45,10 +45,14 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_band_render_matches_single_rank(built, tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 4])  # 64 rows: bands of 32 (one tile row each) and of 16 (two ranks share every tile row)
+def test_band_render_matches_single_rank(built, tmp_path, world):
     from cpvulkan_b200 import scenes
-    port = 29500 + (os.getpid() % 1000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    port = 29500 + (os.getpid() % 1000) + world
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     gathered = np.load(os.path.join(str(tmp_path), "gathered.npy"))
     color, _, st = scenes.run_oracle(scenes.random_triangles(width=96, height=64, tris=150, seed=21))
     assert np.array_equal(gathered, color)
