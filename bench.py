@@ -44,16 +44,40 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: through NVML every 2 ms (the timed region of the default run
+    is a few milliseconds long), or — when the NVML binding is missing — by `nvidia-smi -lms 200`."""
 
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.proc = index, [], None
+        self.done = threading.Event()
+        self.nvml_samples, self.nvml_max, self.nvml_mask = [], None, 0
+
+    def _nvml_loop(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(self.index)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.nvml_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not self.done.is_set():
+            self.nvml_samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml_mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            time.sleep(0.002)
 
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            self.nvml_samples = []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -62,14 +86,25 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def mark(self):
+        """Forget what was sampled so far: called right before the timed region starts."""
+        self.nvml_samples.clear(); self.nvml_mask = 0; self.rows.clear()
+
     def stop(self):
+        self.done.set()
         if self.proc:
             self.proc.terminate()
+        if self.nvml_samples:
+            self.join(timeout=1.0)
+            reasons = sorted(name for bit, name in self.NVML_REASONS if self.nvml_mask & bit)
+            return {"sm_mhz": float(statistics.median(self.nvml_samples)), "sm_max_mhz": float(self.nvml_max), "reasons": reasons,
+                    "samples": len(self.nvml_samples), "source": "nvml, every 2 ms"}
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "source": "nvidia-smi -lms 200"}
 
 
 def oracle_draw_seconds(scene, repeats=1):
@@ -277,19 +312,21 @@ def run_ours(args):
         time.sleep(0.3)
     launches0 = dev.launch_count()
     barrier()
+    if sampler and sampler.nvml_samples:
+        sampler.mark()  # NVML samples every 2 ms: keep only those taken inside the timed region (nvidia-smi's 200 ms rows are all kept)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         frame()
     e1.record()
     barrier()
+    clocks = sampler.stop() if sampler else None
     ms_total = e0.elapsed_time(e1)
     launches = dev.launch_count() - launches0
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t[0])
-    clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     prims = 2 * NX * NY
 
