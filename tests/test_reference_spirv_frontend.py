@@ -16,6 +16,7 @@ EXPECTED = {  # (storage class, Location) in module order; storage: 0 UniformCon
     "cube.vert": (0, [(3, 0), (1, 1), (3, -1), (2, -1), (1, 0)]),
     "cube.frag": (4, [(3, 0), (1, 0)]),
     "builtins.vert": (0, [(3, 0), (1, 1), (3, -1), (1, -1), (1, -1), (1, 0), (1, 2)]),               # VertexIndex, InstanceIndex: Inputs without Location
+    "points.vert": (0, [(3, 0), (1, 1), (3, -1), (1, 0), (1, 2)]),                                   # + gl_PointSize from an attribute
     "matmath.vert": (0, [(3, 0), (1, 1), (3, -1), (2, -1), (1, 0), (1, 2)]),                          # two mat4 + a float in one UBO
     "texcube.vert": (0, [(3, 0), (1, 1), (3, -1), (2, -1), (1, 0)]),
     "texcube.frag": (4, [(3, 0), (0, -1), (1, 0)]),
@@ -53,3 +54,8 @@ def test_reference_front_end_accepts_our_shaders(checker, tmp_path, name):
     assert any(l.startswith("entry %d main" % model) for l in out)
     got = [(int(l.split()[3]), int(l.split()[5])) for l in out if l.startswith("variable")]
     assert got == variables
+
+
+def test_every_shader_in_the_tree_is_checked():
+    have = {f[:-len(".spvasm")] for f in os.listdir(os.path.join(ROOT, "cpvulkan_b200", "shaders")) if f.endswith(".spvasm")}
+    assert have == set(EXPECTED), have ^ set(EXPECTED)
