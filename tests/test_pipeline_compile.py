@@ -70,3 +70,41 @@ def test_missing_vertex_attribute_is_refused(built):
         d.attributeCount = 1
     lib, rc, _, _ = compile_only(scenes.draw_cube(32, 32), drop)
     assert rc == capi.E_UNSUPPORTED and b"location" in lib.cpvk_cuda_last_error()
+
+
+def _with_fs(scene, fs):
+    scene.fs = fs
+    return scene
+
+
+def _with_vs(scene, vs):
+    scene.vs = vs
+    return scene
+
+
+FRONT_END_SCENES = {
+    "separate_image_sampler": lambda: scenes.separate_image_sampler(64, 64),
+    "input_attachment": lambda: scenes.input_attachment(64, 64),
+    "uint_output": lambda: _with_fs(scenes.random_triangles(width=32, height=32, tris=2, color_fmt=41), "uintout.frag"),
+    "sint_output": lambda: _with_fs(scenes.random_triangles(width=32, height=32, tris=2, color_fmt=42), "sintout.frag"),
+    "flat": lambda: _with_fs(scenes.random_triangles(width=32, height=32, tris=2), "flat.frag"),
+    "noperspective": lambda: _with_fs(scenes.random_triangles(width=32, height=32, tris=2), "nopersp.frag"),
+    "frag_coord": lambda: _with_fs(scenes.random_triangles(width=32, height=32, tris=2), "fragcoord.frag"),
+    "glsl_math": lambda: _with_fs(scenes.random_triangles(width=32, height=32, tris=2, color_fmt=scenes.R32G32B32A32_SFLOAT), "glslmath.frag"),
+    "push_spec_loop": lambda: _with_fs(scenes.random_triangles(width=32, height=32, tris=2), "complex.frag"),
+    "builtins": lambda: _with_vs(scenes.random_points_lines(width=32, height=32, count=4, topology=scenes.POINT_LIST), "builtins.vert"),
+    "lines": lambda: scenes.random_points_lines(width=32, height=32, count=4, topology=scenes.LINE_STRIP),
+    "texel_buffer": lambda: scenes.texel_buffer(32, 32),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FRONT_END_SCENES))
+def test_every_shader_family_links(built, name):
+    """Each shader in the tree, in a pipeline of the kind the GPU tests use it in, goes all the way to an sm_100a cubin here."""
+    lib, rc, p, _ = compile_only(FRONT_END_SCENES[name]())
+    assert rc == 0, lib.cpvk_cuda_last_error()
+    n = C.c_size_t()
+    cubin = lib.cpvk_cuda_pipeline_cubin(p, C.byref(n))
+    blob = C.string_at(cubin, n.value)
+    assert blob[:4] == b"\x7fELF" and b"cpvk_k_raster" in blob and b"cpvk_k_vertex" in blob
+    lib.cpvk_cuda_pipeline_destroy(None, p)
