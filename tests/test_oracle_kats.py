@@ -826,3 +826,28 @@ def test_line_interpolation_and_depth_against_numpy(oracle, seed, perspective):
     got_c = color.view(np.float32).reshape(H, W, 4); got_z = depth.view(np.float32).reshape(H, W)
     assert np.array_equal(got_c[inside].view(np.uint32), want[inside].view(np.uint32))
     assert np.array_equal(got_z[inside].view(np.uint32), z[inside].view(np.uint32))
+
+
+# ---- sRGB (ImageCompiler.cpp:103-158, :1350-1383): piecewise 0.04045 / 12.92 / 2.4 with llvm.pow — libm, so 1e-5, not bits ----
+
+def test_srgb_unpack_and_pack_against_numpy(oracle):
+    f = np.float32
+    codes = np.arange(256, dtype=np.uint8)
+    raw = np.stack([codes, codes[::-1], (codes * 7).astype(np.uint8), codes], axis=1).reshape(-1)
+    got = unpack_raw(oracle, 43, 4, raw)  # R8G8B8A8_SRGB
+    v = (raw.reshape(-1, 4).astype(np.float32) / f(255.0)).astype(np.float32)
+    lin = np.where(v > f(0.04045), np.power(((v + f(0.055)).astype(np.float32) / f(1.055)).astype(np.float64), 2.4), (v / f(12.92)).astype(np.float64))
+    assert np.allclose(got[:, :3], lin[:, :3], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(got[:, 3], v[:, 3])  # alpha is linear (the conversion skips channel 3)
+    # pack: clamp, linear -> sRGB on rgb, * 255, llvm.round; compared through the code it produces (+-1 only where pow's last bits decide a tie)
+    x = np.linspace(0, 1, 1001, dtype=np.float32)
+    vals = np.stack([x, x[::-1], (x * x).astype(np.float32), x], axis=1)
+    packed = pack_raw(oracle, 43, 4, vals).reshape(-1, 4)
+    s = np.where(vals > f(0.0031308), np.power(vals.astype(np.float64), 1.0 / 2.4) * 1.055 - 0.055, vals.astype(np.float64) * 12.92)
+    want_rgb = np.floor(s[:, :3] * 255.0 + 0.5)
+    assert np.max(np.abs(packed[:, :3].astype(np.int64) - want_rgb.astype(np.int64))) <= 1
+    assert np.mean(packed[:, :3] == want_rgb) > 0.995
+    assert np.array_equal(packed[:, 3], np.floor((vals[:, 3] * f(255.0)).astype(np.float64) + 0.5).astype(np.uint8))
+    # round trip of every code is the identity
+    back = pack_raw(oracle, 43, 4, got).reshape(-1, 4)
+    assert np.array_equal(back, raw.reshape(-1, 4))
