@@ -92,6 +92,8 @@ struct InOut {
     uint32_t interpolation; // 0 perspective, 1 linear, 2 flat
     uint32_t size;       // bytes (side-specific)
     uint32_t offset;     // bytes within the vertex record (24 + ...)
+    uint32_t comps = 0;  // fragment inputs: 32-bit components SetDatum walks (TotalSize / ElementSize of the variable's format)
+    bool floats = false; // fragment inputs: 32-bit SFLOAT components (anything else with Perspective / Linear is FATAL_ERROR)
 };
 
 struct StageInfo {
@@ -142,6 +144,12 @@ void Reflect(StageInfo& s, bool vertex) {
                 io.interpolation = m.hasDeco(v.id, DecoFlat) ? 2 : (m.hasDeco(v.id, DecoNoPerspective) ? 1 : 0);
                 io.size = vertex ? 0 : VariableSize(m, pointee);
                 io.offset = inOff; inOff += io.size;
+                if (!vertex) {
+                    const Type& t = m.types[pointee];
+                    const Type& et = t.kind == Type::Vector ? m.types[t.elem] : t;
+                    io.floats = et.kind == Type::Float && (t.kind == Type::Vector || t.kind == Type::Float);
+                    io.comps = t.kind == Type::Vector ? t.count : 1;
+                }
                 s.inputs.push_back(io);
             } else {
                 io.size = vertex ? AllocSize(m, pointee) : 0;
@@ -329,6 +337,10 @@ struct DrawContext {
     std::vector<uint8_t> vertexStorage;
     Window win;
     CpvkDrawStats stats{};
+    // fragment-stream mode (cpvk_oracle_raster_records): no shaders; every fragment the rasteriser emits is written down
+    // with the arguments the reference would call the fragment wrapper with and the interpolated inputs
+    std::vector<uint32_t>* trace = nullptr;
+    bool traceOriginUpper = true;
 };
 
 void CheckSupported(const CpvkPipelineDesc& d) {
@@ -399,19 +411,20 @@ void Fragment(DrawContext& c, int32_t x, int32_t y, float depth, bool front, con
     const CpvkDrawState& st = *c.st;
     Module& m = c.fs.mod;
     c.stats.fragmentsCovered++;
-    c.fsi.BeginInvocation();
+    size_t traceAt = 0;
+    if (c.trace) { traceAt = c.trace->size(); uint32_t words = 8; for (const InOut& in : c.fs.inputs) words += in.size / 4; c.trace->resize(traceAt + words, 0); }
+    else c.fsi.BeginInvocation();
+    uint32_t traceWord = 8;
     // interpolants (Draw.cpp:816-872, 911-951)
     for (const InOut& in : c.fs.inputs) {
-        uint32_t* dst = c.fsi.VarData(in.var);
+        uint32_t* dst = c.trace ? c.trace->data() + traceAt + traceWord : c.fsi.VarData(in.var);
+        traceWord += in.size / 4;
         const uint8_t* data[3];
         for (int k = 0; k < nv; k++) data[k] = c.vertexStorage.data() + (size_t)idx[k] * c.vs.outputStride + in.offset;
         if (nv == 1) { std::memcpy(dst, data[0], in.size); continue; }
         if (in.interpolation == 2) { std::memcpy(dst, c.vertexStorage.data() + (size_t)provoking * c.vs.outputStride + in.offset, in.size); continue; }
-        const Type& t = m.types[in.type];
-        const Type& et = t.kind == Type::Vector ? m.types[t.elem] : t;
-        if (et.kind != Type::Float || (t.kind != Type::Vector && t.kind != Type::Float)) Fail("SetDatum: only 32-bit float inputs interpolate (FATAL_ERROR, Draw.cpp:863-869)");
-        const uint32_t comps = t.kind == Type::Vector ? t.count : 1;
-        for (uint32_t e = 0; e < comps; e++) {
+        if (!in.floats) Fail("SetDatum: only 32-bit float inputs interpolate (FATAL_ERROR, Draw.cpp:863-869)");
+        for (uint32_t e = 0; e < in.comps; e++) {
             float values[3]; for (int k = 0; k < nv; k++) std::memcpy(&values[k], data[k] + 4 * e, 4);
             float result;
             if (in.interpolation == 0) {
@@ -424,11 +437,17 @@ void Fragment(DrawContext& c, int32_t x, int32_t y, float depth, bool front, con
             std::memcpy(&dst[e], &result, 4);
         }
     }
-    if (c.fs.fragCoordVar) {
+    if (c.fs.fragCoordVar || c.trace) {
         float fc[4];
-        fc[0] = m.originUpperLeft ? (float)x : st.viewport.width - (float)x - 1; // Draw.cpp:1579
+        fc[0] = (c.trace ? c.traceOriginUpper : m.originUpperLeft) ? (float)x : st.viewport.width - (float)x - 1; // Draw.cpp:1579
         fc[1] = (float)y; fc[2] = depth; fc[3] = 1.0f;
-        std::memcpy(c.fsi.VarData(c.fs.fragCoordVar), fc, 16);
+        std::memcpy(c.trace ? c.trace->data() + traceAt + 4 : c.fsi.VarData(c.fs.fragCoordVar), fc, 16);
+    }
+    if (c.trace) {
+        const float shaderDepth = (st.viewport.maxDepth - st.viewport.minDepth) * depth + st.viewport.minDepth; // Draw.cpp:1310
+        uint32_t* t = c.trace->data() + traceAt;
+        t[0] = (uint32_t)x; t[1] = (uint32_t)y; t[2] = front ? 1u : 0u; std::memcpy(&t[3], &shaderDepth, 4);
+        return;
     }
     depth = (st.viewport.maxDepth - st.viewport.minDepth) * depth + st.viewport.minDepth; // Draw.cpp:1310
     c.fsi.Call(m.entryPoint, nullptr, nullptr, 0);
@@ -701,6 +720,77 @@ int cpvk_oracle_draw(const CpvkPipelineDesc* desc, const CpvkDrawState* state, C
 int cpvk_oracle_draw_window(const CpvkPipelineDesc* desc, const CpvkDrawState* state, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
                             CpvkDrawStats* stats) {
     return DrawImpl(desc, state, Window{x0, y0, x1, y1}, stats);
+}
+
+// Fragment-stream mode, the counterpart of oracle/ref_draw_check.cpp `raster`: the vertex stage's output records are given
+// (no shaders run), CalculatePrimitives + ProcessPoints / ProcessLines / ProcessTriangles + GetFragmentInput / SetDatum /
+// DrawPixel of THIS file produce, per emitted fragment and in emission order, the words
+//   x, y, front, depth as the fragment wrapper receives it (after the viewport transform), fragCoord[4], interpolated inputs.
+// inputs = {offset, VkFormat, interpolation (0 perspective, 1 linear, 2 flat), size} per fragment input, as
+// VariableInOutData has them (Draw.cpp:97-106). Returns the number of fragments, or a negative error; `out` receives at
+// most `capacityWords` words (the count is still exact, so a caller can size the buffer and call again).
+int64_t cpvk_oracle_raster_records(float width, float height, float minDepth, float maxDepth, float lineWidth, uint32_t topology,
+                                   uint32_t frontFace, uint32_t cullMode, uint32_t originUpper, uint32_t vertexCount, uint32_t stride,
+                                   const uint32_t* inputs, uint32_t inputCount, const uint8_t* records, uint32_t* out, uint64_t capacityWords) {
+    try {
+        CpvkPipelineDesc desc{};
+        desc.topology = topology; desc.frontFace = frontFace; desc.cullMode = cullMode; desc.lineWidth = lineWidth;
+        CpvkDrawState st{};
+        st.viewport.width = width; st.viewport.height = height; st.viewport.minDepth = minDepth; st.viewport.maxDepth = maxDepth;
+        DrawContext c;
+        c.desc = &desc; c.st = &st; c.win = Window{0, 0, INT32_MAX, INT32_MAX};
+        std::vector<uint32_t> trace;
+        c.trace = &trace; c.traceOriginUpper = originUpper != 0;
+        c.vs.outputStride = stride;
+        c.vertexStorage.assign(records, records + (size_t)vertexCount * stride);
+        uint32_t words = 8;
+        for (uint32_t i = 0; i < inputCount; i++) {
+            InOut io{};
+            io.location = i; io.offset = inputs[4 * i]; io.interpolation = inputs[4 * i + 2]; io.size = inputs[4 * i + 3];
+            const FormatInfo fi = GetFormatInformation(inputs[4 * i + 1]);
+            if (fi.type == FmtType::Invalid) Fail("raster_records: unknown input format");
+            io.comps = fi.totalSize / fi.elementSize;                      // SetDatum: TotalSize / ElementSize (Draw.cpp:841-842)
+            io.floats = fi.base == Base::SFloat && fi.elementSize == 4;   // :845-869
+            c.fs.inputs.push_back(io);
+            words += io.size / 4;
+        }
+        const uint32_t n = vertexCount;
+        uint32_t primCount = 0;
+        switch (topology) {
+        case 3: primCount = n / 3; break;
+        case 4: case 5: primCount = n > 2 ? n - 2 : 0; break;
+        case 0: primCount = n; break;
+        case 1: primCount = n / 2; break;
+        case 2: primCount = n > 1 ? n - 1 : 0; break;
+        default: Fail("topology unsupported (TODO_ERROR, Draw.cpp:663-668)");
+        }
+        if (topology == 0) ProcessPoints(c, primCount);
+        else if (topology <= 2) ProcessLines(c, primCount, topology);
+        else ProcessTriangles(c, primCount, topology);
+        const uint64_t total = trace.size();
+        std::memcpy(out, trace.data(), (size_t)std::min<uint64_t>(total, capacityWords) * 4);
+        return (int64_t)(total / words);
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// ApplyBlend on its own (Draw.cpp:1105-1262), the counterpart of oracle/ref_draw_check.cpp `blend`: state = the eight
+// VkPipelineColorBlendAttachmentState members in order; source / destination / constant / out are float[4].
+int cpvk_oracle_apply_blend(const uint32_t state[8], const float* source, const float* destination, const float* constant, float* out) {
+    try {
+        CpvkBlendAttachment b{};
+        b.blendEnable = state[0]; b.srcColorBlendFactor = state[1]; b.dstColorBlendFactor = state[2]; b.colorBlendOp = state[3];
+        b.srcAlphaBlendFactor = state[4]; b.dstAlphaBlendFactor = state[5]; b.alphaBlendOp = state[6]; b.colorWriteMask = state[7];
+        F4 s, d, k; std::memcpy(s.v, source, 16); std::memcpy(d.v, destination, 16); std::memcpy(k.v, constant, 16);
+        const F4 r = ApplyBlend(s, d, k, b);
+        std::memcpy(out, r.v, 16);
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return CPVK_E_UNSUPPORTED;
+    }
 }
 
 // Render-pass clear == ClearImage: SetPixel on every texel of the subresource (Draw.cpp:117-149, ImageSampler.cpp:723-761).

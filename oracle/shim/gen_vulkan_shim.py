@@ -125,6 +125,40 @@ typedef union VkClearColorValue { float float32[4]; int32_t int32[4]; uint32_t u
 typedef struct VkClearDepthStencilValue { float depth; uint32_t stencil; } VkClearDepthStencilValue;
 typedef union VkClearValue { VkClearColorValue color; VkClearDepthStencilValue depthStencil; } VkClearValue;
 """)
+
+# ---- what CPVulkanBase/PipelineState.h and the sliced parts of CPVulkan/CommandBuffer.Draw.cpp need (oracle/_ref/draw_check) ----
+advanced_blend = ['ZERO', 'SRC', 'DST', 'SRC_OVER', 'DST_OVER', 'SRC_IN', 'DST_IN', 'SRC_OUT', 'DST_OUT', 'SRC_ATOP', 'DST_ATOP', 'XOR', 'MULTIPLY', 'SCREEN', 'OVERLAY', 'DARKEN', 'LIGHTEN', 'COLORDODGE', 'COLORBURN', 'HARDLIGHT', 'SOFTLIGHT', 'DIFFERENCE', 'EXCLUSION', 'INVERT', 'INVERT_RGB', 'LINEARDODGE', 'LINEARBURN', 'VIVIDLIGHT', 'LINEARLIGHT', 'PINLIGHT', 'HARDMIX', 'HSL_HUE', 'HSL_SATURATION', 'HSL_COLOR', 'HSL_LUMINOSITY', 'PLUS', 'PLUS_CLAMPED', 'PLUS_CLAMPED_ALPHA', 'PLUS_DARKER', 'MINUS', 'MINUS_CLAMPED', 'CONTRAST', 'INVERT_OVG', 'RED', 'GREEN', 'BLUE']
+factors = ["ZERO", "ONE", "SRC_COLOR", "ONE_MINUS_SRC_COLOR", "DST_COLOR", "ONE_MINUS_DST_COLOR", "SRC_ALPHA", "ONE_MINUS_SRC_ALPHA",
+           "DST_ALPHA", "ONE_MINUS_DST_ALPHA", "CONSTANT_COLOR", "ONE_MINUS_CONSTANT_COLOR", "CONSTANT_ALPHA", "ONE_MINUS_CONSTANT_ALPHA",
+           "SRC_ALPHA_SATURATE", "SRC1_COLOR", "ONE_MINUS_SRC1_COLOR", "SRC1_ALPHA", "ONE_MINUS_SRC1_ALPHA"]
+topologies = ["POINT_LIST", "LINE_LIST", "LINE_STRIP", "TRIANGLE_LIST", "TRIANGLE_STRIP", "TRIANGLE_FAN", "LINE_LIST_WITH_ADJACENCY",
+              "LINE_STRIP_WITH_ADJACENCY", "TRIANGLE_LIST_WITH_ADJACENCY", "TRIANGLE_STRIP_WITH_ADJACENCY", "PATCH_LIST"]
+o.append("typedef enum VkBlendFactor {\n" + "".join("    VK_BLEND_FACTOR_%s = %d,\n" % (n, i) for i, n in enumerate(factors)) + "} VkBlendFactor;\n")
+o.append("typedef enum VkBlendOp {\n    VK_BLEND_OP_ADD = 0, VK_BLEND_OP_SUBTRACT = 1, VK_BLEND_OP_REVERSE_SUBTRACT = 2, VK_BLEND_OP_MIN = 3, VK_BLEND_OP_MAX = 4,\n"
+         + "".join("    VK_BLEND_OP_%s_EXT = %d,\n" % (n, 1000148000 + i) for i, n in enumerate(advanced_blend)) + "} VkBlendOp;\n")
+o.append("typedef enum VkPrimitiveTopology {\n" + "".join("    VK_PRIMITIVE_TOPOLOGY_%s = %d,\n" % (n, i) for i, n in enumerate(topologies)) + "} VkPrimitiveTopology;\n")
+o.append("""typedef enum VkPolygonMode { VK_POLYGON_MODE_FILL = 0, VK_POLYGON_MODE_LINE = 1, VK_POLYGON_MODE_POINT = 2 } VkPolygonMode;
+typedef enum VkFrontFace { VK_FRONT_FACE_COUNTER_CLOCKWISE = 0, VK_FRONT_FACE_CLOCKWISE = 1 } VkFrontFace;
+typedef enum VkCullModeFlagBits { VK_CULL_MODE_NONE = 0, VK_CULL_MODE_FRONT_BIT = 1, VK_CULL_MODE_BACK_BIT = 2, VK_CULL_MODE_FRONT_AND_BACK = 3 } VkCullModeFlagBits;
+typedef VkFlags VkCullModeFlags;
+#define VK_EXT_line_rasterization 1
+typedef enum VkLineRasterizationModeEXT { VK_LINE_RASTERIZATION_MODE_DEFAULT_EXT = 0, VK_LINE_RASTERIZATION_MODE_RECTANGULAR_EXT = 1, VK_LINE_RASTERIZATION_MODE_BRESENHAM_EXT = 2, VK_LINE_RASTERIZATION_MODE_RECTANGULAR_SMOOTH_EXT = 3 } VkLineRasterizationModeEXT;
+typedef enum VkVertexInputRate { VK_VERTEX_INPUT_RATE_VERTEX = 0, VK_VERTEX_INPUT_RATE_INSTANCE = 1 } VkVertexInputRate;
+typedef struct VkVertexInputBindingDescription { uint32_t binding, stride; VkVertexInputRate inputRate; } VkVertexInputBindingDescription;
+typedef struct VkVertexInputAttributeDescription { uint32_t location, binding; VkFormat format; uint32_t offset; } VkVertexInputAttributeDescription;
+typedef enum VkStencilOp { VK_STENCIL_OP_KEEP = 0, VK_STENCIL_OP_ZERO = 1, VK_STENCIL_OP_REPLACE = 2, VK_STENCIL_OP_INCREMENT_AND_CLAMP = 3, VK_STENCIL_OP_DECREMENT_AND_CLAMP = 4, VK_STENCIL_OP_INVERT = 5, VK_STENCIL_OP_INCREMENT_AND_WRAP = 6, VK_STENCIL_OP_DECREMENT_AND_WRAP = 7 } VkStencilOp;
+typedef struct VkStencilOpState { VkStencilOp failOp, passOp, depthFailOp; VkCompareOp compareOp; uint32_t compareMask, writeMask, reference; } VkStencilOpState;
+typedef enum VkLogicOp { VK_LOGIC_OP_CLEAR = 0, VK_LOGIC_OP_AND = 1, VK_LOGIC_OP_AND_REVERSE = 2, VK_LOGIC_OP_COPY = 3, VK_LOGIC_OP_AND_INVERTED = 4, VK_LOGIC_OP_NO_OP = 5, VK_LOGIC_OP_XOR = 6, VK_LOGIC_OP_OR = 7, VK_LOGIC_OP_NOR = 8, VK_LOGIC_OP_EQUIVALENT = 9, VK_LOGIC_OP_INVERT = 10, VK_LOGIC_OP_OR_REVERSE = 11, VK_LOGIC_OP_COPY_INVERTED = 12, VK_LOGIC_OP_OR_INVERTED = 13, VK_LOGIC_OP_NAND = 14, VK_LOGIC_OP_SET = 15 } VkLogicOp;
+typedef struct VkPipelineColorBlendAttachmentState { VkBool32 blendEnable; VkBlendFactor srcColorBlendFactor, dstColorBlendFactor; VkBlendOp colorBlendOp; VkBlendFactor srcAlphaBlendFactor, dstAlphaBlendFactor; VkBlendOp alphaBlendOp; VkColorComponentFlags colorWriteMask; } VkPipelineColorBlendAttachmentState;
+typedef VkFlags VkAttachmentDescriptionFlags;
+typedef enum VkAttachmentLoadOp { VK_ATTACHMENT_LOAD_OP_LOAD = 0, VK_ATTACHMENT_LOAD_OP_CLEAR = 1, VK_ATTACHMENT_LOAD_OP_DONT_CARE = 2 } VkAttachmentLoadOp;
+typedef enum VkAttachmentStoreOp { VK_ATTACHMENT_STORE_OP_STORE = 0, VK_ATTACHMENT_STORE_OP_DONT_CARE = 1 } VkAttachmentStoreOp;
+typedef VkFlags VkSubpassDescriptionFlags;
+typedef enum VkPipelineBindPoint { VK_PIPELINE_BIND_POINT_GRAPHICS = 0, VK_PIPELINE_BIND_POINT_COMPUTE = 1 } VkPipelineBindPoint;
+typedef VkFlags VkPipelineStageFlags;
+typedef VkFlags VkAccessFlags;
+typedef VkFlags VkDependencyFlags;
+""")
 here = os.path.dirname(os.path.abspath(__file__))
 open(os.path.join(here, "vulkan", "vulkan_core.h"), "w").write("".join(o))
 open(os.path.join(here, "vulkan", "vulkan.h"), "w").write("#pragma once\n#include \"vulkan_core.h\"\n")

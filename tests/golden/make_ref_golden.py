@@ -1,7 +1,8 @@
 """Generates tests/golden/ref_*.{txt,npz}: outputs of the REFERENCE's own code for the pieces of the path that execute
 in this image — CPVulkanBase/Formats.cpp (format table, image layout, GetImagePixelOffset), CPVulkanBase/FloatFormat.h
-(half <-> float, the codec behind R16G16B16A16_SFLOAT) and CPVulkan/ImageSampler.cpp (the texture sampler) — compiled in
-place into oracle/_ref/formats_check and oracle/_ref/sampler_check (oracle/Makefile, oracle/ref_*_check.cpp). Run in the build container (needs /root/reference):
+(half <-> float, the codec behind R16G16B16A16_SFLOAT) and CPVulkan/ImageSampler.cpp (the texture sampler) and the rasteriser / interpolator /
+blend functions of CPVulkan/CommandBuffer.Draw.cpp — compiled in
+place into oracle/_ref/formats_check, oracle/_ref/sampler_check and oracle/_ref/draw_check (oracle/Makefile, oracle/ref_*_check.cpp). Run in the build container (needs /root/reference):
 
     make -C oracle ref && python tests/golden/make_ref_golden.py
 
@@ -107,7 +108,50 @@ def sampler3d_golden():
     print("sampler 3d: %d + %d coordinates x 2 filters" % (len(out["coords_a"]), len(out["coords_b"])))
 
 
+DRAW_CHECK = os.path.join(os.path.dirname(CHECK), "draw_check")
+
+
+def run_draw_check(mode, payload):
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src, dst = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        with open(src, "wb") as f:
+            f.write(payload)
+        subprocess.run([DRAW_CHECK, mode, src, dst], check=True)
+        with open(dst, "rb") as f:
+            return f.read()
+
+
+def draw_golden():
+    """The reference's CalculatePrimitives / ProcessTriangles / ProcessLines / ProcessPoints / GetFragmentInput / SetDatum /
+    DrawPixel (fragment streams) and ApplyBlend, run by oracle/_ref/draw_check on the seeded cases of tests/ref_draw_cases.py.
+    Cases flagged `full` keep every fragment record; the others keep the fragment count and the SHA-256 of the stream. NaN bit patterns are canonicalised first
+    (rc.canonical: sign and payload of a NaN differ between any two builds)."""
+    import hashlib
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    import ref_draw_cases as rc
+    cases = rc.raster_cases()
+    streams = [rc.canonical(t) for t in rc.parse_raster_output(run_draw_check("raster", rc.raster_file(cases)), len(cases))]
+    out = {"names": np.array([c.name for c in cases]), "counts": np.array([len(s) for s in streams], dtype=np.uint64),
+           "sha256": np.array([hashlib.sha256(np.ascontiguousarray(s).tobytes()).hexdigest() for s in streams])}
+    for i, (c, s) in enumerate(zip(cases, streams)):
+        assert s.shape[1] == rc.WORDS or len(s) == 0
+        if c.full:
+            out["stream_%d" % i] = s
+    states, operands = rc.blend_cases()
+    res = np.frombuffer(run_draw_check("blend", rc.blend_file(states, operands)), dtype="<u4").reshape(len(states), 4)
+    out["blend_bits"] = rc.canonical_floats(res)
+    np.savez_compressed(os.path.join(HERE, "ref_draw.npz"), **out)
+    total = int(sum(len(s) for s in streams))
+    full = int(sum(len(s) for c, s in zip(cases, streams) if c.full))
+    print("draw: %d raster cases, %d fragments (%d stored in full), %d blend cases" % (len(cases), total, full, len(states)))
+    for c, s in zip(cases, streams):
+        print("   %-28s %8d fragments%s" % (c.name, len(s), "  (full)" if c.full else ""))
+
+
 def main():
+    draw_golden()
     sampler_golden()
     sampler3d_golden()
     open(os.path.join(HERE, "ref_formats.txt"), "w").write(run("formats"))
