@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
     // binning pass 0, fused: count the (primitive, tile) pairs while the bbox is in registers
     bool small = false; int tx0 = 0, ty0 = 0, tw = 1, n = 0;
     if (bb.x1 > bb.x0) {
-        tx0 = bb.x0 / CPVK_TILE_W; ty0 = bb.y0 / CPVK_TILE_H;
-        const int tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
+        tx0 = bb.x0 / CPVK_TILE_W; ty0 = bb.y0 / CPVK_TILE_H - (int)a.tileRow0;
+        const int tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty1 = (bb.y1 - 1) / CPVK_TILE_H - (int)a.tileRow0;
         tw = tx1 - tx0 + 1; n = tw * (ty1 - ty0 + 1);
         if (n > CPVK_BIN_SMALL) a.largeList[atomicAdd(a.meta + 2, 1u)] = p;
         else small = true;
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(256) k_bin(CpvkBinArgs a, int pass) {
     if (p < a.primCount) {
         const CpvkBBox bb = a.bboxes[p];
         if (bb.x1 > bb.x0) {
-            tx0 = bb.x0 / CPVK_TILE_W; ty0 = bb.y0 / CPVK_TILE_H;
-            const int tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
+            tx0 = bb.x0 / CPVK_TILE_W; ty0 = bb.y0 / CPVK_TILE_H - (int)a.tileRow0;
+            const int tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty1 = (bb.y1 - 1) / CPVK_TILE_H - (int)a.tileRow0;
             tw = tx1 - tx0 + 1; n = tw * (ty1 - ty0 + 1);
             small = n <= CPVK_BIN_SMALL; // larger ones are deferred to k_bin_large (listed by k_setup)
         }
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) k_bin_large(CpvkBinArgs a, int pass) {
     for (cpvk_u32 li = blockIdx.x; li < nLarge; li += gridDim.x) {
         const cpvk_u32 p = a.largeList[li];
         const CpvkBBox bb = a.bboxes[p];
-        const int tx0 = bb.x0 / CPVK_TILE_W, tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty0 = bb.y0 / CPVK_TILE_H, ty1 = (bb.y1 - 1) / CPVK_TILE_H;
+        const int tx0 = bb.x0 / CPVK_TILE_W, tx1 = (bb.x1 - 1) / CPVK_TILE_W, ty0 = bb.y0 / CPVK_TILE_H - (int)a.tileRow0, ty1 = (bb.y1 - 1) / CPVK_TILE_H - (int)a.tileRow0;
         const int tw = tx1 - tx0 + 1, n = tw * (ty1 - ty0 + 1);
         for (int k = threadIdx.x; k < n; k += blockDim.x) {
             const int ty = ty0 + k / tw, tx = tx0 + k % tw;

@@ -20,6 +20,7 @@ struct CpvkSetupArgs {
     CpvkBBox* bboxes;
     // binning pass 0 (count) is fused into setup: the bbox is in registers right here
     cpvk_u32 tilesX;
+    cpvk_u32 tileRow0;   // first tile row of the render area (a band starts below row 0): tile ids count from there
     cpvk_u32* counts;    // [tiles], zeroed by the host
     cpvk_u32* largeList; // [primCount]
     cpvk_u32* meta;      // [2] = number of deferred (large) primitives, zeroed by the host
@@ -27,7 +28,7 @@ struct CpvkSetupArgs {
 
 struct CpvkBinArgs {
     const CpvkBBox* bboxes;
-    cpvk_u32 primCount, tilesX, tilesY;
+    cpvk_u32 primCount, tilesX, tilesY, tileRow0; // tilesY rows starting at tile row tileRow0
     cpvk_u32* counts;    // [tiles]
     cpvk_u32* offsets;   // [tiles + 1]
     cpvk_u32* cursors;   // [tiles]

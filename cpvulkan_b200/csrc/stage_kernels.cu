@@ -208,10 +208,10 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     const bool listsSorted = triangles && p.binMeta[1] > CPVK_CHUNK;
     const cpvk_u32 listBegin = triangles ? p.tileOffsets[tile] : 0u, listEnd = triangles ? p.tileOffsets[tile + 1] : 1u;
     const cpvk_u32 lazyMask = p.lazyMask;
-    const cpvk_u32 ty = tile / p.tilesX, tx = tile - ty * p.tilesX;
-    const int tileX0 = (int)tx * CPVK_TILE_W, tileY0 = (int)ty * CPVK_TILE_H;
+    const cpvk_u32 tyr = tile / p.tilesX, tx = tile - tyr * p.tilesX;
+    const int tileX0 = (int)tx * CPVK_TILE_W, tileY0 = (int)(tyr + p.tileRow0) * CPVK_TILE_H;
     // nothing to draw and no clear to fold: done — unless mirrors are on, then even untouched tiles of the band travel
-    if (listBegin == listEnd && lazyMask == 0 && !(p.mirrorCount != 0 && tileY0 + CPVK_TILE_H > p.clipY0)) return;
+    if (listBegin == listEnd && lazyMask == 0 && p.mirrorCount == 0) return;
 
     const cpvk_u32 dsFormat = cpvk_spec_u32(CPVK_SPEC_DS_FORMAT);
     const bool depthTest = cpvk_spec_u32(CPVK_SPEC_DEPTH_TEST) != 0, depthWrite = cpvk_spec_u32(CPVK_SPEC_DEPTH_WRITE) != 0;
@@ -248,8 +248,12 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
 
     // tile extent inside the render area
     const int x1 = min(tileX0 + CPVK_TILE_W, p.clipX1), y1 = min(tileY0 + CPVK_TILE_H, p.clipY1);
-    const int tw = x1 - tileX0, th = y1 - tileY0;
+    // rows of this tile inside the render area: a band need not start on a tile row, and the rows above it belong to
+    // another GPU (which stores them into this frame while this kernel runs) — they are neither read nor written here
+    const int wy0 = max(tileY0, p.clipY0);
+    const int tw = x1 - tileX0, th = y1 - wy0;
     if (tw <= 0 || th <= 0) return;
+    const cpvk_u32 skipRows = (cpvk_u32)(wy0 - tileY0);
 
     // pixel centres in NDC, exactly as Draw.cpp:1524,1573,1578: ((float)x / W + (1/W)*0.5) * 2 - 1
     if (threadIdx.x < CPVK_TILE_W) {
@@ -274,7 +278,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             cpvk_set_depth_stencil(dsFormat, one, p.lazyDepth, p.lazyStencil);
             cpvk_tile_fill(sDepth, dsTexel, one);
         } else
-            cpvk_tile_copy(sDepth, dsPitch, reinterpret_cast<const cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel,
+            cpvk_tile_copy(sDepth + skipRows * dsPitch, dsPitch, reinterpret_cast<const cpvk_u8*>(p.ds.address) + (cpvk_u64)wy0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel,
                            p.ds.rowPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th, dsPitch);
     }
     #pragma unroll
@@ -287,7 +291,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                 else { const float v[4] = {__uint_as_float(p.lazyColor[a][0]), __uint_as_float(p.lazyColor[a][1]), __uint_as_float(p.lazyColor[a][2]), __uint_as_float(p.lazyColor[a][3])}; cpvk_set_pixel_f32(cf, one, v); }
                 cpvk_tile_fill(sColor[a], cTexel[a], one);
             } else
-                cpvk_tile_copy(sColor[a], cTexel[a] * CPVK_TILE_W, reinterpret_cast<const cpvk_u8*>(p.color[a].address) + (cpvk_u64)tileY0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a],
+                cpvk_tile_copy(sColor[a] + skipRows * cTexel[a] * CPVK_TILE_W, cTexel[a] * CPVK_TILE_W, reinterpret_cast<const cpvk_u8*>(p.color[a].address) + (cpvk_u64)wy0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a],
                                p.color[a].rowPitch, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th, cTexel[a] * CPVK_TILE_W);
         }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -804,21 +808,18 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     __syncthreads();
     // ---- write the tile back: shared -> HBM, row segments are contiguous in the linear image ----
     if (dsUsed && ((depthTest && depthWrite) || stencilOn || (lazyMask & 0x100u)))
-        cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.ds.address) + (cpvk_u64)tileY0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel, p.ds.rowPitch,
-                       sDepth, dsPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th, dsPitch);
+        cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.ds.address) + (cpvk_u64)wy0 * p.ds.rowPitch + (cpvk_u64)tileX0 * dsTexel, p.ds.rowPitch,
+                       sDepth + skipRows * dsPitch, dsPitch, (cpvk_u32)tw * dsTexel, (cpvk_u32)th, dsPitch);
     #pragma unroll
     for (int a = 0; a < CPVK_MAX_COLOR; a++)
         if (sColor[a])
-            cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.color[a].address) + (cpvk_u64)tileY0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a], p.color[a].rowPitch,
-                           sColor[a], cTexel[a] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th, cTexel[a] * CPVK_TILE_W);
+            cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.color[a].address) + (cpvk_u64)wy0 * p.color[a].rowPitch + (cpvk_u64)tileX0 * cTexel[a], p.color[a].rowPitch,
+                           sColor[a] + skipRows * cTexel[a] * CPVK_TILE_W, cTexel[a] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th, cTexel[a] * CPVK_TILE_W);
     // ---- the fused gather: the band's rows of this tile go to every peer's copy of colour attachment 0 ----
-    if (p.mirrorCount && sColor[0]) {
-        const int my0 = max(tileY0, p.clipY0);
-        if (my0 < y1)
-            for (cpvk_u32 m = 0; m < p.mirrorCount; m++)
-                cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.mirror[m]) + (cpvk_u64)my0 * p.color[0].rowPitch + (cpvk_u64)tileX0 * cTexel[0], p.color[0].rowPitch,
-                               sColor[0] + (cpvk_u32)(my0 - tileY0) * cTexel[0] * CPVK_TILE_W, cTexel[0] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[0], (cpvk_u32)(y1 - my0), cTexel[0] * CPVK_TILE_W);
-    }
+    if (p.mirrorCount && sColor[0])
+        for (cpvk_u32 m = 0; m < p.mirrorCount; m++)
+            cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.mirror[m]) + (cpvk_u64)wy0 * p.color[0].rowPitch + (cpvk_u64)tileX0 * cTexel[0], p.color[0].rowPitch,
+                           sColor[0] + skipRows * cTexel[0] * CPVK_TILE_W, cTexel[0] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[0], (cpvk_u32)th, cTexel[0] * CPVK_TILE_W);
     if (p.stats && lane == 0 && (nCov | nPass)) {
         atomicAdd(p.stats + 0, (cpvk_u64)nCov);
         atomicAdd(p.stats + 1, (cpvk_u64)nPass);

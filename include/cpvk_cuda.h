@@ -291,7 +291,10 @@ int cpvk_cuda_flush(CpvkDevice* device);
 /* Draws are enqueued to the end without waiting for the binning counts: list capacity, sort mode and the large-
    primitive passes are guessed from the previous draw, checked on the device, and the tail of the draw is replayed
    with exact sizes when the guess was wrong (the check happens before this library enqueues or reads anything else,
-   so results never depend on the guess). 0 turns this off: every draw then waits for its counts (one host round trip). */
+   so results never depend on the guess). On a stream supplied through cpvk_cuda_device_set_stream the check (and the
+   replay, if any) happens before cpvk_cuda_draw returns, so that work the caller enqueues on that stream right after the
+   call — a collective, an event, a copy — is ordered after the complete draw; on the device's own stream it happens at the
+   next entry point. 0 turns speculation off: every draw then waits for its counts (one host round trip). */
 int cpvk_cuda_device_set_speculation(CpvkDevice* device, int enable);
 int cpvk_cuda_device_set_lazy_clear(CpvkDevice* device, int enable);
 
