@@ -2,17 +2,28 @@
 """bench.py — headline benchmark of the B200 draw path (BASELINE.json: Mtris/s and Gfragments/s for
 vkCmdDrawIndexed at 4K; ms/frame at 1/2/4/8 B200).
 
-Workload (config.workload = "C3/M1"): SURVEY §8(d) C3 — one vkCmdDrawIndexed of a 1000x500-quad grid
-(1,000,000 triangles, 3,000,000 u32 indices, 501,501 vertices {vec4 pos, vec4 rgba}) at 3840x2160,
-R8G8B8A8_UNORM + D32_SFLOAT, depth LESS_OR_EQUAL + write, opaque. A "step" is one frame: render-pass clear of
-colour and depth + the draw. With --gpus N (torchrun, one rank per GPU) the frame is split sort-first into N
-horizontal bands, vertex work replicated, and the finished bands are all-gathered over NCCL (scaling: strong).
+Default workload (config.workload "C3/M1"): one vkCmdDrawIndexed of a 1000x500-quad grid (1,000,000
+triangles, 3,000,000 u32 indices, 501,501 vertices {vec4 pos, vec4 rgba}) at 3840x2160, R8G8B8A8_UNORM + D32_SFLOAT,
+depth LESS_OR_EQUAL + write, opaque. `--config c4` runs BASELINE config 4 instead: all 2,000 alpha-blended
+LINEAR-textured full-screen quads at 7680x4320 RGBA16F. A "step" is one frame: render-pass clear + the draw
+(+ the band exchange on N > 1 GPUs).
 
-One JSON line on stdout (rank 0). Keys beyond the base contract: roofline, cpu_baseline, e2e, clocks, gpu_launches,
-plus gfragments_per_s / ms_per_frame breakdown.
+With --gpus N (torchrun, one rank per GPU) the frame is split sort-first into N bands of tile rows, vertex work is
+replicated, and k_raster stores every finished tile of a rank's band straight into the presenting GPU's frame (rank 0;
+`--gather all`: into every GPU's frame) over NVLink — peer memory mapped through the C ABI's cudaIpc export / import, the
+handles exchanged with torch.distributed; a 4-byte NCCL all-reduce on the draw stream orders the GPUs after the stores.
+Scaling is strong (fixed frame).
+
+Timing: the K steps asked for are one block, bracketed by barrier + synchronize and timed with CUDA events on the launching
+stream; blocks are repeated until at least 0.5 s and 200 frames have been timed (>= 5 blocks), and `value` comes from the
+MEDIAN block (max over ranks per block), so a scheduling hiccup in one block does not move the headline.
+
+One JSON line on stdout (rank 0). Keys beyond the base contract: roofline, cpu_baseline, e2e, clocks, gpu_launches, icd,
+blocks, kernel_ms_rank0, other_configs.
 
   python bench.py                       # N=1, C3/M1
-  python bench.py --impl reference      # the CPU arm: the oracle restatement of the reference path on host cores
+  python bench.py --config c4           # N=1, the full C4 frame
+  python bench.py --impl reference      # the CPU arm: the oracle restatement of the reference path on the host cores
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N
 """
 import argparse
@@ -107,23 +118,86 @@ class ClockSampler(threading.Thread):
                 "source": "nvidia-smi -lms 200"}
 
 
-def oracle_draw_seconds(scene, repeats=1):
-    """Time the oracle's equivalent of DrawIndexedCommand::Process (draw only; clears outside) on one host core."""
+TILE = 32
+
+
+class Workload:
+    """What one step renders, and how its numbers are named."""
+
+    def __init__(self, key, quads=None):
+        self.key = key
+        if key == "c3":
+            self.scene = scenes.mesh_indexed(WIDTH, HEIGHT, NX, NY)
+            self.prims = 2 * NX * NY
+            self.metric = "Mtris/s (vkCmdDrawIndexed, 1M triangles at 3840x2160, D32 depth test, opaque)"
+            self.unit, self.scale = "Mtris/s", 1e6
+            self.workload = "C3/M1: 1,000,000-triangle indexed grid, 3840x2160 RGBA8+D32, LESS_OR_EQUAL, opaque; step = clear + draw"
+            self.l2 = ("working set (indices 12 MB + vertices 16 MB + shaded vertices 16 MB + setup records 104 MB + tile lists 5 MB + "
+                       "targets 66 MB) exceeds the 126 MB L2; no explicit flush")
+        else:
+            self.quads = quads or 2000
+            self.scene = scenes.overdraw_quads(7680, 4320, quads=self.quads, tex_size=1024)
+            self.prims = 2 * self.quads
+            self.metric = "Gfragments/s (%s alpha-blended LINEAR-textured full-screen quads at 7680x4320 RGBA16F)" % ("2,000" if self.quads == 2000 else str(self.quads))
+            self.unit, self.scale = "Gfragments/s", 1e9
+            self.workload = "C4: %d alpha-blended LINEAR / REPEAT textured full-screen quads, 7680x4320 RGBA16F, 1024^2 RGBA8 texture; step = clear + draw" % self.quads
+            self.l2 = "the 265 MB colour target exceeds the 126 MB L2; tiles live in shared memory between the quads; no explicit flush"
+
+    def units(self, n_cov):
+        """What `value` counts per step: triangles (C3) or coverage-passing fragments (C4)."""
+        return self.prims if self.key == "c3" else n_cov
+
+    def algorithmic_bytes(self, n_cov, n_pass):
+        # SURVEY §8(d): depth read per covered fragment, depth write + colour write (+ colour read when blending) per passing one
+        return n_cov * 4 + n_pass * 8 if self.key == "c3" else n_pass * 16
+
+
+def band_rows(height, rank, world):
+    """Rows [y0, y1) of rank's sort-first band: whole 32-row tile rows, spread evenly (the same split cpvk_cuda_draw makes for
+    the members of a group), so no tile is rasterised by two GPUs."""
+    tile_rows = (height + TILE - 1) // TILE
+    a, b = rank * tile_rows // world, (rank + 1) * tile_rows // world
+    return min(a * TILE, height), min(b * TILE, height)
+
+
+def oracle_draw_seconds(scene, threads=1, repeats=1):
+    """Time the oracle's equivalent of DrawIndexedCommand::Process (draw only; clears outside). threads > 1: the frame is cut
+    into that many horizontal windows rendered concurrently (cpvk_oracle_draw_window; pixels are independent in the reference,
+    every window replays the vertex stage) — the reference itself is single-threaded (Queue.cpp:52-59)."""
+    from concurrent.futures import ThreadPoolExecutor
     lib = capi.load_oracle()
     mem = scenes.HostMemory()
     m = scenes.materialize(scene, mem.alloc)
-    times, stats = [], capi.DrawStats()
-    for _ in range(repeats):
-        for img, att in ((scene.color, m.color_attachment), (scene.depth, m.depth_attachment)):
-            if img is not None and img.clear is not None:
-                cv, is_ds = scenes.clear_value(img)
-                lib.cpvk_oracle_clear(C.byref(att), C.byref(cv), is_ds)
-        t0 = time.perf_counter()
-        rc = lib.cpvk_oracle_draw(C.byref(m.desc), C.byref(m.state), C.byref(stats))
-        times.append(time.perf_counter() - t0)
+    times, covered = [], 0
+    h, w = scene.color.height, scene.color.width
+    cuts = [(i * h // threads, (i + 1) * h // threads) for i in range(threads)]
+
+    def one(window):
+        st = capi.DrawStats()
+        rc = lib.cpvk_oracle_draw_window(C.byref(m.desc), C.byref(m.state), 0, window[0], w, window[1], C.byref(st))
         if rc != 0:
             raise RuntimeError(lib.cpvk_oracle_last_error().decode())
-    return statistics.median(times), stats
+        return int(st.fragmentsCovered)
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        for _ in range(repeats):
+            for img, att in ((scene.color, m.color_attachment), (scene.depth, m.depth_attachment)):
+                if img is not None and img.clear is not None:
+                    cv, is_ds = scenes.clear_value(img)
+                    lib.cpvk_oracle_clear(C.byref(att), C.byref(cv), is_ds)
+            t0 = time.perf_counter()
+            covered = sum(pool.map(one, cuts))
+            times.append(time.perf_counter() - t0)
+    return statistics.median(times), covered
+
+
+def cpu_sample(work, threads):
+    """The bounded CPU sample of a workload: C3 = the whole draw; C4 = the whole 8K frame for 2 of the quads (the cost is linear
+    in quads: every quad covers every pixel)."""
+    if work.key == "c3":
+        return work.scene, 1.0, "full C3/M1 draw (1,000,000 triangles), draw only"
+    q = 2
+    return scenes.overdraw_quads(7680, 4320, quads=q, tex_size=1024), work.quads / q, "%d of the %d quads at 7680x4320 (cost is linear in quads), draw only" % (q, work.quads)
 
 
 def cpu_info():
@@ -140,30 +214,39 @@ def cpu_info():
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm for the path on the host CPU. The reference ICD cannot be
-    built in this image (LLVM-8 / Vulkan SDK / GSL / glm missing), so this arm times the oracle
-    restatement, single-threaded like the reference's inline vkQueueSubmit (Queue.cpp:52-59)."""
+    """--impl reference: the reference's own algorithm for the path on the host CPU. The reference ICD cannot be built in this
+    image (LLVM-8 / Vulkan SDK / GSL / glm >= 0.9.9 missing), so this arm times the oracle restatement (pinned
+    against the reference's own Draw.cpp / ImageSampler.cpp / Formats.cpp) on every host core it can use."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     build.build_oracle()
-    scene = scenes.mesh_indexed(WIDTH, HEIGHT, NX, NY)
-    for _ in range(min(args.warmup, 1)):
-        oracle_draw_seconds(scene)
-    t, st = oracle_draw_seconds(scene, repeats=max(1, min(args.steps, 5)))
-    prims = 2 * NX * NY
+    work = Workload(args.config)
+    threads = max(1, len(os.sched_getaffinity(0)))
+    scene, factor, what = cpu_sample(work, threads)
+    for _ in range(args.warmup):
+        oracle_draw_seconds(scene, threads)
+    times = []
+    covered = 0
+    for _ in range(args.steps):
+        t, covered = oracle_draw_seconds(scene, threads)
+        times.append(t * factor)
+    t = statistics.median(times)
+    t1, _ = oracle_draw_seconds(scene, 1)
     model, ncpu = cpu_info()
-    val = prims / t / 1e6
+    units = work.units(int(covered * factor))
+    val = units / t / work.scale
     line = {
-        "impl": "reference", "metric": "Mtris/s (vkCmdDrawIndexed, 1M triangles at 3840x2160, D32 depth test, opaque)", "value": val, "unit": "Mtris/s",
-        "n_gpus": args.gpus, "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": work.metric, "value": val, "unit": work.unit,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3/M1: 1,000,000-triangle indexed grid, 3840x2160 RGBA8+D32, LESS_OR_EQUAL, opaque", "l2": "n/a (CPU)"},
-        "gfragments_per_s": st.fragmentsCovered / t / 1e9,
-        "cpu_baseline": {"value": val, "unit": "Mtris/s", "cores": 1, "kind": "port",
-                         "sample": "full C3/M1 draw (1,000,000 triangles, %d fragments), draw only, median of runs; %s, %s logical CPUs; "
-                                   "oracle omits the reference's JIT/indirect-call overhead (optimistic stand-in)" % (st.fragmentsCovered, model, ncpu)},
-        "e2e": {"value": val, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": work.workload, "parallelism": "sort-first bands x%d" % args.gpus, "l2": "n/a (CPU)"},
+        "gfragments_per_s": covered * factor / t / 1e9, "ms_per_frame": t * 1e3,
+        "cpu_baseline": {"value": val, "unit": work.unit, "cores": threads, "kind": "port",
+                         "sample": "%s, median of %d steps, %d threads (one horizontal window each); one thread: %.3f %s; %s, %s logical CPUs; "
+                                   "the oracle omits the reference's JIT / indirect-call overhead (optimistic stand-in)"
+                                   % (what, args.steps, threads, units / (t1 * factor) / work.scale, work.unit, model, ncpu)},
+        "e2e": {"value": val, "unit": work.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
@@ -193,6 +276,300 @@ def bind_near_gpu(index):
         return "unchanged (%s)" % type(e).__name__
 
 
+class Rig:
+    """One rank's device, scene and frame function for a workload; on N > 1 ranks also the peer mapping of the colour frame."""
+
+    def __init__(self, work, torch, dist, stream, local, rank, world, gather):
+        from cpvulkan_b200.device import Device, SceneOnDevice
+        self.torch, self.dist, self.work, self.rank, self.world = torch, dist, work, rank, world
+        self.dev = Device(local, stream=stream.cuda_stream, stats=True)
+        self.sod = SceneOnDevice(self.dev, work.scene)
+        scene = work.scene
+        self.band = band_rows(scene.color.height, rank, world) if world > 1 else None
+        self.peers = []
+        self.token = torch.zeros(1, dtype=torch.int32, device="cuda") if world > 1 else None
+        if world > 1:
+            st = self.sod.m.state
+            st.bandY0, st.bandY1 = self.band
+            # the colour frame of every rank, mapped into this process (cudaIpc through the C ABI; torch.distributed only carries
+            # the 64-byte handles)
+            handles = [None] * world
+            dist.all_gather_object(handles, self.dev.export_handle(self.sod.m.addr["color"]))
+            targets = [r for r in range(world) if r != rank] if gather == "all" else ([0] if rank != 0 else [])
+            for i, r in enumerate(targets):
+                addr = self.dev.import_handle(handles[r])
+                self.peers.append(addr)
+                st.mirrorColor0[i] = addr
+            st.mirrorCount = len(targets)
+
+    def frame(self):
+        self.sod.clear(band_only=self.world > 1)
+        self.sod.draw()
+        if self.world > 1:
+            # orders the GPUs: the collective starts on a rank after its raster kernel (and its peer stores) finished, and ends
+            # everywhere only after it started everywhere
+            self.dist.all_reduce(self.token)
+
+    def single_gpu_frame(self):
+        """The frame one GPU renders without bands, into a second image (the reference for the exchange)."""
+        st = self.sod.m.state
+        saved = (st.bandY0, st.bandY1, st.mirrorCount, st.color[0].address, self.sod.m.color_attachment.address)
+        whole = self.dev.alloc(self.work.scene.color.nbytes)
+        st.bandY0 = st.bandY1 = 0
+        st.mirrorCount = 0
+        st.color[0].address = self.sod.m.color_attachment.address = whole
+        self.sod.clear(); self.sod.draw(); self.dev.sync()
+        out = self.dev.download(whole, self.work.scene.color.nbytes)
+        st.bandY0, st.bandY1, st.mirrorCount, st.color[0].address, self.sod.m.color_attachment.address = saved
+        self.dev.free(whole)
+        return out
+
+    def close(self):
+        self.dev.sync()
+        for a in self.peers:
+            self.dev.unimport(a)
+        self.sod.close()
+        self.dev.close()
+
+
+def timed_blocks(torch, dist, world, frame, steps, min_seconds=0.5, min_frames=200, min_blocks=5, max_blocks=400):
+    """Blocks of exactly `steps` frames, each bracketed by barrier + synchronize and timed with CUDA events on the current
+    stream; per block the max over ranks. Returns the list of block times in ms."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    blocks, total_ms, frames = [], 0.0, 0
+    while len(blocks) < max_blocks and (len(blocks) < min_blocks or total_ms < min_seconds * 1e3 or frames < min_frames):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            frame()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        blocks.append(ms); total_ms += ms; frames += steps
+    return blocks
+
+
+def measure(rig, steps, warmup, sampler=None):
+    """Resident throughput of rig.frame(): -> dict(ms_step, blocks, n_cov, n_pass, local_cov, local_pass, launches_per_step, kernel_ms)."""
+    torch, dist, world, dev = rig.torch, rig.dist, rig.world, rig.dev
+    for _ in range(max(warmup, 3)):
+        rig.frame()
+    torch.cuda.synchronize()
+    st = dev.stats()
+    local_cov, local_pass = int(st.fragmentsCovered), int(st.fragmentsWritten)
+    n_cov, n_pass = local_cov, local_pass
+    if world > 1:
+        t = torch.tensor([n_cov, n_pass], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        n_cov, n_pass = int(t[0]), int(t[1])
+    dev.set_stats(False)
+    launches0 = dev.launch_count()
+    if sampler and sampler.nvml_samples:
+        sampler.mark()  # NVML samples every 2 ms: keep only those taken inside the timed region
+    blocks = timed_blocks(torch, dist, world, rig.frame, steps)
+    launches = (dev.launch_count() - launches0) / (len(blocks) * steps)
+    ms_step = statistics.median(blocks) / steps
+    # per-kernel durations (CUDA events inside the library, a separate pass so that they do not perturb `value`)
+    dev.set_timing(True)
+    vs, su, bn, rs = [], [], [], []
+    for _ in range(min(steps, 10)):
+        rig.sod.clear(band_only=world > 1)
+        rig.sod.draw()
+        s2 = dev.stats()
+        vs.append(s2.msVertex); su.append(s2.msSetup); bn.append(s2.msBin); rs.append(s2.msRaster)
+    dev.set_timing(False)
+    if world > 1:
+        dist.all_reduce(rig.token)
+        torch.cuda.synchronize()
+    return {"ms_step": ms_step, "blocks": blocks, "n_cov": n_cov, "n_pass": n_pass, "local_cov": local_cov, "local_pass": local_pass,
+            "launches_per_step": launches, "bin_entries": int(s2.binEntries),
+            "kernel_ms": {"vertex": statistics.mean(vs), "setup": statistics.mean(su), "bin": statistics.mean(bn), "raster": statistics.mean(rs)}}
+
+
+def verify_exchange(rig):
+    """N > 1: the frame rank 0 holds after the exchange must be, byte for byte, the frame one GPU renders without bands."""
+    torch = rig.torch
+    rig.frame()
+    torch.cuda.synchronize()
+    rig.dist.barrier()
+    if rig.rank == 0:
+        got = rig.dev.download(rig.sod.m.addr["color"], rig.work.scene.color.nbytes)
+        want = rig.single_gpu_frame()
+        if not np.array_equal(got, want):
+            raise SystemExit("the gathered frame differs from the single-GPU frame (%d bytes)" % int((got != want).sum()))
+    rig.dist.barrier()
+
+
+def e2e_single(torch, rig, local, steps):
+    """e2e through the C ABI with HOST buffers on one GPU: every frame uploads its inputs (vertices, indices, uniforms) from pinned
+    host memory, clears, draws and reads the colour result back into pinned host memory. Like a double-buffered application,
+    two device objects (each with its own stream, scratch and frame) alternate frames, so the read-back of frame k overlaps the
+    upload and rendering of frame k+1; a frame's buffers are reused only after its read-back is done."""
+    from cpvulkan_b200.device import Device, SceneOnDevice
+    scene = rig.work.scene
+    names = [n for n in ("vb", "ib", "ubo") if n in scene.buffers]
+    lanes = []
+    n_lanes = int(os.environ.get("CPVK_E2E_LANES", "2"))
+    for i in range(n_lanes):
+        ldev = Device(local, stats=False)  # runs on its own stream
+        lsod = SceneOnDevice(ldev, scene)
+        staged = {}
+        for nme in names:
+            data = scene.buffers[nme]
+            a = ldev.alloc(data.nbytes, host_shadow=True)
+            ldev.shadow(a)[:data.nbytes] = data
+            staged[nme] = (a, data.nbytes)
+        out_dev = ldev.alloc(scene.color.nbytes, host_shadow=True)  # only its pinned shadow is used as the read-back target
+        lanes.append((ldev, lsod, staged, ldev.allocs[out_dev][1]))
+    h2d = sum(v[1] for v in lanes[0][2].values())
+    d2h = scene.color.nbytes
+
+    def step(k):
+        ldev, lsod, staged, out_host = lanes[k % n_lanes]
+        ldev.sync()  # frame k - n_lanes (same lane) has been read back: its buffers are free
+        for nme in names:
+            src_alloc, nbytes = staged[nme]
+            ldev.upload_async(lsod.m.addr[nme], ldev.allocs[src_alloc][1], nbytes)
+        lsod.clear()
+        lsod.draw()
+        ldev.download_into_async(out_host, lsod.m.addr["color"], d2h)
+
+    for k in range(2 * n_lanes):
+        step(k)
+    for lane in lanes:
+        lane[0].sync()
+    ref_frame = rig.dev.download(rig.sod.m.addr["color"], d2h)  # the read-back frame must be the frame the resident path produced
+    for lane in lanes:
+        got = np.ctypeslib.as_array(C.cast(lane[3], C.POINTER(C.c_uint8)), shape=(d2h,))
+        if not np.array_equal(got, ref_frame):
+            raise SystemExit("e2e read-back differs from the resident frame")
+    n = max(steps, min(200, int(0.5 / 1e-3)))
+    if rig.work.key != "c3":
+        n = steps
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(n):
+        step(k)
+    for lane in lanes:
+        lane[0].sync()
+    ms = (time.perf_counter() - t0) * 1e3 / n
+    for lane in lanes:
+        lane[1].close()
+        lane[0].close()
+    return {"ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "frames_timed": n,
+            "through": "C ABI (cpvk_cuda_mem_upload / clear / draw / mem_download_async + sync) with pinned host buffers; two device objects alternate frames (double buffering)"}
+
+
+def e2e_multi(torch, dist, rig, local, steps):
+    """e2e on N > 1 GPUs (every rank takes part): per frame each rank uploads 1/N of the geometry from its own pinned buffer over
+    its own PCIe link, an NCCL all-gather over NVLink completes every rank's copy (vertex work is replicated, so every GPU needs
+    all of it), the rank renders its band — peer stores and the ordering collective stay in the frame — and reads ITS band back
+    into pinned host memory: the host ends up with the whole frame, one band per process, 1/N of the traffic per link in both
+    directions. The read-back of frame k overlaps frame k+1 (staging copy on the draw stream, a second device object on its own
+    stream carries it to the host; events order the two streams both ways)."""
+    from cpvulkan_b200.device import Device
+    scene, dev, sod, rank, world = rig.work.scene, rig.dev, rig.sod, rig.rank, rig.world
+    stream = torch.cuda.current_stream()
+    names = [n for n in ("vb", "ib") if n in scene.buffers]
+    shards = {}
+    for nme in names:
+        data = scene.buffers[nme]
+        per = (data.nbytes + world - 1) // world
+        per = (per + 15) // 16 * 16
+        full = torch.zeros(per * world, dtype=torch.uint8, device="cuda")     # the gathered copy the draw reads
+        host = torch.zeros(per, dtype=torch.uint8).pin_memory()
+        chunk = data[rank * per:(rank + 1) * per]
+        host[:len(chunk)] = torch.from_numpy(np.ascontiguousarray(chunk))
+        shards[nme] = (full, host, per, data.nbytes)
+    ubo = scene.buffers["ubo"]
+    ubo_stage = dev.alloc(ubo.nbytes, host_shadow=True)
+    dev.shadow(ubo_stage)[:ubo.nbytes] = ubo
+    st = sod.m.state
+    saved = ({b: st.vertexBuffers[b] for b in scene.vertex_buffers}, st.indexBuffer)
+    for b, nme in scene.vertex_buffers.items():
+        st.vertexBuffers[b] = shards[nme][0].data_ptr()
+    if scene.index_buffer:
+        st.indexBuffer = shards[scene.index_buffer][0].data_ptr()
+    y0, y1 = rig.band
+    band_bytes = (y1 - y0) * scene.color.pitch
+    band_addr = sod.m.addr["color"] + y0 * scene.color.pitch
+    stream2 = torch.cuda.Stream()
+    dev2 = Device(local, stream=stream2.cuda_stream, stats=False)
+    slots = []
+    for _ in range(2):
+        staging = torch.empty(max(band_bytes, 16), dtype=torch.uint8, device="cuda")
+        out_dev = dev2.alloc(max(band_bytes, 16), host_shadow=True)  # only its pinned shadow is used, as the read-back target
+        slots.append({"staging": staging, "host": dev2.allocs[out_dev][1], "copied": torch.cuda.Event(), "read": torch.cuda.Event()})
+        slots[-1]["read"].record(stream2)
+
+    def step(k):
+        sl = slots[k % 2]
+        for nme in names:
+            full, host, per, _ = shards[nme]
+            full[rank * per:(rank + 1) * per].copy_(host, non_blocking=True)
+            dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per])
+        dev.upload_async(sod.m.addr["ubo"], dev.allocs[ubo_stage][1], ubo.nbytes)
+        rig.frame()
+        if band_bytes:
+            stream.wait_event(sl["read"])                       # the staging buffer's previous contents have reached the host
+            dev.copy_rows(sl["staging"].data_ptr(), band_bytes, band_addr, band_bytes, band_bytes, 1)
+            sl["copied"].record(stream)
+            stream2.wait_event(sl["copied"])
+            dev2.download_into_async(sl["host"], sl["staging"].data_ptr(), band_bytes)
+            sl["read"].record(stream2)
+
+    for k in range(4):
+        step(k)
+    torch.cuda.synchronize()
+    if band_bytes:
+        want = dev.download(band_addr, band_bytes)
+        for sl in slots:
+            got = np.ctypeslib.as_array(C.cast(sl["host"], C.POINTER(C.c_uint8)), shape=(band_bytes,))
+            if not np.array_equal(got, want):
+                raise SystemExit("e2e read-back of rank %d's band differs from the resident frame" % rank)
+    n = max(steps, 200) if rig.work.key == "c3" else steps
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(n):
+        step(k)
+    dist.barrier(); torch.cuda.synchronize()  # both streams have drained
+    t = torch.tensor([(time.perf_counter() - t0) * 1e3 / n], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    for b in scene.vertex_buffers:
+        st.vertexBuffers[b] = saved[0][b]
+    st.indexBuffer = saved[1]
+    dev2.close()
+    h2d = sum(v[3] for v in shards.values()) + ubo.nbytes * world
+    return {"ms_per_step": float(t[0]), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": scene.color.nbytes, "frames_timed": n,
+            "through": "C ABI on every rank: 1/N of the geometry per rank from pinned host memory + NCCL all-gather over NVLink, clear / draw with "
+                       "the fused peer stores + ordering all-reduce, copy_rows of the rank's band to a staging buffer, mem_download_async on a second "
+                       "device object; read-back of frame k overlapped with frame k+1; max over ranks"}
+
+
+def icd_leg(scene, frames=40):
+    """ms/frame as BASELINE.md §4 defines it: wall clock vkQueueSubmit -> fence signalled, through the Vulkan ICD
+    (libCPVulkan_b200.so loaded by the loader harness via its manifest; reference: Queue.cpp:11-77). The command buffer holds
+    render pass (clear + vkCmdDrawIndexed) + vkCmdCopyImageToBuffer, so the frame is in host-visible memory at the fence; the
+    harness also rewrites its vertex data through the mapping every frame, like an application would."""
+    import tempfile
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            _, _, info = scenes.run_icd(scene, tmp, frames=frames)
+        return {"ms_per_frame_icd": info["ms_submit_to_fence"], "ms_per_frame_icd_with_vertex_rewrite": info["ms_per_frame"], "frames": frames,
+                "what": "cpvk_harness -> libCPVulkan_b200.so: median wall clock of vkQueueSubmit .. vkWaitForFences (render pass + copy to the host-visible read-back buffer)"}
+    except Exception as e:  # never lose the bench line over the extra leg
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -211,318 +588,119 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from cpvulkan_b200.device import Device, SceneOnDevice
-
     build.build_cuda()
-    scene = scenes.mesh_indexed(WIDTH, HEIGHT, NX, NY)
-    # One explicit stream for everything: the draw kernels, the NCCL gather and the timing events. (torch's default
+    # One explicit stream for everything: the draw kernels, the NCCL collectives and the timing events. (torch's default
     # stream has handle 0, which the C ABI reads as "use the device's own stream" — events recorded on the default
     # stream would then not be ordered against the kernels.)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    dev = Device(local, stream=stream.cuda_stream, stats=True)
-    rows = HEIGHT // world
-    band = (rank * rows, (rank + 1) * rows) if world > 1 else None
 
-    # Colour attachment owned by torch. Multi-GPU: peer-mapped (symmetric memory) so that k_raster can store every
-    # finished tile of this rank's band straight into the other GPUs' frames over NVLink — the gather of SURVEY §8(e)
-    # fused into rasterisation; `--gather nccl` keeps the frame private and all-gathers the bands afterwards.
-    symm = None
-    if world > 1 and args.gather == "fused":
-        import torch.distributed._symmetric_memory as symm_mem
-        color_t = symm_mem.empty(scene.color.nbytes, dtype=torch.uint8, device=torch.device("cuda", local))
-        color_t.zero_()
-        symm = symm_mem.rendezvous(color_t, dist.group.WORLD)
-    else:
-        color_t = torch.zeros(scene.color.nbytes, dtype=torch.uint8, device="cuda")
-
-    class Placed(SceneOnDevice):
-        pass
-
-    sod = SceneOnDevice.__new__(Placed)
-    sod.dev, sod.scene, sod.owned = dev, scene, []
-
-    def alloc(name, nbytes, init):
-        if name == "color":
-            return color_t.data_ptr()
-        a = dev.alloc(nbytes)
-        sod.owned.append(a)
-        if init is not None:
-            dev.upload(a, np.ascontiguousarray(init).view(np.uint8).reshape(-1)[:nbytes])
-        return a
-
-    sod.m = scenes.materialize(scene, alloc)
-    sod.pipeline = dev.create_pipeline(sod.m.desc)
-    sod.m.state.pipeline = sod.pipeline.value
-    if band:
-        sod.m.state.bandY0, sod.m.state.bandY1 = band
-    band_bytes = rows * scene.color.pitch
-    if symm is not None:
-        peers = [int(p) for i, p in enumerate(symm.buffer_ptrs) if i != rank]
-        sod.m.state.mirrorCount = len(peers)
-        for i, ptr in enumerate(peers):
-            sod.m.state.mirrorColor0[i] = ptr
-
-    def frame():
-        sod.clear(band_only=world > 1)
-        sod.draw()
-        if symm is not None:
-            symm.barrier()  # every GPU's tiles have landed in every frame before anyone reads or redraws
-        elif world > 1:
-            dist.all_gather_into_tensor(color_t, color_t[rank * band_bytes:(rank + 1) * band_bytes])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        frame()
-    barrier()
-    st = dev.stats()
-    n_cov, n_pass = int(st.fragmentsCovered), int(st.fragmentsWritten)
+    work = Workload(args.config)
+    rig = Rig(work, torch, dist, stream, local, rank, world, args.gather)
     if world > 1:
-        # every rank must now hold the same, complete frame (cheap integrity check of the exchange, outside the timed region)
-        digest = torch.stack([color_t.view(torch.int32).to(torch.int64).sum(), (color_t.view(torch.int32)[::4097].to(torch.int64) * 31).sum()])
-        all_digests = [torch.zeros_like(digest) for _ in range(world)]
-        dist.all_gather(all_digests, digest)
-        if any(not torch.equal(all_digests[0], x) for x in all_digests):
-            raise SystemExit("ranks disagree on the gathered frame")
-        # ... and that frame must be, byte for byte, what one GPU renders without bands
-        whole = torch.zeros_like(color_t)
-        saved = (sod.m.state.bandY0, sod.m.state.bandY1, sod.m.state.mirrorCount, sod.m.state.color[0].address, sod.m.color_attachment.address)
-        sod.m.state.bandY0 = sod.m.state.bandY1 = 0
-        sod.m.state.mirrorCount = 0
-        sod.m.state.color[0].address = sod.m.color_attachment.address = whole.data_ptr()
-        sod.clear(); sod.draw(); dev.sync()
-        sod.m.state.bandY0, sod.m.state.bandY1, sod.m.state.mirrorCount, sod.m.state.color[0].address, sod.m.color_attachment.address = saved
-        if not torch.equal(whole, color_t):
-            raise SystemExit("the gathered frame differs from the single-GPU frame")
-        del whole
-    if world > 1:
-        t = torch.tensor([n_cov, n_pass], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t)
-        n_cov, n_pass = int(t[0]), int(t[1])
-    dev.set_stats(False)
-
+        verify_exchange(rig)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    launches0 = dev.launch_count()
-    barrier()
-    if sampler and sampler.nvml_samples:
-        sampler.mark()  # NVML samples every 2 ms: keep only those taken inside the timed region (nvidia-smi's 200 ms rows are all kept)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        frame()
-    e1.record()
-    barrier()
+    m = measure(rig, args.steps, args.warmup, sampler)
     clocks = sampler.stop() if sampler else None
-    ms_total = e0.elapsed_time(e1)
-    launches = dev.launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t[0])
-    ms_step = ms_total / args.steps
-    prims = 2 * NX * NY
-
-    # per-kernel durations (CUDA events on the launching stream, second pass so the events do not perturb `value`)
-    dev.set_timing(True)
-    vs, su, bn, rs = [], [], [], []
-    for _ in range(args.steps):
-        sod.clear(band_only=world > 1)
-        sod.draw()
-        s2 = dev.stats()
-        vs.append(s2.msVertex); su.append(s2.msSetup); bn.append(s2.msBin); rs.append(s2.msRaster)
-    dev.set_timing(False)
-    ms_raster = statistics.mean(rs)
-    bin_entries = int(s2.binEntries)
-
-    # roofline of the dominant kernel (cpvk_k_raster): algorithmic attachment bytes per launch, SURVEY §8(d):
-    #   N_cov * bD (depth read) + N_pass * (bD + bC) (depth write + colour write); RGBA8 + D32 -> 12 B / fragment
-    local_cov, local_pass = int(st.fragmentsCovered), int(st.fragmentsWritten)
-    b_alg = local_cov * 4 + local_pass * (4 + 4)
+    ms_step, ms_raster = m["ms_step"], m["kernel_ms"]["raster"]
+    b_alg = work.algorithmic_bytes(m["local_cov"], m["local_pass"])
     peak, peak_src = measured_peaks()
     achieved = b_alg / (ms_raster * 1e-3) / 1e9 if ms_raster > 0 else 0.0
 
-    # e2e on N > 1 GPUs (every rank takes part): each frame, every rank uploads the (replicated) geometry from its own pinned
-    # buffers over its own PCIe link, renders its band — the fused gather and its barrier stay in the frame — and reads ITS band
-    # back into pinned host memory: the host ends up with the whole frame, one band per process, 1/N of the read-back per link.
-    # The read-back of frame k overlaps the upload and rendering of frame k+1: the finished band is copied to one of two
-    # staging buffers on the draw stream (16 MB, device to device) and a second device object, on its own stream, carries
-    # it to the host; events order the two streams in both directions.
-    e2e_multi = None
-    if world > 1:
-        names = ["vb", "ib", "ubo"]
-        staged = {}
-        for nme in names:
-            data = scene.buffers[nme]
-            a = dev.alloc(data.nbytes, host_shadow=True)
-            dev.shadow(a)[:data.nbytes] = data
-            staged[nme] = (a, data.nbytes)
-        stream2 = torch.cuda.Stream()
-        dev2 = Device(local, stream=stream2.cuda_stream, stats=False)
-        band_addr = color_t.data_ptr() + rank * band_bytes
-        slots = []
-        for _ in range(2):
-            staging = torch.empty(band_bytes, dtype=torch.uint8, device="cuda")
-            out_dev = dev2.alloc(band_bytes, host_shadow=True)  # only its pinned shadow is used, as the read-back target
-            slots.append({"staging": staging, "host": dev2.allocs[out_dev][1], "copied": torch.cuda.Event(), "read": torch.cuda.Event()})
-            slots[-1]["read"].record(stream2)
+    e2e = e2e_multi(torch, dist, rig, local, args.steps) if world > 1 else e2e_single(torch, rig, local, args.steps)
+    e2e["value"] = work.units(m["n_cov"]) / (e2e["ms_per_step"] * 1e-3) / work.scale
+    e2e["unit"] = work.unit
 
-        def e2e_frame(k):
-            sl = slots[k % 2]
-            for nme in names:
-                src_alloc, nbytes = staged[nme]
-                dev.upload_async(sod.m.addr[nme], dev.allocs[src_alloc][1], nbytes)
-            frame()
-            stream.wait_event(sl["read"])                       # the staging buffer's previous contents have reached the host
-            dev.copy_rows(sl["staging"].data_ptr(), band_bytes, band_addr, band_bytes, band_bytes, 1)
-            sl["copied"].record(stream)
-            stream2.wait_event(sl["copied"])
-            dev2.download_into_async(sl["host"], sl["staging"].data_ptr(), band_bytes)
-            sl["read"].record(stream2)
-
-        for k in range(4):
-            e2e_frame(k)
-        torch.cuda.synchronize()
-        want = color_t[rank * band_bytes:(rank + 1) * band_bytes].cpu()
-        for sl in slots:
-            got = torch.from_numpy(np.ctypeslib.as_array(C.cast(sl["host"], C.POINTER(C.c_uint8)), shape=(band_bytes,)).copy())
-            if not torch.equal(got, want):
-                raise SystemExit("e2e read-back of rank %d's band differs from the resident frame" % rank)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            e2e_frame(k)
-        barrier()  # torch.cuda.synchronize() inside: both streams have drained
-        t = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t[0])
-        e2e_multi = {"value": prims / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": world * sum(v[1] for v in staged.values()),
-                     "d2h_bytes_per_step": world * band_bytes, "ms_per_step": e2e_ms,
-                     "through": "C ABI on every rank (cpvk_cuda_mem_upload of the replicated geometry / clear / draw with the fused gather / copy_rows of "
-                                "the rank's band to a staging buffer / mem_download_async on a second device object), pinned host buffers, "
-                                "read-back of frame k overlapped with frame k+1; max over ranks"}
-        dev2.close()
-
+    # the other BASELINE configs, short, on every N (SCALE_rNN.json then holds C4's scaling next to C3's)
+    extras = None
+    if not args.no_extras:
+        extras = secondary_configs(args, torch, dist, stream, local, rank, world, rig)
     line = None
     if rank == 0:
-        # e2e through the C ABI with HOST buffers: every frame uploads its inputs (vertices, indices, uniforms) from pinned
-        # host memory, clears, draws and reads the colour result back into pinned host memory. Like a double-buffered
-        # application, two device objects (each with its own stream, scratch and frame) alternate frames, so the read-back of
-        # frame k overlaps the upload and rendering of frame k+1; a frame's buffers are reused only after its read-back is done.
-        e2e = e2e_multi
-        if world == 1:
-            names = ["vb", "ib", "ubo"]
-            lanes = []
-            n_lanes = int(os.environ.get("CPVK_E2E_LANES", "2"))
-            for i in range(n_lanes):
-                ldev = dev if i == 0 else Device(local, stats=False)  # the second one runs on its own stream
-                lsod = sod if i == 0 else SceneOnDevice(ldev, scene)
-                staged = {}
-                for nme in names:
-                    data = scene.buffers[nme]
-                    a = ldev.alloc(data.nbytes, host_shadow=True)
-                    ldev.shadow(a)[:data.nbytes] = data
-                    staged[nme] = (a, data.nbytes)
-                out_dev = ldev.alloc(scene.color.nbytes, host_shadow=True)  # only its pinned shadow is used as the readback target
-                lanes.append((ldev, lsod, staged, ldev.allocs[out_dev][1]))
-            h2d = sum(v[1] for v in lanes[0][2].values())
-            d2h = scene.color.nbytes
-
-            def e2e_step(k):
-                ldev, lsod, staged, out_host = lanes[k % n_lanes]
-                ldev.sync()  # frame k-2 (same lane) has been read back: its buffers are free
-                for nme in names:
-                    src_alloc, nbytes = staged[nme]
-                    ldev.upload_async(lsod.m.addr[nme], ldev.allocs[src_alloc][1], nbytes)
-                lsod.clear()
-                lsod.draw()
-                ldev.download_into_async(out_host, lsod.m.addr["color"], d2h)
-
-            for k in range(2 * n_lanes):
-                e2e_step(k)
-            for lane in lanes:
-                lane[0].sync()
-            # the read-back frame must be the frame the resident path produced
-            ref_frame = color_t.cpu().numpy()
-            for lane in lanes:
-                got = np.ctypeslib.as_array(C.cast(lane[3], C.POINTER(C.c_uint8)), shape=(d2h,))
-                if not np.array_equal(got, ref_frame):
-                    raise SystemExit("e2e read-back differs from the resident frame")
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for k in range(args.steps):
-                e2e_step(k)
-            for lane in lanes:
-                lane[0].sync()
-            e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-            e2e = {"value": prims / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                   "through": "C ABI (cpvk_cuda_mem_upload / clear / draw / mem_download_async + sync) with pinned host buffers; two device objects alternate frames (double buffering)"}
-            for lane in lanes[1:]:
-                lane[1].close()
-                lane[0].close()
-        extras = None
-        if world == 1 and not args.no_extras:
-            extras = secondary_configs(dev, torch)
         cpu = None
         if world == 1 and not args.no_cpu:
             build.build_oracle()
-            t_cpu, st_cpu = oracle_draw_seconds(scene, repeats=3)
+            threads = max(1, len(os.sched_getaffinity(0)))
+            scene, factor, what = cpu_sample(work, threads)
+            t_cpu, cov_cpu = oracle_draw_seconds(scene, threads, repeats=3 if work.key == "c3" else 1)
+            t_one, _ = oracle_draw_seconds(scene, 1)
             model, ncpu = cpu_info()
-            cpu = {"value": prims / t_cpu / 1e6, "unit": "Mtris/s", "cores": 1, "kind": "port",
-                   "sample": "full C3/M1 draw, draw only, median of 3; %s, %d logical CPUs; optimistic stand-in for the reference ICD (no JIT/indirection overhead)" % (model, ncpu),
-                   "fragments_match_gpu": int(st_cpu.fragmentsCovered) == n_cov}
+            cpu = {"value": work.units(int(cov_cpu * factor)) / (t_cpu * factor) / work.scale, "unit": work.unit, "cores": threads, "kind": "port",
+                   "sample": "%s, median of runs, %d threads (one horizontal window each); one thread: %.3f %s; %s, %d logical CPUs; optimistic stand-in "
+                             "for the reference ICD (no JIT / indirection overhead)" % (what, threads, work.units(int(cov_cpu * factor)) / (t_one * factor) / work.scale, work.unit, model, ncpu),
+                   "fragments_match_gpu": int(cov_cpu * factor) == m["n_cov"]}
+        icd = icd_leg(work.scene) if (world == 1 and work.key == "c3" and not args.no_extras) else None
+        exchange = ""
+        if world > 1:
+            exchange = " + bands stored by k_raster over NVLink into %s + 4-byte NCCL all-reduce" % ("every GPU's frame" if args.gather == "all" else "the presenting GPU's frame (rank 0)")
+        blocks = m["blocks"]
         line = {
-            "metric": "Mtris/s (vkCmdDrawIndexed, 1M triangles at 3840x2160, D32 depth test, opaque)", "value": prims / (ms_step * 1e-3) / 1e6, "unit": "Mtris/s",
+            "metric": work.metric, "value": work.units(m["n_cov"]) / (ms_step * 1e-3) / work.scale, "unit": work.unit,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3/M1: 1,000,000-triangle indexed grid, 3840x2160 RGBA8+D32, LESS_OR_EQUAL, opaque; step = clear + draw" +
-                                   ((" + bands stored into the peers' frames by k_raster over NVLink (fused gather) + barrier" if symm is not None else " + NCCL all-gather of %d bands" % world) if world > 1 else ""),
-                       "parallelism": "sort-first bands x%d" % world,
-                       "l2": "working set (indices 12 MB + vertices 16 MB + shaded vertices 16 MB + setup records 104 MB + tile lists 5 MB + targets 66 MB) exceeds the 126 MB L2; no explicit flush",
-                       "cpu_affinity": affinity},
-            "gfragments_per_s": n_cov / (ms_step * 1e-3) / 1e9, "ms_per_frame": ms_step,
-            "fragments_covered": n_cov, "fragments_written": n_pass, "bin_entries_rank0": bin_entries,
-            "kernel_ms_rank0": {"vertex": statistics.mean(vs), "setup": statistics.mean(su), "bin": statistics.mean(bn), "raster": ms_raster},
+            "config": {"workload": work.workload + exchange, "parallelism": "sort-first bands of tile rows x%d" % world, "l2": work.l2, "cpu_affinity": affinity},
+            "blocks": {"count": len(blocks), "frames_timed": len(blocks) * args.steps, "seconds_timed": sum(blocks) / 1e3,
+                       "ms_per_step_min": min(blocks) / args.steps, "ms_per_step_median": ms_step, "ms_per_step_max": max(blocks) / args.steps},
+            "mtris_per_s": work.prims / (ms_step * 1e-3) / 1e6, "gfragments_per_s": m["n_cov"] / (ms_step * 1e-3) / 1e9, "ms_per_frame": ms_step,
+            "fragments_covered": m["n_cov"], "fragments_written": m["n_pass"], "bin_entries_rank0": m["bin_entries"],
+            "kernel_ms_rank0": m["kernel_ms"],
             "roofline": {"bound": "hbm", "kernel": "cpvk_k_raster", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "traffic": raster_traffic(),
-                         "note": "front end of C3/M1 is instruction-bound (8 px/triangle); see DESIGN.md"},
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "traffic": raster_traffic(work, world),
+                         "note": "rank 0's launch; C3/M1 (8 px per triangle) is instruction-bound, C4 fragment-stage bound; see DESIGN.md §6"},
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(round(m["launches_per_step"] * args.steps)),
+            "gpu_launches_per_step": m["launches_per_step"],
         }
+        if icd:
+            line["icd"] = icd
+            if "ms_per_frame_icd" in icd:
+                line["ms_per_frame_icd"] = icd["ms_per_frame_icd"]
         if extras:
             line["other_configs"] = extras
-    sod.close()
-    dev.close()
+    rig.close()
     if world > 1:
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
-def raster_traffic():
-    """DRAM bytes of one cpvk_k_raster launch from the committed `ncu --set full` capture (never measured inside a bench run)."""
+def raster_traffic(work, world):
+    """DRAM bytes of one cpvk_k_raster launch from the committed `ncu --set full` capture of this very command — only when that
+    capture was taken on the same workload and GPU count; never measured inside a bench run, null otherwise."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "raster_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "raster_traffic.json")) as f:
             t = json.load(f)
+        if t.get("workload") != work.key or int(t.get("n_gpus", 1)) != world:
+            return None
         return t["dram_bytes_read"] + t["dram_bytes_write"]
     except (OSError, KeyError, ValueError):
         return None
 
 
-def secondary_configs(dev, torch):
-    """Short measurements of the other BASELINE configs on the same device (reduced so the default run stays short):
-    C4 = blended, LINEAR-filtered full-screen quads at 7680x4320 RGBA16F (40 of the 2,000 quads);
-    C5 = vkCmdBlitImage / vkCmdCopyImage at 7680x4320. CUDA events on the launching stream, inputs resident."""
-    from cpvulkan_b200 import capi
-    from cpvulkan_b200.device import SceneOnDevice
+def secondary_configs(args, torch, dist, stream, local, rank, world, main_rig):
+    """Short measurements of the other BASELINE configs: C4 (a slice of its 2,000 quads, the whole 8K frame) on EVERY N with the
+    same band split and exchange as the headline; C5 (vkCmdBlitImage / vkCmdCopyImage at 7680x4320) on one GPU. CUDA events on
+    the launching stream, inputs resident. All ranks take part; rank 0 returns the dict."""
     peak, _ = measured_peaks()
     out = {}
+    if args.config == "c3":
+        quads = 100
+        w4 = Workload("c4", quads=quads)
+        rig = Rig(w4, torch, dist, stream, local, rank, world, args.gather)
+        if world > 1:
+            verify_exchange(rig)
+        m = measure_short(rig, reps=3)
+        rig.close()
+        out["C4_overdraw"] = {"workload": w4.workload + " (%d of the 2,000 quads; cost is linear in quads)" % quads, "n_gpus": world,
+                              "ms_per_step": m["ms"], "gfragments_per_s": m["n_cov"] / (m["ms"] * 1e-3) / 1e9, "mtris_per_s": 2 * quads / (m["ms"] * 1e-3) / 1e6,
+                              "ms_per_frame_at_2000_quads": m["ms"] * 2000 / quads,
+                              "roofline_frac_whole_job": m["n_cov"] * 16 / (m["ms"] * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes_per_fragment": 16}
+    if world > 1 or rank != 0:
+        return out if rank == 0 else None
+    dev = main_rig.dev
 
     def timed(fn, reps):
         for _ in range(2):
@@ -536,19 +714,6 @@ def secondary_configs(dev, torch):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    quads = 40
-    sc = scenes.overdraw_quads(width=7680, height=4320, quads=quads, tex_size=1024)
-    s = SceneOnDevice(dev, sc)
-    dev.set_stats(True)
-    s.render()
-    frags = int(dev.stats().fragmentsCovered)
-    dev.set_stats(False)
-    ms = timed(s.render, 3)
-    out["C4_overdraw"] = {"workload": "%d of the 2,000 alpha-blended LINEAR-textured full-screen quads, 7680x4320 RGBA16F; step = clear + draw" % quads,
-                          "ms_per_step": ms, "gfragments_per_s": frags / (ms * 1e-3) / 1e9, "mtris_per_s": 2 * quads / (ms * 1e-3) / 1e6,
-                          "roofline_frac": frags * 16 / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_fragment": 16}
-    s.close()
-
     W, H = 7680, 4320
 
     def image(fmt, w, h, texel):
@@ -558,15 +723,34 @@ def secondary_configs(dev, torch):
     s8, a8 = image(37, W, H, 4)
     d16, a16 = image(97, W, H, 8)
     s4, a4 = image(37, W // 2, H // 2, 4)
+    s4h, a4h = image(97, W // 2, H // 2, 8)
     d8, _ = image(37, W, H, 4)
     b1 = capi.Blit(a8, a16, 0, 0, W, H, 0, 0, W, H, 0)
     b2 = capi.Blit(a4, a16, 0, 0, W // 2, H // 2, 0, 0, W, H, 1)
+    b3 = capi.Blit(a4h, a16, 0, 0, W // 2, H // 2, 0, 0, W, H, 1)
     for key, fn, nbytes in (("blit_8k_rgba8_to_rgba16f_nearest", lambda: dev.blit(b1), W * H * 12),
-                            ("blit_4k_to_8k_rgba16f_linear", lambda: dev.blit(b2), W * H * 8 + W * H),
+                            ("blit_4k_rgba8_to_8k_rgba16f_linear", lambda: dev.blit(b2), W * H * 8 + W * H),
+                            ("blit_4k_to_8k_rgba16f_linear", lambda: dev.blit(b3), W * H * 8 + W * H * 2),
                             ("copy_image_8k_rgba8", lambda: dev.copy_rows(d8.data_ptr(), W * 4, s8.data_ptr(), W * 4, W * 4, H), W * H * 8)):
-        ms = timed(fn, 5)
+        ms = timed(fn, 10)
         out["C5_" + key] = {"ms": ms, "GBps": nbytes / ms / 1e6, "roofline_frac": nbytes / ms / 1e6 / peak, "algorithmic_bytes": nbytes}
     return out
+
+
+def measure_short(rig, reps):
+    torch, dist, world = rig.torch, rig.dist, rig.world
+    for _ in range(2):
+        rig.frame()
+    torch.cuda.synchronize()
+    st = rig.dev.stats()
+    n_cov = int(st.fragmentsCovered)
+    if world > 1:
+        t = torch.tensor([n_cov], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        n_cov = int(t[0])
+    rig.dev.set_stats(False)
+    blocks = timed_blocks(torch, dist, world, rig.frame, reps, min_seconds=0.0, min_frames=reps, min_blocks=3, max_blocks=3)
+    return {"ms": statistics.median(blocks) / reps, "n_cov": n_cov}
 
 
 _RESULT_OUT = sys.stdout
@@ -578,9 +762,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c4"], help="c3 (default): the 1M-triangle 4K draw; c4: all 2,000 blended quads at 8K")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU exchange: peer stores from k_raster (default) or an NCCL all-gather after the draw")
-    ap.add_argument("--no-extras", action="store_true", help="skip the short C4 / C5 measurements reported under other_configs")
+    ap.add_argument("--gather", default="one", choices=["one", "all"], help="multi-GPU exchange target of k_raster's peer stores: the presenting GPU (rank 0) or every GPU")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short C4 / C5 measurements (other_configs) and the ICD leg")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON record: whatever libraries print to file descriptor 1 on the way (NCCL's
     # version banner under torchrun, for one) is sent to stderr instead

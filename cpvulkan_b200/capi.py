@@ -156,6 +156,7 @@ ABI_SYMBOLS = [
     "cpvk_cuda_launch_count", "cpvk_cuda_clear", "cpvk_cuda_copy_rows", "cpvk_cuda_blit",
     "cpvk_cuda_flush", "cpvk_cuda_device_set_lazy_clear", "cpvk_cuda_device_set_speculation", "cpvk_cuda_mem_download_async",
     "cpvk_cuda_abi_sizeof",
+    "cpvk_cuda_device_create_group", "cpvk_cuda_group_size", "cpvk_cuda_gather", "cpvk_cuda_mem_export", "cpvk_cuda_mem_import", "cpvk_cuda_mem_unimport",
 ]
 
 
@@ -215,6 +216,13 @@ def load_cuda():
     lib.cpvk_cuda_blit.argtypes = [vp, C.POINTER(Blit)]
     lib.cpvk_cuda_abi_sizeof.argtypes = [C.c_char_p]
     lib.cpvk_cuda_abi_sizeof.restype = C.c_size_t
+    lib.cpvk_cuda_device_create_group.argtypes = [C.POINTER(C.c_int), u32, pvp]
+    lib.cpvk_cuda_group_size.argtypes = [vp]
+    lib.cpvk_cuda_group_size.restype = u32
+    lib.cpvk_cuda_gather.argtypes = [vp, C.POINTER(Attachment), u32]
+    lib.cpvk_cuda_mem_export.argtypes = [vp, u64, vp]
+    lib.cpvk_cuda_mem_import.argtypes = [vp, vp, C.POINTER(u64)]
+    lib.cpvk_cuda_mem_unimport.argtypes = [vp, u64]
     _cuda_lib = lib
     return lib
 

@@ -21,10 +21,15 @@ def _check(lib, rc):
 
 
 class Device:
-    def __init__(self, ordinal=0, stream=None, stats=True, timing=False):
+    def __init__(self, ordinal=0, stream=None, stats=True, timing=False, group=None):
+        """group = list of CUDA ordinals: one handle driving several GPUs of the box (cpvk_cuda_device_create_group)."""
         self.lib = capi.load_cuda()
         self.handle = C.c_void_p()
-        _check(self.lib, self.lib.cpvk_cuda_device_create(ordinal, C.byref(self.handle)))
+        if group is not None:
+            ords = (C.c_int * len(group))(*group)
+            _check(self.lib, self.lib.cpvk_cuda_device_create_group(ords, len(group), C.byref(self.handle)))
+        else:
+            _check(self.lib, self.lib.cpvk_cuda_device_create(ordinal, C.byref(self.handle)))
         if stream is not None:
             _check(self.lib, self.lib.cpvk_cuda_device_set_stream(self.handle, C.c_void_p(stream)))
         _check(self.lib, self.lib.cpvk_cuda_device_set_stats(self.handle, int(stats)))
@@ -118,6 +123,28 @@ class Device:
     def blit(self, blit):
         _check(self.lib, self.lib.cpvk_cuda_blit(self.handle, C.byref(blit)))
 
+    def gather(self, attachments):
+        """After the draws of a pass on a group: exchange the members' bands of these images (no-op on a plain device)."""
+        arr = (capi.Attachment * len(attachments))(*attachments)
+        _check(self.lib, self.lib.cpvk_cuda_gather(self.handle, arr, len(attachments)))
+
+    def group_size(self):
+        return int(self.lib.cpvk_cuda_group_size(self.handle))
+
+    def export_handle(self, addr):
+        h = (C.c_uint8 * 64)()
+        _check(self.lib, self.lib.cpvk_cuda_mem_export(self.handle, addr, h))
+        return bytes(h)
+
+    def import_handle(self, handle):
+        out = C.c_uint64()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        _check(self.lib, self.lib.cpvk_cuda_mem_import(self.handle, buf, C.byref(out)))
+        return out.value
+
+    def unimport(self, addr):
+        _check(self.lib, self.lib.cpvk_cuda_mem_unimport(self.handle, addr))
+
     def launch_count(self):
         return int(self.lib.cpvk_cuda_launch_count(self.handle))
 
@@ -159,6 +186,12 @@ class SceneOnDevice:
     def render(self):
         self.clear()
         self.draw()
+        self.gather()
+
+    def gather(self):
+        """Group devices: bring every member's band of the attachments to every replica (no-op on one GPU)."""
+        atts = [a for img, a in ((self.scene.color, self.m.color_attachment), (self.scene.depth, self.m.depth_attachment)) if img is not None]
+        self.dev.gather(atts)
 
     def read_color(self):
         return self.dev.download(self.m.addr["color"], self.scene.color.nbytes)

@@ -176,6 +176,19 @@ void ExecBeginRenderPass(Device& d, RenderPass* rp, Framebuffer* fb, const std::
     }
 }
 
+// Several GPUs behind one VkDevice (CPVK_CUDA_DEVICES): each renders its sort-first band of the attachments; when a subpass
+// ends, the bands are exchanged over NVLink so that every GPU's replica of every attachment is whole again for whatever
+// reads it next (the next subpass's input attachments, a copy, a blit, a sampled read, the host). No-op on one GPU.
+void GatherSubpassAttachments(Device& d) {
+    DeviceState& s = d.state;
+    if (!s.renderPass || !s.framebuffer || cpvk_cuda_group_size(d.cuda) < 2) return;
+    const Subpass& sp = s.renderPass->subpasses[s.subpass];
+    std::vector<CpvkAttachment> atts;
+    for (const VkAttachmentReference& ref : sp.color) if (ref.attachment != VK_ATTACHMENT_UNUSED) atts.push_back(AttachmentOf(s.framebuffer->views[ref.attachment]));
+    if (sp.depthStencil.attachment != VK_ATTACHMENT_UNUSED) atts.push_back(AttachmentOf(s.framebuffer->views[sp.depthStencil.attachment]));
+    if (!atts.empty()) CU_CHECK(cpvk_cuda_gather(d.cuda, atts.data(), (uint32_t)atts.size()));
+}
+
 void FillDescriptor(CpvkDescriptor& out, uint32_t set, uint32_t binding, uint32_t element, const DescriptorValue& v, uint32_t dynamicOffset) { // LoadUniforms, Draw.cpp:356-408
     memset(&out, 0, sizeof out);
     out.set = set; out.binding = binding; out.arrayElement = element;
@@ -345,8 +358,14 @@ VKFN(VkResult) CreateDevice(VkPhysicalDevice, const VkDeviceCreateInfo*, const V
     auto* dev = new Dispatchable<Device>();
     int ordinal = 0;
     if (const char* e = getenv("CPVK_CUDA_DEVICE")) ordinal = atoi(e);
-    if (cpvk_cuda_device_create(ordinal, &dev->obj.cuda) != 0) { fprintf(stderr, "CPVulkan_b200: %s\n", cpvk_cuda_last_error()); delete dev; return VK_ERROR_INITIALIZATION_FAILED; }
-    if (const char* b = getenv("CPVK_BAND")) { unsigned r = 0, w = 1, h = 0; if (sscanf(b, "%u/%u/%u", &r, &w, &h) == 3 && w > 0 && r < w) { dev->obj.bandY0 = r * (h / w); dev->obj.bandY1 = (r + 1 == w) ? h : (r + 1) * (h / w); } }
+    // CPVK_CUDA_DEVICES=0,1,...: one VkDevice over several GPUs of the box — the group (peer access between all of them) is set up
+    // here, at vkCreateDevice, where the reference accepts and ignores device groups (Queue.cpp:27-29)
+    std::vector<int> ordinals;
+    if (const char* e = getenv("CPVK_CUDA_DEVICES")) { for (const char* q = e; *q;) { char* end; const long v = strtol(q, &end, 10); if (end == q) break; ordinals.push_back((int)v); q = *end == ',' ? end + 1 : end; } }
+    const int rc = ordinals.size() > 1 ? cpvk_cuda_device_create_group(ordinals.data(), (uint32_t)ordinals.size(), &dev->obj.cuda)
+                                       : cpvk_cuda_device_create(ordinals.size() == 1 ? ordinals[0] : ordinal, &dev->obj.cuda);
+    if (rc != 0) { fprintf(stderr, "CPVulkan_b200: %s\n", cpvk_cuda_last_error()); delete dev; return VK_ERROR_INITIALIZATION_FAILED; }
+    if (const char* b = ordinals.size() > 1 ? nullptr : getenv("CPVK_BAND")) { unsigned r = 0, w = 1, h = 0; if (sscanf(b, "%u/%u/%u", &r, &w, &h) == 3 && w > 0 && r < w) { dev->obj.bandY0 = r * (h / w); dev->obj.bandY1 = (r + 1 == w) ? h : (r + 1) * (h / w); } }
     dev->obj.queue = new Dispatchable<Queue>();
     dev->obj.queue->obj.device = &dev->obj;
     *pDevice = Wrap<VkDevice>(dev);
@@ -673,8 +692,8 @@ VKFN(void) CmdBeginRenderPass(VkCommandBuffer cb, const VkRenderPassBeginInfo* i
     for (uint32_t i = 0; i < info->clearValueCount && i < clears.size(); i++) clears[i] = info->pClearValues[i];
     RECORD(cb)([rp, fb, clears](Device& d) { ExecBeginRenderPass(d, rp, fb, clears); });
 }
-VKFN(void) CmdNextSubpass(VkCommandBuffer cb, VkSubpassContents) { RECORD(cb)([](Device& d) { d.state.subpass++; }); }
-VKFN(void) CmdEndRenderPass(VkCommandBuffer cb) { RECORD(cb)([](Device& d) { d.state.renderPass = nullptr; d.state.framebuffer = nullptr; }); }
+VKFN(void) CmdNextSubpass(VkCommandBuffer cb, VkSubpassContents) { RECORD(cb)([](Device& d) { GatherSubpassAttachments(d); d.state.subpass++; }); }
+VKFN(void) CmdEndRenderPass(VkCommandBuffer cb) { RECORD(cb)([](Device& d) { GatherSubpassAttachments(d); d.state.renderPass = nullptr; d.state.framebuffer = nullptr; }); }
 VKFN(void) CmdDraw(VkCommandBuffer cb, uint32_t vertexCount, uint32_t instanceCount, uint32_t firstVertex, uint32_t firstInstance) { // Draw.cpp:2350-2354
     RECORD(cb)([=](Device& d) { ExecDraw(d, vertexCount, instanceCount, firstVertex, 0, firstInstance, false); });
 }

@@ -298,6 +298,26 @@ int cpvk_cuda_flush(CpvkDevice* device);
 int cpvk_cuda_device_set_speculation(CpvkDevice* device, int enable);
 int cpvk_cuda_device_set_lazy_clear(CpvkDevice* device, int enable);
 
+/* ---- multi-GPU (the reference's hook is the device-group plumbing it accepts and ignores, Queue.cpp:27-29, :52-74) ----
+   One process, one handle, N GPUs of one box. cpvk_cuda_device_create_group returns the LEADER device; every entry point of
+   this header accepts it and fans out: allocations exist on every member (the leader's address is the handle), uploads,
+   clears, copies and blits run on every member (replicated resources, one PCIe link each), cpvk_cuda_draw renders one
+   sort-first band of tile rows per member (vertex work replicated), and cpvk_cuda_gather copies every member's band of the
+   named images into every other member's replica over NVLink (peer copies ordered by events), after which all replicas hold
+   the whole images again. Between a draw and its gather only the member's own band of the attachments is defined.
+   Downloads read the leader's replica. CPVK_GROUP_SERIAL=1 enqueues the members one after the other from the calling thread
+   instead of from one worker thread per member. A group runs on its members' own streams (set_stream is refused). An ordinal
+   may be listed more than once: each occurrence is a member of its own (replicas, stream, band) on that GPU. */
+int cpvk_cuda_device_create_group(const int* ordinals, uint32_t count, CpvkDevice** out);
+uint32_t cpvk_cuda_group_size(const CpvkDevice* device); /* 1 for a plain device */
+int cpvk_cuda_gather(CpvkDevice* device, const CpvkAttachment* images, uint32_t count); /* no-op on a plain device */
+/* One process per GPU (torchrun): whole allocations made by cpvk_cuda_mem_alloc can be mapped into another process's device
+   (cudaIpc): export fills a 64-byte handle, import returns the address in the importing process, to be used as a
+   CpvkDrawState.mirrorColor0[] target. */
+int cpvk_cuda_mem_export(CpvkDevice* device, uint64_t dev, void* handle64);
+int cpvk_cuda_mem_import(CpvkDevice* device, const void* handle64, uint64_t* outDev);
+int cpvk_cuda_mem_unimport(CpvkDevice* device, uint64_t dev);
+
 /* vkCmdCopyImage / CopyBufferToImage / CopyImageToBuffer: raw row memcpy (CommandBuffer.Copy.cpp:77-200). */
 int cpvk_cuda_copy_rows(CpvkDevice* device, uint64_t dst, uint32_t dstPitch, uint64_t src, uint32_t srcPitch,
                         uint32_t rowBytes, uint32_t rows);
