@@ -15,7 +15,8 @@ handles exchanged with torch.distributed; a 4-byte NCCL all-reduce on the draw s
 Scaling is strong (fixed frame).
 
 Timing: the K steps asked for are one block, bracketed by barrier + synchronize and timed with CUDA events on the launching
-stream; blocks are repeated until at least 0.5 s and 200 frames have been timed (>= 5 blocks), and `value` comes from the
+stream; blocks are repeated until at least 0.5 s and 200 frames have been timed (>= 5 blocks; a workload whose frames take
+seconds stops after 5 blocks), and `value` comes from the
 MEDIAN block (max over ranks per block), so a scheduling hiccup in one block does not move the headline.
 
 One JSON line on stdout (rank 0). Keys beyond the base contract: roofline, cpu_baseline, e2e, clocks, gpu_launches, icd,
@@ -332,7 +333,7 @@ class Rig:
         self.dev.close()
 
 
-def timed_blocks(torch, dist, world, frame, steps, min_seconds=0.5, min_frames=200, min_blocks=5, max_blocks=400):
+def timed_blocks(torch, dist, world, frame, steps, min_seconds=0.5, min_frames=200, min_blocks=5, max_blocks=400, enough_seconds=3.0):
     """Blocks of exactly `steps` frames, each bracketed by barrier + synchronize and timed with CUDA events on the current
     stream; per block the max over ranks. Returns the list of block times in ms."""
     def barrier():
@@ -341,7 +342,8 @@ def timed_blocks(torch, dist, world, frame, steps, min_seconds=0.5, min_frames=2
         torch.cuda.synchronize()
 
     blocks, total_ms, frames = [], 0.0, 0
-    while len(blocks) < max_blocks and (len(blocks) < min_blocks or total_ms < min_seconds * 1e3 or frames < min_frames):
+    # at least min_blocks blocks and min_seconds; then on until min_frames frames, unless enough_seconds have been timed already
+    while len(blocks) < max_blocks and (len(blocks) < min_blocks or total_ms < min_seconds * 1e3 or (frames < min_frames and total_ms < enough_seconds * 1e3)):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -55,10 +55,8 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
     float P[3][4];
     #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const uint4 pv = __ldg(a.vsPos + idx[k]);
-        const float pos[4] = {__uint_as_float(pv.x), __uint_as_float(pv.y), __uint_as_float(pv.z), __uint_as_float(pv.w)};
-        P[k][0] = pos[0] / pos[3]; P[k][1] = pos[1] / pos[3]; P[k][2] = pos[2] / pos[3]; // glm vec4 / scalar
-        P[k][3] = pos[3];                                                                 // Draw.cpp:1544-1546
+        const uint4 pv = __ldg(a.vsPos + idx[k]); // already position / position.w with .w = position.w (cpvk_store_position; Draw.cpp:1541-1546)
+        P[k][0] = __uint_as_float(pv.x); P[k][1] = __uint_as_float(pv.y); P[k][2] = __uint_as_float(pv.z); P[k][3] = __uint_as_float(pv.w);
     }
     const float W = a.vpWidth, H = a.vpHeight;
     int sx[3], sy[3];
@@ -431,6 +429,20 @@ __global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
     }
 }
 
+// Diagnostics: cpvk_div_shared (cpvk_device.cuh) on caller-supplied operands, three numerators per denominator, next to the
+// plain operator — tests/test_parity_gpu.py compares both with IEEE division computed on the host over every exponent range.
+__global__ void __launch_bounds__(256) k_selftest_div(const float* a, const float* b, cpvk_u32 n, float* shared, float* plain) {
+    const cpvk_u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v[3] = {a[3 * i], a[3 * i + 1], a[3 * i + 2]};
+    const float d = b[i];
+    #pragma unroll
+    for (int k = 0; k < 3; k++) plain[3 * i + k] = v[k] / d;
+    cpvk_div_shared(v, d);
+    #pragma unroll
+    for (int k = 0; k < 3; k++) shared[3 * i + k] = v[k];
+}
+
 // ---- host-callable launchers (cpvk_abi.cpp is plain C++) ----
 static inline unsigned cpvk_grid(unsigned long long n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
@@ -475,6 +487,11 @@ cudaError_t cpvk_launch_copy_rows(unsigned long long dst, unsigned dstPitch, uns
     unsigned grid = cpvk_grid((unsigned long long)rowBytes * rows / 16 + 1, 256);
     if (grid > 148 * 16) grid = 148 * 16;
     k_copy_rows<<<grid, 256, 0, s>>>((cpvk_u8*)dst, dstPitch, (const cpvk_u8*)src, srcPitch, rowBytes, rows);
+    return cudaGetLastError();
+}
+cudaError_t cpvk_launch_selftest_div(const float* a, const float* b, unsigned n, float* shared, float* plain, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    k_selftest_div<<<cpvk_grid(n, 256), 256, 0, s>>>(a, b, n, shared, plain);
     return cudaGetLastError();
 }
 cudaError_t cpvk_launch_blit(const CpvkBlitArgs* b, cudaStream_t s) {

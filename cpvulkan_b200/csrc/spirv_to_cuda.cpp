@@ -541,7 +541,7 @@ private:
             }
             if (positionVar) for (int q = 0; q < 4; q++) pos[q] = "g" + std::to_string(positionVar) + "[" + std::to_string(q) + "]";
             if (pointSizeVar) psz = "g" + std::to_string(pointSizeVar) + "[0]";
-            body << "  dp->vsPos[rawId] = make_uint4(" << pos[0] << ", " << pos[1] << ", " << pos[2] << ", " << pos[3] << ");\n";
+            body << "  cpvk_store_position(dp, rawId, " << pos[0] << ", " << pos[1] << ", " << pos[2] << ", " << pos[3] << ");\n";
             if (desc.topology == 0) body << "  dp->vsPointSize[rawId] = " << psz << ";\n"; // point lists read the size back (Draw.cpp:1345)
             (void)clip; // clip distances have no consumer (no clipping)
             uint32_t byteOff = 24;

@@ -171,6 +171,15 @@ __device__ __forceinline__ void cpvk_tile_copy(cpvk_u8* dst, cpvk_u32 dstPitch, 
 
 // Fill a whole 32x32 shared-memory tile with one packed texel (texel size is a compile-time constant per pipeline).
 CPVK_DEV void cpvk_tile_fill(cpvk_u8* dst, cpvk_u32 texel, const cpvk_u8* one) {
+    if (texel == 4 || texel == 8 || texel == 2) { // 16-byte stores of the repeated texel: a 4 KB tile is one store per thread
+        uint4 v;
+        if (texel == 4) { const cpvk_u32 t = *reinterpret_cast<const cpvk_u32*>(one); v = make_uint4(t, t, t, t); }
+        else if (texel == 8) { const uint2 t = *reinterpret_cast<const uint2*>(one); v = make_uint4(t.x, t.y, t.x, t.y); }
+        else { const cpvk_u32 t = *reinterpret_cast<const unsigned short*>(one) * 0x10001u; v = make_uint4(t, t, t, t); }
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        for (cpvk_u32 i = threadIdx.x; i < CPVK_TILE_W * CPVK_TILE_H * texel / 16; i += blockDim.x) d[i] = v;
+        return;
+    }
     for (cpvk_u32 i = threadIdx.x; i < CPVK_TILE_W * CPVK_TILE_H; i += blockDim.x) {
         cpvk_u8* d = dst + i * texel;
         if (texel == 16) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(one);
@@ -194,6 +203,9 @@ extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 // round trip (GlslFunctions.cpp:842-928) on shared memory, and HBM sees one read and one write per tile byte.
 #ifndef CPVK_COVER_ROWS
 #define CPVK_COVER_ROWS 5   /* rows of the coverage window evaluated per pass over its columns (measured on C3/M1: 2 -> 242 us, 4 -> 235, 5 -> 228, 6 -> 231, 8 -> 249 with spills) */
+#endif
+#ifndef CPVK_ORDER_BITS
+#define CPVK_ORDER_BITS (128 * CPVK_RASTER_THREADS) /* width of the id window the in-tile bitmap ordering covers: 128 bits per thread */
 #endif
 #ifndef CPVK_COVER_UNROLL
 #define CPVK_COVER_UNROLL 1
@@ -309,7 +321,16 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                             + warp * CPVK_FRAG_CAP;                                                  // [warps][CPVK_FRAG_CAP]
     cpvk_u32* sSorted = reinterpret_cast<cpvk_u32*>(cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * CPVK_CHUNK); // [CPVK_CHUNK], aliases sFrag (idle until the chunk is staged)
     cpvk_u8* sMask = cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * (CPVK_CHUNK + CPVK_FRAG_CAP * 2); // [CPVK_CHUNK] warp regions a bbox meets
-    if (triangles && !listsSorted) reinterpret_cast<cpvk_u32*>(sBB)[threadIdx.x] = firstKey; // sKeys of the ranking pass
+    // Ordering scratch (aliases the setup planes, idle until the chunk is staged): a bitmap of the ids present in this tile's
+    // list relative to the lowest one, the warps' lowest / highest ids, the warps' bit counts.
+    cpvk_u32* sBits = reinterpret_cast<cpvk_u32*>(sQ);   // [CPVK_ORDER_BITS / 32]
+    cpvk_u32* sRange = sBits + CPVK_ORDER_BITS / 32;     // [0..8) lowest id per warp, [8..16) highest, [16..24) set bits per warp
+    if (triangles && !listsSorted) {
+        reinterpret_cast<cpvk_u32*>(sBB)[threadIdx.x] = firstKey; // sKeys of the ranking pass (fallback)
+        reinterpret_cast<uint4*>(sBits)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u); // CPVK_ORDER_BITS == 128 bits per thread
+        const cpvk_u32 mn = __reduce_min_sync(0xFFFFFFFFu, firstKey), mx = __reduce_max_sync(0xFFFFFFFFu, firstKey == 0xFFFFFFFFu ? 0u : firstKey);
+        if (lane == 0) { sRange[warp] = mn; sRange[8 + warp] = mx; }
+    }
     __syncthreads(); // tile, pixel centres, lut and the unsorted ids are staged
 
     // ---- the fragment wrapper epilogue (PipelineCompiler.cpp:1061-1080) on the shared tile; returns "colour written" ----
@@ -403,7 +424,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             const uint4 q3 = sQ[3 * CPVK_CHUNK + kt], q4 = sQ[4 * CPVK_CHUNK + kt], q5 = sQ[5 * CPVK_CHUNK + kt];
             const float area = __uint_as_float(q3.w);
             CpvkFragCtx ctx;
-            w0 /= area; w1 /= area; w2 /= area;                                                   // Draw.cpp:905-907
+            { float w[3] = {w0, w1, w2}; cpvk_div_shared(w, area); w0 = w[0]; w1 = w[1]; w2 = w[2]; } // w /= area (Draw.cpp:905-907), one reciprocal for the three
             const float depth = __uint_as_float(q3.x) * w0 + __uint_as_float(q3.y) * w1 + __uint_as_float(q3.z) * w2; // Draw.cpp:909
             ctx.w[0] = w0; ctx.w[1] = w1; ctx.w[2] = w2;
             ctx.pw[0] = __uint_as_float(q4.x); ctx.pw[1] = __uint_as_float(q4.y); ctx.pw[2] = __uint_as_float(q4.z);
@@ -411,7 +432,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             {
                 float den = 0.0f; // dead code unless the shader has a perspective-interpolated input
                 if (ctx.unitW) { den += w0; den += w1; den += w2; }
-                else { den += w0 / ctx.pw[0]; den += w1 / ctx.pw[1]; den += w2 / ctx.pw[2]; }
+                else { den += w0 / ctx.pw[0]; den += w1 / ctx.pw[1]; den += w2 / ctx.pw[2]; } // (ptxas merges these reciprocals with the interpolation's when it can)
                 ctx.persDen = den;
             }
             front = (q4.w & 1u) != 0;
@@ -466,7 +487,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                     const cpvk_u32 s0 = slotOf(prim);
                     const uint4 pv = __ldg(p.vsPos + s0);
                     const float pw = __uint_as_float(pv.w);
-                    const float X = __uint_as_float(pv.x) / pw, Y = __uint_as_float(pv.y) / pw, Z = __uint_as_float(pv.z) / pw;
+                    const float X = __uint_as_float(pv.x), Y = __uint_as_float(pv.y), Z = __uint_as_float(pv.z); // stored divided by w (cpvk_store_position)
                     const float pointSize = __uint_as_float(__ldg(p.vsPointSize + s0));
                     const int sx = cpvk_cvtt((X + 1.0f) * 0.5f * (W - 1.0f)), sy = cpvk_cvtt((Y + 1.0f) * 0.5f * (H - 1.0f));
                     const int half = cpvk_cvtt(ceilf(pointSize / 2.0f));
@@ -478,8 +499,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                     const cpvk_u32 s0 = slotOf(i0), s1 = slotOf(i0 + 1u);
                     const uint4 v0 = __ldg(p.vsPos + s0), v1 = __ldg(p.vsPos + s1);
                     const float w0 = __uint_as_float(v0.w), w1 = __uint_as_float(v1.w);
-                    const float P0[4] = {__uint_as_float(v0.x) / w0, __uint_as_float(v0.y) / w0, __uint_as_float(v0.z) / w0, w0};
-                    const float P1[4] = {__uint_as_float(v1.x) / w1, __uint_as_float(v1.y) / w1, __uint_as_float(v1.z) / w1, w1};
+                    const float P0[4] = {__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), w0}; // stored divided by w (cpvk_store_position)
+                    const float P1[4] = {__uint_as_float(v1.x), __uint_as_float(v1.y), __uint_as_float(v1.z), w1};
                     const float lw = cpvk_spec_f32(6);
                     const float lwx = lw / W, lwy = lw / H;
                     const float d0 = P1[0] - P0[0], d1 = P1[1] - P0[1], d2 = P1[2] - P0[2], d3 = P1[3] - P0[3];
@@ -575,21 +596,52 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     for (cpvk_u32 chunkBase = listBegin; triangles && chunkBase < listEnd; chunkBase += CPVK_CHUNK) {
         const int n = (int)min((cpvk_u32)CPVK_CHUNK, listEnd - chunkBase);
         if (!listsSorted) {
-            // Binning claims list slots with atomics, so a tile's ids arrive in arbitrary order. When every list fits
-            // one chunk the host skips k_bin_sort and the tile orders its own list here: ids are unique, so each id's
-            // rank (number of smaller ids) is its position in API order. Broadcast shared-memory reads, no barriers
-            // inside the loop.
-            const cpvk_u32* sKeys = reinterpret_cast<const cpvk_u32*>(sBB);  // staged before the first barrier; reused before the bboxes are staged
-            const cpvk_u32 key = firstKey;
-            if ((int)threadIdx.x < n) {
-                cpvk_u32 rank = 0xFFFFFFFFu;
-                const uint4* k4 = reinterpret_cast<const uint4*>(sKeys);
-                // rank += (v <= key): the carry of key - v (set when there is no borrow, i.e. v <= key) is added straight
-                // into the rank, 1.5 instructions per key. The key itself is counted once, hence the start value -1.
-                #define CPVK_RANK_STEP(v) asm("{ .reg .u32 t; sub.cc.u32 t, %2, %1; addc.u32 %0, %0, 0; }" : "+r"(rank) : "r"(v), "r"(key))
-                for (int j = 0; j < (n + 3) / 4; j++) { const uint4 v = k4[j]; CPVK_RANK_STEP(v.x); CPVK_RANK_STEP(v.y); CPVK_RANK_STEP(v.z); CPVK_RANK_STEP(v.w); }
-                #undef CPVK_RANK_STEP
-                sSorted[rank] = key;
+            // Binning claims list slots with atomics, so a tile's ids arrive in arbitrary order. When every list fits one chunk
+            // the host skips k_bin_sort and the tile orders its own list here (ids are unique; ascending id = API order).
+            // Usual case — the ids of a tile lie within CPVK_ORDER_BITS of each other (any draw of fewer primitives, any mesh
+            // with some locality): every id sets its bit in a shared-memory bitmap, each thread counts the bits of its 128-bit
+            // slice, a block-wide prefix sum gives the slice's first position, and the slice's ids are written out in order:
+            // a few dozen instructions per thread instead of one compare per pair of ids.
+            const uint4 mnA = reinterpret_cast<const uint4*>(sRange)[0], mnB = reinterpret_cast<const uint4*>(sRange)[1];
+            const uint4 mxA = reinterpret_cast<const uint4*>(sRange)[2], mxB = reinterpret_cast<const uint4*>(sRange)[3];
+            const cpvk_u32 lo = min(min(min(mnA.x, mnA.y), min(mnA.z, mnA.w)), min(min(mnB.x, mnB.y), min(mnB.z, mnB.w)));
+            const cpvk_u32 hi = max(max(max(mxA.x, mxA.y), max(mxA.z, mxA.w)), max(max(mxB.x, mxB.y), max(mxB.z, mxB.w)));
+            if (hi - lo < (cpvk_u32)CPVK_ORDER_BITS) { // block-uniform
+                if (firstKey != 0xFFFFFFFFu) atomicOr(sBits + ((firstKey - lo) >> 5), 1u << ((firstKey - lo) & 31u));
+                __syncthreads();
+                const uint4 bits = reinterpret_cast<const uint4*>(sBits)[threadIdx.x];
+                const cpvk_u32 cnt = (cpvk_u32)(__popc(bits.x) + __popc(bits.y)) + (cpvk_u32)(__popc(bits.z) + __popc(bits.w));
+                cpvk_u32 incl = cnt;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const cpvk_u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
+                if (lane == 31) sRange[16 + warp] = incl;
+                __syncthreads();
+                if (cnt) {
+                    cpvk_u32 pos = incl - cnt;
+                    for (int q = 0; q < warp; q++) pos += sRange[16 + q];
+                    const cpvk_u32 w4[4] = {bits.x, bits.y, bits.z, bits.w};
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        cpvk_u32 m = w4[q];
+                        const cpvk_u32 idBase = lo + threadIdx.x * 128u + (cpvk_u32)q * 32u;
+                        while (m) { sSorted[pos++] = idBase + (cpvk_u32)__ffs((int)m) - 1u; m &= m - 1u; }
+                    }
+                }
+            } else {
+                // ids too far apart for the bitmap: each id's rank (number of ids <= it, minus one) is its position. Broadcast
+                // shared-memory reads, no barriers inside the loop.
+                const cpvk_u32* sKeys = reinterpret_cast<const cpvk_u32*>(sBB);  // staged before the first barrier; reused before the bboxes are staged
+                const cpvk_u32 key = firstKey;
+                if ((int)threadIdx.x < n) {
+                    cpvk_u32 rank = 0xFFFFFFFFu;
+                    const uint4* k4 = reinterpret_cast<const uint4*>(sKeys);
+                    // rank += (v <= key): the carry of key - v (set when there is no borrow, i.e. v <= key) is added straight
+                    // into the rank, 1.5 instructions per key. The key itself is counted once, hence the start value -1.
+                    #define CPVK_RANK_STEP(v) asm("{ .reg .u32 t; sub.cc.u32 t, %2, %1; addc.u32 %0, %0, 0; }" : "+r"(rank) : "r"(v), "r"(key))
+                    for (int j = 0; j < (n + 3) / 4; j++) { const uint4 v = k4[j]; CPVK_RANK_STEP(v.x); CPVK_RANK_STEP(v.y); CPVK_RANK_STEP(v.z); CPVK_RANK_STEP(v.w); }
+                    #undef CPVK_RANK_STEP
+                    sSorted[rank] = key;
+                }
             }
             __syncthreads();
         }

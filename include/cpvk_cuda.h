@@ -318,6 +318,11 @@ int cpvk_cuda_mem_export(CpvkDevice* device, uint64_t dev, void* handle64);
 int cpvk_cuda_mem_import(CpvkDevice* device, const void* handle64, uint64_t* outDev);
 int cpvk_cuda_mem_unimport(CpvkDevice* device, uint64_t dev);
 
+/* Diagnostics. The kernels divide several numerators by one denominator through one shared reciprocal (edge weights / area,
+   interpolated components / denominator, position / w), claiming the bits of the IEEE `/` operator: this runs both on device
+   arrays a[3 n], b[n] -> outShared[3 n], outPlain[3 n] so that a test can hold them to a host-side IEEE division. */
+int cpvk_cuda_selftest_div(CpvkDevice* device, uint64_t a, uint64_t b, uint32_t n, uint64_t outShared, uint64_t outPlain);
+
 /* vkCmdCopyImage / CopyBufferToImage / CopyImageToBuffer: raw row memcpy (CommandBuffer.Copy.cpp:77-200). */
 int cpvk_cuda_copy_rows(CpvkDevice* device, uint64_t dst, uint32_t dstPitch, uint64_t src, uint32_t srcPitch,
                         uint32_t rowBytes, uint32_t rows);

@@ -701,3 +701,44 @@ def test_vertex_and_instance_index_builtins(dev, kw):
         sc.buffers["ib"] = idx.view(np.uint8).reshape(-1)
         sc.index_buffer, sc.index_stride, sc.vertex_offset = "ib", 2, 0
     compare(dev, sc)
+
+
+def test_shared_reciprocal_division_is_ieee_division(dev):
+    """cpvk_div_shared (edge weights / area, interpolants / denominator, position / w share one reciprocal per denominator) must
+    return the bits of the `/` operator = IEEE-754 round-to-nearest-even division, which numpy computes on the host: random bit
+    patterns over every exponent (subnormals, zeros of both signs, infinities, NaNs), operands at the edges of the fast path's
+    exponent window, quotients that round to the subnormal / overflow boundaries, and mantissa patterns that are hard to round."""
+    rng = np.random.default_rng(2026)
+    n = 1 << 20
+    a = rng.integers(0, 1 << 32, size=(n, 3), dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+    # a second million with exponents packed around the fast-path window [2^-62, 2^63) and around 1
+    e = rng.choice(np.array([1, 2, 63, 64, 65, 66, 100, 126, 127, 128, 150, 188, 189, 190, 191, 253, 254], dtype=np.uint32), size=(n, 4))
+    m = rng.integers(0, 1 << 23, size=(n, 4), dtype=np.uint64).astype(np.uint32)
+    m[rng.random((n, 4)) < 0.15] = 0x7FFFFF
+    m[rng.random((n, 4)) < 0.15] = 0
+    sgn = rng.integers(0, 2, size=(n, 4), dtype=np.uint64).astype(np.uint32) << 31
+    packed = sgn | (e << 23) | m
+    a = np.concatenate([a, packed[:, :3]]); b = np.concatenate([b, packed[:, 3]])
+    special = np.array([0x00000000, 0x80000000, 0x7F800000, 0xFF800000, 0x7FC00000, 0x00000001, 0x807FFFFF, 0x00800000, 0x3F800000, 0xBF800000], dtype=np.uint32)
+    sa = np.array([[x, y, z] for x in special for y in special[:3] for z in special[-3:]], dtype=np.uint32)
+    a = np.concatenate([a, np.tile(sa, (len(special), 1))]); b = np.concatenate([b, np.repeat(special, len(sa))])
+    total = len(b)
+    with np.errstate(all="ignore"):
+        want = (a.view(np.float32) / b.view(np.float32)[:, None]).astype(np.float32).view(np.uint32)
+    da, db, ds, dp = dev.alloc(a.nbytes), dev.alloc(b.nbytes), dev.alloc(a.nbytes), dev.alloc(a.nbytes)
+    dev.upload(da, a); dev.upload(db, b)
+    from cpvulkan_b200.device import _check
+    _check(dev.lib, dev.lib.cpvk_cuda_selftest_div(dev.handle, da, db, total, ds, dp))
+    shared = dev.download(ds, a.nbytes).view(np.uint32).reshape(-1, 3)
+    plain = dev.download(dp, a.nbytes).view(np.uint32).reshape(-1, 3)
+    for x in (da, db, ds, dp):
+        dev.free(x)
+
+    def canon(v):
+        v = v.copy(); v[(v & 0x7FFFFFFF) > 0x7F800000] = 0x7FC00000
+        return v
+    assert np.array_equal(canon(plain), canon(want)), "the GPU's `/` is not IEEE division?"
+    bad = np.argwhere(canon(shared) != canon(want))
+    assert len(bad) == 0, "cpvk_div_shared differs from IEEE division in %d quotients, first: %08x / %08x -> %08x, want %08x" % (
+        len(bad), a[bad[0][0], bad[0][1]], b[bad[0][0]], shared[bad[0][0], bad[0][1]], want[bad[0][0], bad[0][1]])
