@@ -381,50 +381,93 @@ __device__ __forceinline__ CpvkBlitAxis cpvk_blit_axis(int i, int dst0, int dst1
     }
     return r;
 }
-__global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
-    __shared__ float lut[256]; // (float)k / 255.0f by the IEEE divide itself: exact UNORM8 decode without a divide per channel
+// Texel codecs of the blit, chosen at compile time for the formats render targets and textures mostly have (K8 = R8G8B8A8 / B8G8R8A8
+// UNORM, K16F = R16G16B16A16_SFLOAT); KDYN goes through the run-time format switch.
+enum { KDYN = 0, K8 = 1, K16F = 2 };
+template <int K> __device__ __forceinline__ void cpvk_blit_load(cpvk_u32 format, const cpvk_u8* p, float v[4], const float* lut) {
+    if (K == K8) {
+        const cpvk_u32 t = *reinterpret_cast<const cpvk_u32*>(p);
+        const float b0 = cpvk_unorm8(t & 0xFFu), b1 = cpvk_unorm8((t >> 8) & 0xFFu), b2 = cpvk_unorm8((t >> 16) & 0xFFu), b3 = cpvk_unorm8(t >> 24);
+        v[0] = format == 37 ? b0 : b2; v[1] = b1; v[2] = format == 37 ? b2 : b0; v[3] = b3;
+    } else if (K == K16F) {
+        cpvk_unpack_half4(*reinterpret_cast<const uint2*>(p), v);
+    } else cpvk_get_pixel_f32_dyn(format, p, v, lut);
+}
+__device__ __forceinline__ cpvk_u32 cpvk_blit_pack8(cpvk_u32 format, const float v[4]) {
+    const cpvk_u32 r = cpvk_float_to_unorm(v[0], 255.0f), g = cpvk_float_to_unorm(v[1], 255.0f), b = cpvk_float_to_unorm(v[2], 255.0f), a = cpvk_float_to_unorm(v[3], 255.0f);
+    return format == 37 ? (r | (g << 8) | (b << 16) | (a << 24)) : (b | (g << 8) | (r << 16) | (a << 24));
+}
+// Four destination columns per thread, CPVK_BLIT_ROWS rows per CTA: the per-column terms are computed once per thread, the per-row
+// terms once per CTA, and an aligned run of four destination texels leaves as one (K8) or two (K16F) 16-byte stores.
+template <int KS, int KD, int FILTER> __global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
+    __shared__ float lut[256]; // (float)k / 255.0f by the IEEE divide itself, for the run-time format path
     __shared__ CpvkBlitAxis rows[CPVK_BLIT_ROWS];
-    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    if (KS == KDYN) lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
     const int dstW = abs(b.dstX1 - b.dstX0), dstH = abs(b.dstY1 - b.dstY0);
     const cpvk_u32 stexel = cpvk_texel_size(b.src.format), dtexel = cpvk_texel_size(b.dst.format);
     const cpvk_u64 spitch = (cpvk_u64)stexel * b.src.width; // the sampler addresses a level as tightly packed rows (Formats.cpp:583-587)
     const cpvk_u8* src = reinterpret_cast<const cpvk_u8*>(b.src.address);
     const CpvkFormat fi = cpvk_format(b.src.format);
     const cpvk_u32 comps = fi.type == CPVK_FT_DEPTH ? 1u : fi.comps;
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    const bool colLive = x < dstW;
-    const CpvkBlitAxis cx = cpvk_blit_axis(colLive ? x : 0, b.dstX0, b.dstX1, b.srcX0, b.srcX1, b.src.width, b.filter);
+    const int x4 = (int)(blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    CpvkBlitAxis cx[4];
+    #pragma unroll
+    for (int k = 0; k < 4; k++) cx[k] = cpvk_blit_axis(x4 + k < dstW ? x4 + k : 0, b.dstX0, b.dstX1, b.srcX0, b.srcX1, b.src.width, FILTER);
     // the z axis: one destination "slice" 0, source slices [0, 1) of a depth-1 image
-    const CpvkBlitAxis cz = cpvk_blit_axis(0, 0, 1, 0, 1, 1u, b.filter);
+    const CpvkBlitAxis cz = cpvk_blit_axis(0, 0, 1, 0, 1, 1u, FILTER);
+    // the four columns form one aligned in-range run of the destination? (then vector stores)
+    const bool run = x4 + 3 < dstW && cx[0].dst >= 0 && (cpvk_u32)cx[3].dst < b.dst.width && cx[3].dst == cx[0].dst + 3 &&
+                     (KD == K8 || KD == K16F) && ((b.dst.address + (cpvk_u64)cx[0].dst * dtexel) & 15u) == 0u && (b.dst.rowPitch & 15u) == 0u;
     for (int rowBase = (int)blockIdx.y * CPVK_BLIT_ROWS; rowBase < dstH; rowBase += (int)gridDim.y * CPVK_BLIT_ROWS) {
         __syncthreads();
         if (threadIdx.x < CPVK_BLIT_ROWS && rowBase + (int)threadIdx.x < dstH)
-            rows[threadIdx.x] = cpvk_blit_axis(rowBase + (int)threadIdx.x, b.dstY0, b.dstY1, b.srcY0, b.srcY1, b.src.height, b.filter);
+            rows[threadIdx.x] = cpvk_blit_axis(rowBase + (int)threadIdx.x, b.dstY0, b.dstY1, b.srcY0, b.srcY1, b.src.height, FILTER);
         __syncthreads();
-        if (!colLive) continue;
+        if (x4 >= dstW) continue;
         const int nRows = min(CPVK_BLIT_ROWS, dstH - rowBase);
+        #pragma unroll 1
         for (int r = 0; r < nRows; r++) {
             const CpvkBlitAxis cy = rows[r];
-            CpvkVec4 value;
-            if (b.filter == 0) {
-                cpvk_get_pixel_f32_dyn(b.src.format, src + (cpvk_u64)(cpvk_u32)cy.c0 * spitch + (cpvk_u64)(cpvk_u32)cx.c0 * stexel, value.v, lut);
-            } else {
-                const cpvk_u8* r0 = src + (cpvk_u64)(cpvk_u32)cy.c0 * spitch;
-                const cpvk_u8* r1 = src + (cpvk_u64)(cpvk_u32)cy.c1 * spitch;
-                CpvkVec4 i0j0, i1j0, i0j1, i1j1;
-                cpvk_get_pixel_f32_dyn(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx.c0 * stexel, i0j0.v, lut);
-                cpvk_get_pixel_f32_dyn(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx.c1 * stexel, i1j0.v, lut);
-                cpvk_get_pixel_f32_dyn(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx.c0 * stexel, i0j1.v, lut);
-                cpvk_get_pixel_f32_dyn(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx.c1 * stexel, i1j1.v, lut);
-                const CpvkVec4 ij0 = cpvk_lerp(i0j0, i1j0, cx.t), ij1 = cpvk_lerp(i0j1, i1j1, cx.t);
-                const CpvkVec4 plane = cpvk_lerp(ij0, ij1, cy.t);
-                value = cpvk_lerp(plane, plane, cz.t); // the two z planes are the same slice
+            const cpvk_u8* r0 = src + (cpvk_u64)(cpvk_u32)cy.c0 * spitch;
+            const cpvk_u8* r1 = src + (cpvk_u64)(cpvk_u32)cy.c1 * spitch;
+            float value[4][4];
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (x4 + k >= dstW) continue;
+                float* v = value[k];
+                if (FILTER == 0) {
+                    cpvk_blit_load<KS>(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx[k].c0 * stexel, v, lut);
+                } else {
+                    CpvkVec4 i0j0, i1j0, i0j1, i1j1;
+                    cpvk_blit_load<KS>(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx[k].c0 * stexel, i0j0.v, lut);
+                    cpvk_blit_load<KS>(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx[k].c1 * stexel, i1j0.v, lut);
+                    cpvk_blit_load<KS>(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx[k].c0 * stexel, i0j1.v, lut);
+                    cpvk_blit_load<KS>(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx[k].c1 * stexel, i1j1.v, lut);
+                    const CpvkVec4 ij0 = cpvk_lerp(i0j0, i1j0, cx[k].t), ij1 = cpvk_lerp(i0j1, i1j1, cx[k].t);
+                    const CpvkVec4 plane = cpvk_lerp(ij0, ij1, cy.t);
+                    const CpvkVec4 out = cpvk_lerp(plane, plane, cz.t); // the two z planes are the same slice
+                    v[0] = out.v[0]; v[1] = out.v[1]; v[2] = out.v[2]; v[3] = out.v[3];
+                }
+                if (comps < 2) v[1] = 0.0f; // SampleImage (ImageSampler.cpp:581-673): absent channels read 0, 0, 1
+                if (comps < 3) v[2] = 0.0f;
+                if (comps < 4) v[3] = 1.0f;
             }
-            if (comps < 2) value.v[1] = 0.0f; // SampleImage (ImageSampler.cpp:581-673): absent channels read 0, 0, 1
-            if (comps < 3) value.v[2] = 0.0f;
-            if (comps < 4) value.v[3] = 1.0f;
-            if (cx.dst < 0 || cy.dst < 0 || (cpvk_u32)cx.dst >= b.dst.width || (cpvk_u32)cy.dst >= b.dst.height) continue;
-            cpvk_set_pixel_f32_dyn(b.dst.format, reinterpret_cast<cpvk_u8*>(b.dst.address) + (cpvk_u64)cy.dst * b.dst.rowPitch + (cpvk_u64)cx.dst * dtexel, value.v);
+            if (cy.dst < 0 || (cpvk_u32)cy.dst >= b.dst.height) continue;
+            cpvk_u8* drow = reinterpret_cast<cpvk_u8*>(b.dst.address) + (cpvk_u64)cy.dst * b.dst.rowPitch;
+            if (run && KD == K8) {
+                *reinterpret_cast<uint4*>(drow + (cpvk_u64)cx[0].dst * 4u) = make_uint4(cpvk_blit_pack8(b.dst.format, value[0]), cpvk_blit_pack8(b.dst.format, value[1]),
+                                                                                       cpvk_blit_pack8(b.dst.format, value[2]), cpvk_blit_pack8(b.dst.format, value[3]));
+            } else if (run && KD == K16F) {
+                const uint2 h0 = cpvk_pack_half4(value[0]), h1 = cpvk_pack_half4(value[1]), h2 = cpvk_pack_half4(value[2]), h3 = cpvk_pack_half4(value[3]);
+                uint4* d = reinterpret_cast<uint4*>(drow + (cpvk_u64)cx[0].dst * 8u);
+                d[0] = make_uint4(h0.x, h0.y, h1.x, h1.y); d[1] = make_uint4(h2.x, h2.y, h3.x, h3.y);
+            } else {
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (x4 + k >= dstW || cx[k].dst < 0 || (cpvk_u32)cx[k].dst >= b.dst.width) continue;
+                    cpvk_set_pixel_f32_dyn(b.dst.format, drow + (cpvk_u64)cx[k].dst * dtexel, value[k]);
+                }
+            }
         }
     }
 }
@@ -498,9 +541,14 @@ cudaError_t cpvk_launch_blit(const CpvkBlitArgs* b, cudaStream_t s) {
     const unsigned long long total = (unsigned long long)abs(b->dstX1 - b->dstX0) * (unsigned long long)abs(b->dstY1 - b->dstY0);
     if (!total) return cudaSuccess;
     const unsigned w = (unsigned)abs(b->dstX1 - b->dstX0), h = (unsigned)abs(b->dstY1 - b->dstY0);
-    dim3 grid(cpvk_grid(w, 256), cpvk_grid(h, CPVK_BLIT_ROWS));
+    dim3 grid(cpvk_grid(cpvk_grid(w, 4), 256), cpvk_grid(h, CPVK_BLIT_ROWS));
     if (grid.y > 65535u) grid.y = 65535u; // the kernel strides over row blocks
-    k_blit<<<grid, 256, 0, s>>>(*b);
+    auto kind = [](unsigned f) { return (f == 37 || f == 44) ? K8 : (f == 97 ? K16F : KDYN); };
+    const int ks = kind(b->src.format), kd = kind(b->dst.format), lin = b->filter != 0;
+    #define CPVK_BLIT_CASE(S, D) if (ks == S && kd == D) { if (lin) k_blit<S, D, 1><<<grid, 256, 0, s>>>(*b); else k_blit<S, D, 0><<<grid, 256, 0, s>>>(*b); return cudaGetLastError(); }
+    CPVK_BLIT_CASE(K8, K8) CPVK_BLIT_CASE(K8, K16F) CPVK_BLIT_CASE(K16F, K8) CPVK_BLIT_CASE(K16F, K16F)
+    #undef CPVK_BLIT_CASE
+    if (lin) k_blit<KDYN, KDYN, 1><<<grid, 256, 0, s>>>(*b); else k_blit<KDYN, KDYN, 0><<<grid, 256, 0, s>>>(*b);
     return cudaGetLastError();
 }
 }

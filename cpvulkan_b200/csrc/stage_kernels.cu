@@ -401,7 +401,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     // test, so the same bits), then GetFragmentInput's normalisation/depth, DrawPixel's viewport depth, the fragment
     // shader, and the epilogue. Fragments of one batch are in API order by lane; the ROP of fragments that share a
     // pixel is serialised lowest lane first (a pixel belongs to exactly one warp, so that is the only hazard).
-    auto shadeBatch = [&](bool active, cpvk_u32 kt, int px, int py) {
+    auto shadeBatch = [&](bool active, cpvk_u32 kt, int px, int py, bool distinct) {
         CpvkFragOut out;
         bool survive = false, front = true;
         float fragDepth = 0.0f;
@@ -447,7 +447,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             survive = !cpvk_fs_main(&ctx, &out);
             key = (cpvk_u32)(py * CPVK_TILE_W + px);
         }
-        const cpvk_u32 same = __match_any_sync(0xFFFFFFFFu, key);
+        // a large triangle's batch holds one pixel per lane by construction (warp-uniform flag): nothing to serialise
+        const cpvk_u32 same = distinct ? (1u << lane) : __match_any_sync(0xFFFFFFFFu, key);
         cpvk_u32 pending = __ballot_sync(0xFFFFFFFFu, survive);
         const cpvk_u32 lowerMask = (1u << lane) - 1u;
         cpvk_u32 writtenMask = 0;
@@ -834,7 +835,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                     int o = 0, row0 = lcy0;
                     #pragma unroll 1
                     for (;;) {
-                        bool active = false; cpvk_u32 bkt = 0; int px = 0, py = 0;
+                        bool active = false, distinct = false; cpvk_u32 bkt = 0; int px = 0, py = 0;
                         if (o < total) {
                             active = o + lane < total;
                             if (active) {
@@ -845,9 +846,9 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                         } else if (firstLarge < 32 && row0 < lcy1) {
                             const int x = lcx0 + (lane & ((1 << lg) - 1)), y = row0 + (lane >> lg);
                             row0 += 32 >> lg;
-                            active = x < lcx1 && y < lcy1; bkt = lkt; px = x - tileX0; py = y - tileY0; // coverage is tested by shadeBatch
+                            active = x < lcx1 && y < lcy1; bkt = lkt; px = x - tileX0; py = y - tileY0; distinct = true; // coverage is tested by shadeBatch
                         } else break;
-                        shadeBatch(active, bkt, px, py); // the only call site: one copy of the fragment shader per kernel
+                        shadeBatch(active, bkt, px, py, distinct); // the only call site: one copy of the fragment shader per kernel
                     }
                     __syncwarp();
                     todo &= ~seg;
