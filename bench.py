@@ -519,6 +519,7 @@ def e2e_multi(torch, dist, rig, local, steps):
             full, host, per, _ = shards[nme]
             full[rank * per:(rank + 1) * per].copy_(host, non_blocking=True)
             dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per])
+        dev.flush()  # the index and vertex bytes were rewritten behind the library's back (copy_ + NCCL): drop what it remembers of them
         dev.upload_async(sod.m.addr["ubo"], dev.allocs[ubo_stage][1], ubo.nbytes)
         rig.frame()
         if band_bytes:

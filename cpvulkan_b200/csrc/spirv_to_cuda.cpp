@@ -561,6 +561,7 @@ private:
             layout.vsWritesMemory = storesToMemory;
         } else {
             layout.originUpperLeft = m.originUpperLeft;
+            layout.fsWritesMemory = storesToMemory;
             // FindShaderLocations (PipelineCompiler.cpp:1729-1798): output at Location L feeds attachment L
             for (const Var& v : m.vars) {
                 if (v.storage != ScOutput || !m.hasDeco(v.id, DecoLocation)) continue;

@@ -21,6 +21,7 @@ struct PipelineLayoutInfo {
     bool originUpperLeft = false;    // FS OriginUpperLeft execution mode (Pipeline.cpp:976-984)
     bool fsSamplesImages = false;    // the fragment shader samples or fetches images (large software sampler inlined: more registers pay off)
     bool vsWritesMemory = false;     // the vertex shader stores to a buffer: its invocation count is observable
+    bool fsWritesMemory = false;     // the fragment shader stores to a buffer
 };
 
 // Translates one stage. `model` is the SPIR-V execution model (0 vertex, 4 fragment). Appends the generated

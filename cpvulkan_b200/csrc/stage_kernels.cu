@@ -137,6 +137,7 @@ __device__ __forceinline__ void cpvk_apply_blend(const float s[4], const float d
     }
 }
 
+// (CPVK_RASTER_THREADS, not blockDim.x, strides the loops below: a compile-time stride spares a division for the trip count.)
 // Copy `bytes` (a multiple of the texel size) between a global row segment and shared memory, all threads of
 // the CTA cooperating over `rows` rows; 16-byte vectors when both sides allow, else 4-byte words, else bytes.
 // `fullBytes` = bytes of a full-width tile row (a link-time constant per pipeline): when the row is full and everything is
@@ -145,24 +146,24 @@ __device__ __forceinline__ void cpvk_tile_copy(cpvk_u8* dst, cpvk_u32 dstPitch, 
     const cpvk_u64 align = ((cpvk_u64)dst | (cpvk_u64)src | dstPitch | srcPitch | bytes);
     if ((align & 15) == 0 && bytes == fullBytes && (fullBytes & (fullBytes - 1u)) == 0u) {
         const cpvk_u32 per = fullBytes >> 4; // power of two
-        for (cpvk_u32 i = threadIdx.x; i < per * rows; i += blockDim.x) {
+        for (cpvk_u32 i = threadIdx.x; i < per * rows; i += CPVK_RASTER_THREADS) {
             const cpvk_u32 r = i / per, c = i & (per - 1u);
             reinterpret_cast<uint4*>(dst + (cpvk_u64)r * dstPitch)[c] = reinterpret_cast<const uint4*>(src + (cpvk_u64)r * srcPitch)[c];
         }
     } else if ((align & 15) == 0) {
         const cpvk_u32 per = bytes >> 4;
-        for (cpvk_u32 i = threadIdx.x; i < per * rows; i += blockDim.x) {
+        for (cpvk_u32 i = threadIdx.x; i < per * rows; i += CPVK_RASTER_THREADS) {
             const cpvk_u32 r = i / per, c = i - r * per;
             reinterpret_cast<uint4*>(dst + (cpvk_u64)r * dstPitch)[c] = reinterpret_cast<const uint4*>(src + (cpvk_u64)r * srcPitch)[c];
         }
     } else if ((align & 3) == 0) {
         const cpvk_u32 per = bytes >> 2;
-        for (cpvk_u32 i = threadIdx.x; i < per * rows; i += blockDim.x) {
+        for (cpvk_u32 i = threadIdx.x; i < per * rows; i += CPVK_RASTER_THREADS) {
             const cpvk_u32 r = i / per, c = i - r * per;
             reinterpret_cast<cpvk_u32*>(dst + (cpvk_u64)r * dstPitch)[c] = reinterpret_cast<const cpvk_u32*>(src + (cpvk_u64)r * srcPitch)[c];
         }
     } else {
-        for (cpvk_u32 i = threadIdx.x; i < bytes * rows; i += blockDim.x) {
+        for (cpvk_u32 i = threadIdx.x; i < bytes * rows; i += CPVK_RASTER_THREADS) {
             const cpvk_u32 r = i / bytes, c = i - r * bytes;
             dst[(cpvk_u64)r * dstPitch + c] = src[(cpvk_u64)r * srcPitch + c];
         }
@@ -177,10 +178,10 @@ CPVK_DEV void cpvk_tile_fill(cpvk_u8* dst, cpvk_u32 texel, const cpvk_u8* one) {
         else if (texel == 8) { const uint2 t = *reinterpret_cast<const uint2*>(one); v = make_uint4(t.x, t.y, t.x, t.y); }
         else { const cpvk_u32 t = *reinterpret_cast<const unsigned short*>(one) * 0x10001u; v = make_uint4(t, t, t, t); }
         uint4* d = reinterpret_cast<uint4*>(dst);
-        for (cpvk_u32 i = threadIdx.x; i < CPVK_TILE_W * CPVK_TILE_H * texel / 16; i += blockDim.x) d[i] = v;
+        for (cpvk_u32 i = threadIdx.x; i < CPVK_TILE_W * CPVK_TILE_H * texel / 16; i += CPVK_RASTER_THREADS) d[i] = v;
         return;
     }
-    for (cpvk_u32 i = threadIdx.x; i < CPVK_TILE_W * CPVK_TILE_H; i += blockDim.x) {
+    for (cpvk_u32 i = threadIdx.x; i < CPVK_TILE_W * CPVK_TILE_H; i += CPVK_RASTER_THREADS) {
         cpvk_u8* d = dst + i * texel;
         if (texel == 16) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(one);
         else if (texel == 8) *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(one);
@@ -214,13 +215,12 @@ extern __shared__ __align__(16) cpvk_u8 cpvk_smem[];
 #define CPVK_RASTER_MIN_CTAS 4 /* resident CTAs per SM the register allocation aims for; build.py builds 4, 3 and 2 */
 #endif
 extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MIN_CTAS) cpvk_k_raster(const __grid_constant__ CpvkDrawParams p) {
-    const cpvk_u32 tile = blockIdx.x;
+    const cpvk_u32 tx = blockIdx.x, tyr = blockIdx.y, tile = tyr * p.tilesX + tx; // grid = (tilesX, tilesY): no division to find the tile
     const bool triangles = cpvk_prim_vertices() == 3; // points and lines are not binned: every tile walks all of them (below)
     if (triangles && p.binMeta[3] != 0) return; // the speculative launch plan did not fit this draw: the host replays it
     const bool listsSorted = triangles && p.binMeta[1] > CPVK_CHUNK;
     const cpvk_u32 listBegin = triangles ? p.tileOffsets[tile] : 0u, listEnd = triangles ? p.tileOffsets[tile + 1] : 1u;
     const cpvk_u32 lazyMask = p.lazyMask;
-    const cpvk_u32 tyr = tile / p.tilesX, tx = tile - tyr * p.tilesX;
     const int tileX0 = (int)tx * CPVK_TILE_W, tileY0 = (int)(tyr + p.tileRow0) * CPVK_TILE_H;
     // nothing to draw and no clear to fold: done — unless mirrors are on, then even untouched tiles of the band travel
     if (listBegin == listEnd && lazyMask == 0 && p.mirrorCount == 0) return;
@@ -276,7 +276,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
         const float H = p.vpHeight; const float hp = (1.0f / H) * 0.5f;
         sYf[j] = ((float)(tileY0 + j) / H + hp) * 2.0f - 1.0f;
     }
-    sLut[threadIdx.x] = (float)threadIdx.x / 255.0f; // CPVK_RASTER_THREADS == 256
+    sLut[threadIdx.x] = cpvk_unorm8(threadIdx.x); // == (float)k / 255.0f for every k; CPVK_RASTER_THREADS == 256
     // Unsorted lists always fit one chunk (the host sorts otherwise): fetch this tile's ids now so the load overlaps tile
     // staging, and park them where the ranking pass below expects them — the staging barrier then covers both.
     cpvk_u32 firstKey = 0xFFFFFFFFu;
@@ -617,16 +617,22 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                 for (int d = 1; d < 32; d <<= 1) { const cpvk_u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
                 if (lane == 31) sRange[16 + warp] = incl;
                 __syncthreads();
-                if (cnt) {
-                    cpvk_u32 pos = incl - cnt;
-                    for (int q = 0; q < warp; q++) pos += sRange[16 + q];
-                    const cpvk_u32 w4[4] = {bits.x, bits.y, bits.z, bits.w};
-                    #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        cpvk_u32 m = w4[q];
-                        const cpvk_u32 idBase = lo + threadIdx.x * 128u + (cpvk_u32)q * 32u;
-                        while (m) { sSorted[pos++] = idBase + (cpvk_u32)__ffs((int)m) - 1u; m &= m - 1u; }
+                cpvk_u32 pos = incl - cnt;
+                for (int q = 0; q < warp; q++) pos += sRange[16 + q];
+                // the slices are written out by the whole warp, one non-empty 32-bit word at a time (its 32 ids = the 32 lanes):
+                // a tile's ids come in a few dense runs, which a per-thread loop would leave to a few busy lanes
+                const cpvk_u32 w4[4] = {bits.x, bits.y, bits.z, bits.w};
+                #pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    cpvk_u32 nonEmpty = __ballot_sync(0xFFFFFFFFu, w4[q] != 0u);
+                    while (nonEmpty) { // warp-uniform
+                        const int srcLane = __ffs((int)nonEmpty) - 1;
+                        nonEmpty &= nonEmpty - 1u;
+                        const cpvk_u32 word = __shfl_sync(0xFFFFFFFFu, w4[q], srcLane), first = __shfl_sync(0xFFFFFFFFu, pos, srcLane);
+                        if ((word >> lane) & 1u)
+                            sSorted[first + (cpvk_u32)__popc(word & ((1u << lane) - 1u))] = lo + ((cpvk_u32)(warp * 32 + srcLane) * 128u + (cpvk_u32)q * 32u) + (cpvk_u32)lane;
                     }
+                    pos += (cpvk_u32)__popc(w4[q]);
                 }
             } else {
                 // ids too far apart for the bitmap: each id's rank (number of ids <= it, minus one) is its position. Broadcast

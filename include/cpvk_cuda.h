@@ -286,7 +286,10 @@ int cpvk_cuda_clear(CpvkDevice* device, const CpvkAttachment* image, const CpvkC
    attachment (its tiles start from the clear value, so the clear costs no pass over HBM); every other entry point of
    this library that could observe the memory materialises pending clears first. Code that reads the memory behind the
    library's back in stream order (e.g. a collective enqueued on the same stream right after a clear) calls
-   cpvk_cuda_flush first; cpvk_cuda_device_set_lazy_clear(device, 0) turns the deferral off. */
+   cpvk_cuda_flush first; cpvk_cuda_device_set_lazy_clear(device, 0) turns the deferral off.
+   The library also remembers the index range of the last indexed draw and forgets it when one of its own commands writes
+   the index bytes; code that rewrites an index buffer behind the library's back (its own kernels, a collective) calls
+   cpvk_cuda_flush afterwards as well. */
 int cpvk_cuda_flush(CpvkDevice* device);
 /* Draws are enqueued to the end without waiting for the binning counts: list capacity, sort mode and the large-
    primitive passes are guessed from the previous draw, checked on the device, and the tail of the draw is replayed

@@ -742,3 +742,49 @@ def test_shared_reciprocal_division_is_ieee_division(dev):
     bad = np.argwhere(canon(shared) != canon(want))
     assert len(bad) == 0, "cpvk_div_shared differs from IEEE division in %d quotients, first: %08x / %08x -> %08x, want %08x" % (
         len(bad), a[bad[0][0], bad[0][1]], b[bad[0][0]], shared[bad[0][0], bad[0][1]], want[bad[0][0], bad[0][1]])
+
+
+def test_index_range_is_recomputed_when_the_indices_change(dev):
+    """The lowest / highest index of an indexed draw is remembered across draws (an application redraws the same range every
+    frame); rewriting the index buffer through the library must drop it. Same buffer address, same count, another range."""
+    from cpvulkan_b200.device import SceneOnDevice
+    a = scenes.mesh_indexed(width=320, height=200, nx=40, ny=25)
+    s = SceneOnDevice(dev, a)
+    try:
+        for round_ in range(2):
+            s.render()
+            assert np.array_equal(s.read_color(), scenes.run_oracle(a)[0])
+        # the same triangles drawn from the upper half of the vertex range only: indices clamped from below change lowest
+        idx = a.buffers["ib"].view(np.uint32).copy()
+        idx[:] = np.maximum(idx, 400)
+        b = scenes.mesh_indexed(width=320, height=200, nx=40, ny=25)
+        b.buffers["ib"] = idx.view(np.uint8).reshape(-1)
+        dev.upload(s.m.addr["ib"], b.buffers["ib"])
+        s.render()
+        oc, od, _ = scenes.run_oracle(b)
+        assert np.array_equal(s.read_color(), oc) and np.array_equal(s.read_depth(), od)
+        # ... and back, through a device-side copy this time
+        tmp = dev.alloc(a.buffers["ib"].nbytes)
+        dev.upload(tmp, a.buffers["ib"])
+        dev.copy_rows(s.m.addr["ib"], a.buffers["ib"].nbytes, tmp, a.buffers["ib"].nbytes, a.buffers["ib"].nbytes, 1)
+        s.render()
+        assert np.array_equal(s.read_color(), scenes.run_oracle(a)[0])
+        dev.free(tmp)
+    finally:
+        s.close()
+
+
+def test_unorm8_decode_all_codes(dev):
+    """(float)k / 255.0f without the divide (cpvk_unorm8): all 256 codes through a NEAREST blit R8G8B8A8_UNORM -> R32G32B32A32_SFLOAT
+    against the host's IEEE division."""
+    import ctypes as C
+    from cpvulkan_b200 import capi
+    src = np.arange(256, dtype=np.uint8).repeat(4).reshape(256, 4).copy().reshape(-1)
+    sa, da = dev.alloc(src.nbytes), dev.alloc(256 * 16)
+    dev.upload(sa, src)
+    dev.blit(capi.Blit(capi.Attachment(sa, 256, 1, 1024, 37), capi.Attachment(da, 256, 1, 4096, 109), 0, 0, 256, 1, 0, 0, 256, 1, 0))
+    got = dev.download(da, 256 * 16).view(np.float32).reshape(256, 4)
+    want = (np.arange(256, dtype=np.float32) / np.float32(255.0)).astype(np.float32)
+    for c in range(4):
+        assert np.array_equal(got[:, c].view(np.uint32), want.view(np.uint32)), "channel %d" % c
+    dev.free(sa); dev.free(da)
