@@ -793,6 +793,29 @@ int cpvk_oracle_apply_blend(const uint32_t state[8], const float* source, const 
     }
 }
 
+// Shader runtime math one operation at a time (a14), the counterpart of oracle/ref_math_check.cpp: the interpreter's own
+// GLSL.std.450 / OpDot / OpMatrixTimes* code (oracle_spirv.h) on raw 32-bit lanes. header = {kind, op, type, n, 0} as documented
+// there; out receives 16 lanes.
+int cpvk_oracle_math(const uint32_t header[5], const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t* out) {
+    try {
+        const uint32_t kind = header[0], op = header[1], n = header[3];
+        for (int i = 0; i < 16; i++) out[i] = 0;
+        switch (kind) {
+        case 0: Interp::GlslOp(op, a, b, c, (op == 66 || op == 67) ? 1 : n, n, out); break;
+        case 1: { const float r = Interp::Dot(a, b, n); std::memcpy(out, &r, 4); break; }
+        case 2: { float s; std::memcpy(&s, b, 4); for (uint32_t i = 0; i < n * n; i++) { float v; std::memcpy(&v, &a[i], 4); v = v * s; std::memcpy(&out[i], &v, 4); } break; } // OpMatrixTimesScalar
+        case 3: Interp::VectorTimesMatrix(a, b, 4, 4, out); break;
+        case 4: Interp::MatrixTimesVector(a, b, n, n, out); break;
+        case 5: Interp::MatrixTimesMatrix(a, b, 4, 4, 4, out); break;
+        default: Fail("cpvk_oracle_math: unknown kind");
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return CPVK_E_UNSUPPORTED;
+    }
+}
+
 // Render-pass clear == ClearImage: SetPixel on every texel of the subresource (Draw.cpp:117-149, ImageSampler.cpp:723-761).
 int cpvk_oracle_clear(const CpvkAttachment* image, const CpvkClearValue* value, int isDepthStencil) {
     const FormatInfo fi = GetFormatInformation(image->format);

@@ -426,6 +426,10 @@ struct Interp {
 
     // glm::dot operand order (func_geometric.inl compute_dot): vec2 a.x*b.x + a.y*b.y; vec3 left to right;
     // vec4 (tmp.x + tmp.y) + (tmp.z + tmp.w).
+    static void GlslOp(uint32_t e, const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t n, uint32_t cnt, uint32_t* r);
+    static void MatrixTimesVector(const uint32_t* a, const uint32_t* v, uint32_t cols, uint32_t rows, uint32_t* out);
+    static void VectorTimesMatrix(const uint32_t* v, const uint32_t* a, uint32_t cols, uint32_t rows, uint32_t* out);
+    static void MatrixTimesMatrix(const uint32_t* a, const uint32_t* b, uint32_t lcols, uint32_t lrows, uint32_t rcols, uint32_t* out);
     static float Dot(const uint32_t* a, const uint32_t* b, uint32_t n) {
         float t[4]; for (uint32_t i = 0; i < n; i++) t[i] = F(a[i]) * F(b[i]);
         if (n == 1) return t[0];
@@ -592,38 +596,22 @@ inline bool Interp::Exec(Function& f, std::vector<uint32_t>& fr, const Inst& in,
     case OpVectorTimesScalar: { const uint32_t* a = V(in.ops[0]); const float s = F(*V(in.ops[1])); for (uint32_t i = 0; i < n; i++) r[i] = U(F(a[i]) * s); return false; }
     case OpMatrixTimesScalar: { const uint32_t* a = V(in.ops[0]); const float s = F(*V(in.ops[1])); for (uint32_t i = 0; i < n; i++) r[i] = U(F(a[i]) * s); return false; }
     case OpMatrixTimesVector: {
-        // glm mat*vec: 4x4 -> (m0*v0 + m1*v1) + (m2*v2 + m3*v3); 2/3 columns -> left to right.
         const Type& mt = m->types[TypeOf(in.ops[0])]; const uint32_t cols = mt.count, rows = m->types[mt.elem].count;
-        const uint32_t* a = V(in.ops[0]); const uint32_t* v = V(in.ops[1]);
         uint32_t out[4];
-        for (uint32_t q = 0; q < rows; q++) {
-            float p[4]; for (uint32_t c = 0; c < cols; c++) p[c] = F(a[c * rows + q]) * F(v[c]);
-            float s;
-            if (cols == 4 && rows == 4) s = (p[0] + p[1]) + (p[2] + p[3]);
-            else { s = p[0]; for (uint32_t c = 1; c < cols; c++) s = s + p[c]; }
-            out[q] = U(s);
-        }
+        MatrixTimesVector(V(in.ops[0]), V(in.ops[1]), cols, rows, out);
         std::memcpy(r, out, rows * 4);
         return false; }
     case OpVectorTimesMatrix: {
-        // glm vec*mat: result[c] = dot-like left-to-right sum over rows of m[c][k] * v[k].
         const Type& mt = m->types[TypeOf(in.ops[1])]; const uint32_t cols = mt.count, rows = m->types[mt.elem].count;
-        const uint32_t* v = V(in.ops[0]); const uint32_t* a = V(in.ops[1]);
         uint32_t out[4];
-        for (uint32_t c = 0; c < cols; c++) { float s = F(a[c * rows]) * F(v[0]); for (uint32_t k = 1; k < rows; k++) s = s + F(a[c * rows + k]) * F(v[k]); out[c] = U(s); }
+        VectorTimesMatrix(V(in.ops[0]), V(in.ops[1]), cols, rows, out);
         std::memcpy(r, out, cols * 4);
         return false; }
     case OpMatrixTimesMatrix: {
-        // glm mat*mat: Result[j] = A0*B[j][0] + A1*B[j][1] + ... left to right.
         const Type& lt = m->types[TypeOf(in.ops[0])]; const uint32_t lcols = lt.count, lrows = m->types[lt.elem].count;
         const Type& rtm = m->types[TypeOf(in.ops[1])]; const uint32_t rcols = rtm.count;
-        const uint32_t* a = V(in.ops[0]); const uint32_t* b = V(in.ops[1]);
         uint32_t out[16];
-        for (uint32_t j = 0; j < rcols; j++) for (uint32_t q = 0; q < lrows; q++) {
-            float s = F(a[q]) * F(b[j * lcols]);
-            for (uint32_t k = 1; k < lcols; k++) s = s + F(a[k * lrows + q]) * F(b[j * lcols + k]);
-            out[j * lrows + q] = U(s);
-        }
+        MatrixTimesMatrix(V(in.ops[0]), V(in.ops[1]), lcols, lrows, rcols, out);
         std::memcpy(r, out, rcols * lrows * 4);
         return false; }
     case OpDot: { const uint32_t cnt = m->types[TypeOf(in.ops[0])].count; r[0] = U(Dot(V(in.ops[0]), V(in.ops[1]), cnt)); return false; }
@@ -723,17 +711,43 @@ inline bool Interp::Exec(Function& f, std::vector<uint32_t>& fr, const Inst& in,
     #undef CMP_F
 }
 
+// @Matrix.Mult.* (SpirvFunctions.cpp:6-60 -> glm operators), column-major, on raw 32-bit lanes.
+// glm mat*vec: 4x4 -> (m0*v0 + m1*v1) + (m2*v2 + m3*v3); 2 / 3 columns -> left to right.
+inline void Interp::MatrixTimesVector(const uint32_t* a, const uint32_t* v, uint32_t cols, uint32_t rows, uint32_t* out) {
+    for (uint32_t q = 0; q < rows; q++) {
+        float p[4]; for (uint32_t c = 0; c < cols; c++) p[c] = F(a[c * rows + q]) * F(v[c]);
+        float s;
+        if (cols == 4 && rows == 4) s = (p[0] + p[1]) + (p[2] + p[3]);
+        else { s = p[0]; for (uint32_t c = 1; c < cols; c++) s = s + p[c]; }
+        out[q] = U(s);
+    }
+}
+// glm vec*mat: result[c] = left-to-right sum over the rows of m[c][k] * v[k].
+inline void Interp::VectorTimesMatrix(const uint32_t* v, const uint32_t* a, uint32_t cols, uint32_t rows, uint32_t* out) {
+    for (uint32_t c = 0; c < cols; c++) { float s = F(a[c * rows]) * F(v[0]); for (uint32_t k = 1; k < rows; k++) s = s + F(a[c * rows + k]) * F(v[k]); out[c] = U(s); }
+}
+// glm mat*mat: Result[j] = A0*B[j][0] + A1*B[j][1] + ... left to right.
+inline void Interp::MatrixTimesMatrix(const uint32_t* a, const uint32_t* b, uint32_t lcols, uint32_t lrows, uint32_t rcols, uint32_t* out) {
+    for (uint32_t j = 0; j < rcols; j++) for (uint32_t q = 0; q < lrows; q++) {
+        float s = F(a[q]) * F(b[j * lcols]);
+        for (uint32_t k = 1; k < lcols; k++) s = s + F(a[k * lrows + q]) * F(b[j * lcols + k]);
+        out[j * lrows + q] = U(s);
+    }
+}
+
 // GLSL.std.450 as the reference implements it (GlslFunctions.cpp:19-321): std::min/max/clamp comparison
 // forms, Mix = x*(1-a)+y*a, glm::normalize = v * (1/sqrt(dot(v,v))), glm::reflect = I - N*dot(N,I)*2.
 inline void Interp::ExtInst(Function& f, std::vector<uint32_t>& fr, const Inst& in) {
     auto V = [&](uint32_t id) { return Val(f, fr, id); };
     if (in.ops[0] != m->glslExt) Fail("unknown extended instruction set");
-    const uint32_t e = in.ops[1];
-    uint32_t* r = V(in.result);
-    const uint32_t n = m->types[in.type].words;
     const uint32_t* a = in.nops > 2 ? V(in.ops[2]) : nullptr;
     const uint32_t* b = in.nops > 3 ? V(in.ops[3]) : nullptr;
     const uint32_t* c = in.nops > 4 ? V(in.ops[4]) : nullptr;
+    GlslOp(in.ops[1], a, b, c, m->types[in.type].words, in.nops > 2 ? m->types[TypeOf(in.ops[2])].words : 0, V(in.result));
+}
+// One GLSL.std.450 instruction on raw 32-bit lanes: n = words of the result, cnt = words of the first operand (the vector width
+// of Length / Distance / Normalize / Reflect / Cross). Also what cpvk_oracle_math runs for tests/test_reference_math.py.
+inline void Interp::GlslOp(uint32_t e, const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t n, uint32_t cnt, uint32_t* r) {
     auto mn = [](auto x, auto y) { return y < x ? y : x; };
     auto mx = [](auto x, auto y) { return x < y ? y : x; };
     auto cl = [](auto v, auto lo, auto hi) { return v < lo ? lo : (hi < v ? hi : v); };
@@ -771,7 +785,6 @@ inline void Interp::ExtInst(Function& f, std::vector<uint32_t>& fr, const Inst& 
     }
     return;
 vector_ops: {
-    const uint32_t cnt = m->types[TypeOf(in.ops[2])].words;
     switch (e) {
     case 66: r[0] = U(std::sqrt(Dot(a, a, cnt))); break;                              // Length = sqrt(dot(v,v))
     case 67: { uint32_t d[4]; for (uint32_t i = 0; i < cnt; i++) d[i] = U(F(b[i]) - F(a[i])); r[0] = U(std::sqrt(Dot(d, d, cnt))); break; } // glm::distance = length(p1 - p0)

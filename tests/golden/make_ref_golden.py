@@ -150,8 +150,33 @@ def draw_golden():
         print("   %-28s %8d fragments%s" % (c.name, len(s), "  (full)" if c.full else ""))
 
 
+MATH_CHECK = os.path.join(os.path.dirname(CHECK), "math_check")
+
+
+def math_golden():
+    """The reference's shader runtime math (LLVMRuntime/SpirvFunctions.cpp through its name table, the GLSL.std.450 templates of
+    CPVulkan/GlslFunctions.cpp:19-321), run by oracle/_ref/math_check on the seeded cases of tests/ref_math_cases.py."""
+    import sys
+    import tempfile
+    sys.path.insert(0, os.path.dirname(HERE))
+    import ref_math_cases as mc
+    hdr, A, B, C = mc.cases()
+    with tempfile.TemporaryDirectory() as d:
+        src, dst = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        with open(src, "wb") as f:
+            f.write(mc.file_bytes(hdr, A, B, C))
+        subprocess.run([MATH_CHECK, src, dst], check=True)
+        out = np.fromfile(dst, dtype="<u4").reshape(len(hdr), 16)
+    # float results only are canonicalised for NaN (integer lanes are compared as they are)
+    isf = hdr[:, 2] == 0
+    out[isf] = mc.canonical(out[isf])
+    np.savez_compressed(os.path.join(HERE, "ref_math.npz"), result_bits=out)
+    print("math: %d cases" % len(hdr))
+
+
 def main():
     draw_golden()
+    math_golden()
     sampler_golden()
     sampler3d_golden()
     open(os.path.join(HERE, "ref_formats.txt"), "w").write(run("formats"))
