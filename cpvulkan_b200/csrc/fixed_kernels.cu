@@ -397,9 +397,10 @@ __device__ __forceinline__ cpvk_u32 cpvk_blit_pack8(cpvk_u32 format, const float
     const cpvk_u32 r = cpvk_float_to_unorm(v[0], 255.0f), g = cpvk_float_to_unorm(v[1], 255.0f), b = cpvk_float_to_unorm(v[2], 255.0f), a = cpvk_float_to_unorm(v[3], 255.0f);
     return format == 37 ? (r | (g << 8) | (b << 16) | (a << 24)) : (b | (g << 8) | (r << 16) | (a << 24));
 }
-// Four destination columns per thread, CPVK_BLIT_ROWS rows per CTA: the per-column terms are computed once per thread, the per-row
-// terms once per CTA, and an aligned run of four destination texels leaves as one (K8) or two (K16F) 16-byte stores.
-template <int KS, int KD, int FILTER> __global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
+// TPT destination columns per thread (4 for NEAREST: an aligned run of four destination texels leaves as one (K8) or two (K16F)
+// 16-byte stores; 1 for LINEAR, whose four taps and twelve double lerps per texel want the registers), CPVK_BLIT_ROWS rows per CTA:
+// the per-column terms are computed once per thread, the per-row terms once per CTA.
+template <int KS, int KD, int FILTER, int TPT> __global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
     __shared__ float lut[256]; // (float)k / 255.0f by the IEEE divide itself, for the run-time format path
     __shared__ CpvkBlitAxis rows[CPVK_BLIT_ROWS];
     if (KS == KDYN) lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
@@ -409,14 +410,14 @@ template <int KS, int KD, int FILTER> __global__ void __launch_bounds__(256) k_b
     const cpvk_u8* src = reinterpret_cast<const cpvk_u8*>(b.src.address);
     const CpvkFormat fi = cpvk_format(b.src.format);
     const cpvk_u32 comps = fi.type == CPVK_FT_DEPTH ? 1u : fi.comps;
-    const int x4 = (int)(blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    CpvkBlitAxis cx[4];
+    const int x4 = (int)(blockIdx.x * blockDim.x + threadIdx.x) * TPT;
+    CpvkBlitAxis cx[TPT];
     #pragma unroll
-    for (int k = 0; k < 4; k++) cx[k] = cpvk_blit_axis(x4 + k < dstW ? x4 + k : 0, b.dstX0, b.dstX1, b.srcX0, b.srcX1, b.src.width, FILTER);
+    for (int k = 0; k < TPT; k++) cx[k] = cpvk_blit_axis(x4 + k < dstW ? x4 + k : 0, b.dstX0, b.dstX1, b.srcX0, b.srcX1, b.src.width, FILTER);
     // the z axis: one destination "slice" 0, source slices [0, 1) of a depth-1 image
     const CpvkBlitAxis cz = cpvk_blit_axis(0, 0, 1, 0, 1, 1u, FILTER);
     // the four columns form one aligned in-range run of the destination? (then vector stores)
-    const bool run = x4 + 3 < dstW && cx[0].dst >= 0 && (cpvk_u32)cx[3].dst < b.dst.width && cx[3].dst == cx[0].dst + 3 &&
+    const bool run = TPT == 4 && x4 + 3 < dstW && cx[0].dst >= 0 && (cpvk_u32)cx[TPT - 1].dst < b.dst.width && cx[TPT - 1].dst == cx[0].dst + 3 &&
                      (KD == K8 || KD == K16F) && ((b.dst.address + (cpvk_u64)cx[0].dst * dtexel) & 15u) == 0u && (b.dst.rowPitch & 15u) == 0u;
     for (int rowBase = (int)blockIdx.y * CPVK_BLIT_ROWS; rowBase < dstH; rowBase += (int)gridDim.y * CPVK_BLIT_ROWS) {
         __syncthreads();
@@ -430,9 +431,9 @@ template <int KS, int KD, int FILTER> __global__ void __launch_bounds__(256) k_b
             const CpvkBlitAxis cy = rows[r];
             const cpvk_u8* r0 = src + (cpvk_u64)(cpvk_u32)cy.c0 * spitch;
             const cpvk_u8* r1 = src + (cpvk_u64)(cpvk_u32)cy.c1 * spitch;
-            float value[4][4];
+            float value[TPT][4];
             #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < TPT; k++) {
                 if (x4 + k >= dstW) continue;
                 float* v = value[k];
                 if (FILTER == 0) {
@@ -454,16 +455,16 @@ template <int KS, int KD, int FILTER> __global__ void __launch_bounds__(256) k_b
             }
             if (cy.dst < 0 || (cpvk_u32)cy.dst >= b.dst.height) continue;
             cpvk_u8* drow = reinterpret_cast<cpvk_u8*>(b.dst.address) + (cpvk_u64)cy.dst * b.dst.rowPitch;
-            if (run && KD == K8) {
-                *reinterpret_cast<uint4*>(drow + (cpvk_u64)cx[0].dst * 4u) = make_uint4(cpvk_blit_pack8(b.dst.format, value[0]), cpvk_blit_pack8(b.dst.format, value[1]),
-                                                                                       cpvk_blit_pack8(b.dst.format, value[2]), cpvk_blit_pack8(b.dst.format, value[3]));
-            } else if (run && KD == K16F) {
-                const uint2 h0 = cpvk_pack_half4(value[0]), h1 = cpvk_pack_half4(value[1]), h2 = cpvk_pack_half4(value[2]), h3 = cpvk_pack_half4(value[3]);
+            if (TPT == 4 && run && KD == K8) {
+                *reinterpret_cast<uint4*>(drow + (cpvk_u64)cx[0].dst * 4u) = make_uint4(cpvk_blit_pack8(b.dst.format, value[0]), cpvk_blit_pack8(b.dst.format, value[1 % TPT]),
+                                                                                       cpvk_blit_pack8(b.dst.format, value[2 % TPT]), cpvk_blit_pack8(b.dst.format, value[3 % TPT]));
+            } else if (TPT == 4 && run && KD == K16F) {
+                const uint2 h0 = cpvk_pack_half4(value[0]), h1 = cpvk_pack_half4(value[1 % TPT]), h2 = cpvk_pack_half4(value[2 % TPT]), h3 = cpvk_pack_half4(value[3 % TPT]);
                 uint4* d = reinterpret_cast<uint4*>(drow + (cpvk_u64)cx[0].dst * 8u);
                 d[0] = make_uint4(h0.x, h0.y, h1.x, h1.y); d[1] = make_uint4(h2.x, h2.y, h3.x, h3.y);
             } else {
                 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+                for (int k = 0; k < TPT; k++) {
                     if (x4 + k >= dstW || cx[k].dst < 0 || (cpvk_u32)cx[k].dst >= b.dst.width) continue;
                     cpvk_set_pixel_f32_dyn(b.dst.format, drow + (cpvk_u64)cx[k].dst * dtexel, value[k]);
                 }
@@ -541,14 +542,15 @@ cudaError_t cpvk_launch_blit(const CpvkBlitArgs* b, cudaStream_t s) {
     const unsigned long long total = (unsigned long long)abs(b->dstX1 - b->dstX0) * (unsigned long long)abs(b->dstY1 - b->dstY0);
     if (!total) return cudaSuccess;
     const unsigned w = (unsigned)abs(b->dstX1 - b->dstX0), h = (unsigned)abs(b->dstY1 - b->dstY0);
-    dim3 grid(cpvk_grid(cpvk_grid(w, 4), 256), cpvk_grid(h, CPVK_BLIT_ROWS));
+    const int lin = b->filter != 0;
+    dim3 grid(cpvk_grid(cpvk_grid(w, lin ? 1 : 4), 256), cpvk_grid(h, CPVK_BLIT_ROWS));
     if (grid.y > 65535u) grid.y = 65535u; // the kernel strides over row blocks
     auto kind = [](unsigned f) { return (f == 37 || f == 44) ? K8 : (f == 97 ? K16F : KDYN); };
-    const int ks = kind(b->src.format), kd = kind(b->dst.format), lin = b->filter != 0;
-    #define CPVK_BLIT_CASE(S, D) if (ks == S && kd == D) { if (lin) k_blit<S, D, 1><<<grid, 256, 0, s>>>(*b); else k_blit<S, D, 0><<<grid, 256, 0, s>>>(*b); return cudaGetLastError(); }
+    const int ks = kind(b->src.format), kd = kind(b->dst.format);
+    #define CPVK_BLIT_CASE(S, D) if (ks == S && kd == D) { if (lin) k_blit<S, D, 1, 1><<<grid, 256, 0, s>>>(*b); else k_blit<S, D, 0, 4><<<grid, 256, 0, s>>>(*b); return cudaGetLastError(); }
     CPVK_BLIT_CASE(K8, K8) CPVK_BLIT_CASE(K8, K16F) CPVK_BLIT_CASE(K16F, K8) CPVK_BLIT_CASE(K16F, K16F)
     #undef CPVK_BLIT_CASE
-    if (lin) k_blit<KDYN, KDYN, 1><<<grid, 256, 0, s>>>(*b); else k_blit<KDYN, KDYN, 0><<<grid, 256, 0, s>>>(*b);
+    if (lin) k_blit<KDYN, KDYN, 1, 1><<<grid, 256, 0, s>>>(*b); else k_blit<KDYN, KDYN, 0, 4><<<grid, 256, 0, s>>>(*b);
     return cudaGetLastError();
 }
 }
