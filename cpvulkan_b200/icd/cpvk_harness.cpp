@@ -300,10 +300,16 @@ int main(int argc, char** argv) {
         depthView = app.MakeView(depthImg, sc.depthFormat, VK_IMAGE_ASPECT_DEPTH_BIT);
     }
     // init_descriptor_and_pipeline_layouts
-    std::vector<VkDescriptorSetLayoutBinding> lb;
-    for (auto& u : sc.uniforms) lb.push_back({u.binding, u.dynRange ? VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC : VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
+    // one set layout per descriptor set number the scene uses (Samples/multiple_sets: the uniform buffer in set 0, the texture in set 1)
+    uint32_t nSets = 1;
+    for (auto& u : sc.uniforms) nSets = std::max(nSets, u.set + 1);
+    for (auto& t : sc.textures) nSets = std::max(nSets, t.set + 1);
+    for (auto& t : sc.texelBuffers) nSets = std::max(nSets, t.set + 1);
+    std::vector<std::vector<VkDescriptorSetLayoutBinding>> lbs(nSets);
+    for (auto& u : sc.uniforms) lbs[u.set].push_back({u.binding, u.dynRange ? VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC : VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
     for (size_t i = 0; i < sc.textures.size(); i++) {
         auto& t = sc.textures[i];
+        auto& lb = lbs[t.set];
         const VkSampler* immutable = t.immutableSampler ? &texObjs[i].sampler : nullptr;
         if (t.inputAttachment) lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_INPUT_ATTACHMENT, 1, VK_SHADER_STAGE_FRAGMENT_BIT, nullptr}); // input_attachment.cpp:194-201
         else if (t.samplerBinding < 0) lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 1, VK_SHADER_STAGE_FRAGMENT_BIT, immutable});
@@ -312,11 +318,14 @@ int main(int argc, char** argv) {
             lb.push_back({(uint32_t)t.samplerBinding, VK_DESCRIPTOR_TYPE_SAMPLER, 1, VK_SHADER_STAGE_FRAGMENT_BIT, immutable});
         }
     }
-    for (auto& t : sc.texelBuffers) lb.push_back({t.binding, VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
-    VkDescriptorSetLayoutCreateInfo li{VK_STRUCTURE_TYPE_DESCRIPTOR_SET_LAYOUT_CREATE_INFO, nullptr, 0, (uint32_t)lb.size(), lb.data()};
-    VkDescriptorSetLayout setLayout; VK(vkCreateDescriptorSetLayout(app.device, &li, nullptr, &setLayout));
+    for (auto& t : sc.texelBuffers) lbs[t.set].push_back({t.binding, VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, nullptr});
+    std::vector<VkDescriptorSetLayout> setLayouts(nSets);
+    for (uint32_t k = 0; k < nSets; k++) {
+        VkDescriptorSetLayoutCreateInfo li{VK_STRUCTURE_TYPE_DESCRIPTOR_SET_LAYOUT_CREATE_INFO, nullptr, 0, (uint32_t)lbs[k].size(), lbs[k].data()};
+        VK(vkCreateDescriptorSetLayout(app.device, &li, nullptr, &setLayouts[k]));
+    }
     VkPushConstantRange pcr{VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, 0, (uint32_t)sc.pushConstants.size()};
-    VkPipelineLayoutCreateInfo pli{VK_STRUCTURE_TYPE_PIPELINE_LAYOUT_CREATE_INFO, nullptr, 0, 1, &setLayout, sc.pushConstants.empty() ? 0u : 1u, sc.pushConstants.empty() ? nullptr : &pcr};
+    VkPipelineLayoutCreateInfo pli{VK_STRUCTURE_TYPE_PIPELINE_LAYOUT_CREATE_INFO, nullptr, 0, nSets, setLayouts.data(), sc.pushConstants.empty() ? 0u : 1u, sc.pushConstants.empty() ? nullptr : &pcr};
     VkPipelineLayout pipeLayout; VK(vkCreatePipelineLayout(app.device, &pli, nullptr, &pipeLayout));
     // init_renderpass (loadOp CLEAR / storeOp STORE) + init_framebuffers
     std::vector<VkAttachmentDescription> atts;
@@ -334,31 +343,31 @@ int main(int argc, char** argv) {
     // init_descriptor_pool / init_descriptor_set
     VkDescriptorPoolSize ps[6] = {{VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 8}, {VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 8}, {VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, 8},
                                   {VK_DESCRIPTOR_TYPE_SAMPLED_IMAGE, 8}, {VK_DESCRIPTOR_TYPE_SAMPLER, 8}, {VK_DESCRIPTOR_TYPE_INPUT_ATTACHMENT, 8}};
-    VkDescriptorPoolCreateInfo dpi{VK_STRUCTURE_TYPE_DESCRIPTOR_POOL_CREATE_INFO, nullptr, 0, 1, 6, ps};
+    VkDescriptorPoolCreateInfo dpi{VK_STRUCTURE_TYPE_DESCRIPTOR_POOL_CREATE_INFO, nullptr, 0, nSets, 6, ps};
     VkDescriptorPool dpool; VK(vkCreateDescriptorPool(app.device, &dpi, nullptr, &dpool));
-    VkDescriptorSetAllocateInfo dsa{VK_STRUCTURE_TYPE_DESCRIPTOR_SET_ALLOCATE_INFO, nullptr, dpool, 1, &setLayout};
-    VkDescriptorSet dset; VK(vkAllocateDescriptorSets(app.device, &dsa, &dset));
+    VkDescriptorSetAllocateInfo dsa{VK_STRUCTURE_TYPE_DESCRIPTOR_SET_ALLOCATE_INFO, nullptr, dpool, nSets, setLayouts.data()};
+    std::vector<VkDescriptorSet> dsets(nSets); VK(vkAllocateDescriptorSets(app.device, &dsa, dsets.data()));
     std::vector<VkDescriptorBufferInfo> binfos(sc.uniforms.size()); std::vector<VkDescriptorImageInfo> iinfos(sc.textures.size() * 2); std::vector<VkWriteDescriptorSet> writes;
     for (size_t i = 0; i < sc.uniforms.size(); i++) {
         const bool dyn = sc.uniforms[i].dynRange != 0; // dynamic_uniform.cpp:196-215: the descriptor covers one element, the offset picks it at bind time
         binfos[i] = {bufs.at(sc.uniforms[i].name), 0, dyn ? (VkDeviceSize)sc.uniforms[i].dynRange : sc.buffers.at(sc.uniforms[i].name).size};
-        writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, sc.uniforms[i].binding, 0, 1, dyn ? VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC : VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, nullptr, &binfos[i], nullptr});
+        writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dsets[sc.uniforms[i].set], sc.uniforms[i].binding, 0, 1, dyn ? VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC : VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, nullptr, &binfos[i], nullptr});
     }
     for (size_t i = 0; i < sc.textures.size(); i++) {
         auto& t = sc.textures[i];
         const VkSampler written = t.immutableSampler ? VkSampler(VK_NULL_HANDLE) : texObjs[i].sampler; // immutable: image_info.sampler = 0 (immutable_sampler.cpp:106)
         if (t.inputAttachment) {
             iinfos[2 * i] = {VK_NULL_HANDLE, texObjs[i].view, VK_IMAGE_LAYOUT_SHADER_READ_ONLY_OPTIMAL};
-            writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, t.binding, 0, 1, VK_DESCRIPTOR_TYPE_INPUT_ATTACHMENT, &iinfos[2 * i], nullptr, nullptr});
+            writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dsets[t.set], t.binding, 0, 1, VK_DESCRIPTOR_TYPE_INPUT_ATTACHMENT, &iinfos[2 * i], nullptr, nullptr});
         } else if (t.samplerBinding < 0) {
             iinfos[2 * i] = {written, texObjs[i].view, VK_IMAGE_LAYOUT_SHADER_READ_ONLY_OPTIMAL};
-            writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, t.binding, 0, 1, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, &iinfos[2 * i], nullptr, nullptr});
+            writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dsets[t.set], t.binding, 0, 1, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, &iinfos[2 * i], nullptr, nullptr});
         } else { // separate_image_sampler.cpp:114-125: image_info.sampler = 0 for the texture, a second info for the sampler
             iinfos[2 * i] = {VK_NULL_HANDLE, texObjs[i].view, VK_IMAGE_LAYOUT_SHADER_READ_ONLY_OPTIMAL};
-            writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, t.binding, 0, 1, VK_DESCRIPTOR_TYPE_SAMPLED_IMAGE, &iinfos[2 * i], nullptr, nullptr});
+            writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dsets[t.set], t.binding, 0, 1, VK_DESCRIPTOR_TYPE_SAMPLED_IMAGE, &iinfos[2 * i], nullptr, nullptr});
             if (!t.immutableSampler) {
                 iinfos[2 * i + 1] = {texObjs[i].sampler, VK_NULL_HANDLE, VK_IMAGE_LAYOUT_UNDEFINED};
-                writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, (uint32_t)t.samplerBinding, 0, 1, VK_DESCRIPTOR_TYPE_SAMPLER, &iinfos[2 * i + 1], nullptr, nullptr});
+                writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dsets[t.set], (uint32_t)t.samplerBinding, 0, 1, VK_DESCRIPTOR_TYPE_SAMPLER, &iinfos[2 * i + 1], nullptr, nullptr});
             }
         }
     }
@@ -367,7 +376,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < sc.texelBuffers.size(); i++) {
         VkBufferViewCreateInfo bvi{VK_STRUCTURE_TYPE_BUFFER_VIEW_CREATE_INFO, nullptr, 0, bufs.at(sc.texelBuffers[i].name), (VkFormat)sc.texelBuffers[i].format, 0, sc.buffers.at(sc.texelBuffers[i].name).size};
         VK(vkCreateBufferView(app.device, &bvi, nullptr, &bufferViews[i]));
-        writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dset, sc.texelBuffers[i].binding, 0, 1, VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, nullptr, nullptr, &bufferViews[i]});
+        writes.push_back({VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET, nullptr, dsets[sc.texelBuffers[i].set], sc.texelBuffers[i].binding, 0, 1, VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER, nullptr, nullptr, &bufferViews[i]});
     }
     vkUpdateDescriptorSets(app.device, (uint32_t)writes.size(), writes.data(), 0, nullptr);
     // init_shaders (SPIR-V words exported by Python; the samples run glslang here) + init_pipeline
@@ -438,10 +447,15 @@ int main(int argc, char** argv) {
         VK(vkBeginCommandBuffer(rec, &sbeg));
     }
     vkCmdBindPipeline(rec, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeline);
-    std::vector<uint32_t> dynOffsets; // in binding order, as the API defines for dynamic descriptors of one set
-    { std::vector<std::pair<uint32_t, uint32_t>> byBinding; for (auto& u : sc.uniforms) if (u.dynRange) byBinding.push_back({u.binding, u.dynOffset});
-      std::sort(byBinding.begin(), byBinding.end()); for (auto& kv : byBinding) dynOffsets.push_back(kv.second); }
-    vkCmdBindDescriptorSets(rec, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeLayout, 0, 1, &dset, (uint32_t)dynOffsets.size(), dynOffsets.empty() ? nullptr : dynOffsets.data());
+    // one vkCmdBindDescriptorSets per set (firstSet = the set number, Binding.cpp:58-80), each with its own dynamic offsets in
+    // binding order, as the API defines for the dynamic descriptors of a set
+    for (uint32_t k = 0; k < nSets; k++) {
+        std::vector<std::pair<uint32_t, uint32_t>> byBinding;
+        for (auto& u : sc.uniforms) if (u.dynRange && u.set == k) byBinding.push_back({u.binding, u.dynOffset});
+        std::sort(byBinding.begin(), byBinding.end());
+        std::vector<uint32_t> dynOffsets; for (auto& kv : byBinding) dynOffsets.push_back(kv.second);
+        vkCmdBindDescriptorSets(rec, VK_PIPELINE_BIND_POINT_GRAPHICS, pipeLayout, k, 1, &dsets[k], (uint32_t)dynOffsets.size(), dynOffsets.empty() ? nullptr : dynOffsets.data());
+    }
     if (!sc.pushConstants.empty()) vkCmdPushConstants(rec, pipeLayout, VK_SHADER_STAGE_VERTEX_BIT | VK_SHADER_STAGE_FRAGMENT_BIT, 0, (uint32_t)sc.pushConstants.size(), sc.pushConstants.data());
     for (auto& kv : sc.vertexBuffers) { VkDeviceSize off = 0; VkBuffer b = bufs.at(kv.second); vkCmdBindVertexBuffers(rec, kv.first, 1, &b, &off); }
     VkViewport vp{sc.viewport[0], sc.viewport[1], sc.viewport[2], sc.viewport[3], sc.viewport[4], sc.viewport[5]};

@@ -359,6 +359,33 @@ def draw_textured_cube(width=500, height=500, filt=NEAREST):
     return s
 
 
+def multiple_sets(width=500, height=500, filt=LINEAR):
+    """Samples/multiple_sets: the textured cube with its uniform buffer in descriptor set 0 and its sampler in set 1, binding 0
+    (two set layouts, one vkCmdBindDescriptorSets per set through the ICD)."""
+    s = draw_textured_cube(width, height, filt)
+    s.name = "multiple_sets_%dx%d" % (width, height)
+    s.fs = "multisets.frag"
+    t = s.textures[0]
+    s.textures = [Texture(0, t.image, filt, CLAMP_TO_EDGE, set_=1)]
+    return s
+
+
+def ubo_arrays(width=500, height=500):
+    """The coloured cube with a second uniform buffer, in descriptor set 1, that holds std140 arrays: vec4 tint[4] (indexed
+    dynamically) and float scale[3] whose ArrayStride (16) is four times its element size."""
+    s = draw_cube(width, height)
+    s.name = "ubo_arrays_%dx%d" % (width, height)
+    s.vs = "uboarray.vert"
+    rng = np.random.RandomState(99)
+    params = np.zeros(28, dtype=np.float32)                    # 4 x vec4, then 3 floats at a stride of 4 floats
+    params[0:16] = rng.uniform(0.2, 1.0, 16)
+    params[16:28] = rng.uniform(-9.0, 9.0, 12)                 # the padding lanes hold garbage a wrong stride would pick up
+    params[16], params[20], params[24] = 0.03, 0.07, 0.11      # scale[0..2]
+    s.buffers["params"] = params.view(np.uint8).reshape(-1)
+    s.uniforms = [(0, 0, "ubo"), (1, 0, "params")]
+    return s
+
+
 def separate_image_sampler(width=500, height=500, filt=LINEAR, immutable=False):
     """Samples/separate_image_sampler: the textured cube with `texture2D tex` at binding 1 and `sampler samp` at binding 2,
     combined in the shader by OpSampledImage (sampler2D(tex, samp)); the fragment shader also darkens a 1 % border."""

@@ -149,3 +149,15 @@ def test_icd_dynamic_uniform_offset(built, tmp_path):
     oc, _, _ = scenes.run_oracle(scenes.draw_cube(200, 160))
     gc, _, _ = scenes.run_icd(sc, str(tmp_path))
     assert np.array_equal(oc, gc), "the dynamic offset must select the same matrix the plain cube uses"
+
+
+def test_icd_multiple_descriptor_sets(built, tmp_path):
+    """Samples/multiple_sets: the uniform buffer in set 0, the sampler in set 1 — two set layouts in the pipeline layout, one
+    vkCmdBindDescriptorSets per set with firstSet = its number (Binding.cpp:58-80, LoadUniforms Draw.cpp:356-408)."""
+    check(scenes.multiple_sets(filt=scenes.LINEAR), tmp_path)
+
+
+def test_icd_uniform_arrays_in_a_second_set(built, tmp_path):
+    """A second uniform buffer in set 1 with std140 arrays (vec4[4] indexed dynamically, float[3] at ArrayStride 16:
+    SPIRVCompiler.cpp:104-184)."""
+    check(scenes.ubo_arrays(), tmp_path)

@@ -851,3 +851,25 @@ def test_srgb_unpack_and_pack_against_numpy(oracle):
     # round trip of every code is the identity
     back = pack_raw(oracle, 43, 4, got).reshape(-1, 4)
     assert np.array_equal(back, raw.reshape(-1, 4))
+
+
+def test_uniform_arrays_with_std140_stride_against_premultiplied_colours(oracle):
+    """uboarray.vert computes outColor = inColor * p.tint[int(inColor.x * 3.99)] + vec4(p.scale[2]) from a uniform block in
+    descriptor set 1 whose float array has ArrayStride 16. The same frame must come out of the plain cube shaders when the host
+    applies that formula to the vertex colours beforehand (float32, one rounding per operation) — which pins the array stride,
+    the dynamic index and the second descriptor set of the interpreter without reference to its own addressing code."""
+    f = np.float32
+    sc = scenes.ubo_arrays(160, 120)
+    got, gd, st = scenes.run_oracle(sc)
+    params = sc.buffers["params"].view(np.float32)
+    tint = params[0:16].reshape(4, 4); scale2 = params[24]
+    pre = scenes.draw_cube(160, 120)
+    vb = pre.buffers["vb"].view(np.float32).reshape(-1, 8).copy()
+    col = vb[:, 4:8]
+    idx = np.trunc((col[:, 0] * f(3.99)).astype(np.float32)).astype(np.int64)
+    vb[:, 4:8] = ((col * tint[idx]).astype(np.float32) + scale2).astype(np.float32)
+    pre.buffers["vb"] = vb.view(np.uint8).reshape(-1)
+    want, wd, st2 = scenes.run_oracle(pre)
+    assert st.fragmentsCovered == st2.fragmentsCovered > 500
+    assert np.array_equal(got, want) and np.array_equal(gd, wd)
+    assert len(set(idx.tolist())) >= 2  # the dynamic index really varies over the vertices

@@ -788,3 +788,10 @@ def test_unorm8_decode_all_codes(dev):
     for c in range(4):
         assert np.array_equal(got[:, c].view(np.uint32), want.view(np.uint32)), "channel %d" % c
     dev.free(sa); dev.free(da)
+
+
+def test_multiple_descriptor_sets_and_uniform_arrays(dev):
+    """f3: resources spread over descriptor sets 0 and 1 (Samples/multiple_sets), and a uniform block with std140 arrays whose
+    stride exceeds the element size, one of them indexed dynamically."""
+    compare(dev, scenes.multiple_sets(200, 150, filt=scenes.LINEAR))
+    compare(dev, scenes.ubo_arrays(200, 150))

@@ -95,6 +95,8 @@ FRONT_END_SCENES = {
     "builtins": lambda: _with_vs(scenes.random_points_lines(width=32, height=32, count=4, topology=scenes.POINT_LIST), "builtins.vert"),
     "lines": lambda: scenes.random_points_lines(width=32, height=32, count=4, topology=scenes.LINE_STRIP),
     "texel_buffer": lambda: scenes.texel_buffer(32, 32),
+    "multiple_sets": lambda: scenes.multiple_sets(64, 64),
+    "ubo_arrays": lambda: scenes.ubo_arrays(64, 64),
 }
 
 
