@@ -3,12 +3,19 @@
 // TEST INFRASTRUCTURE ONLY. May be used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs — as the checker, never as the thing shipped. The product path (libcpvk_cuda.so)
 // never links or calls this.
-// PARITY: the reference has no tests, golden vectors or published outputs for this path and the ICD
-// cannot be built in this image (LLVM-8, Vulkan SDK, GSL, glm: SURVEY F10). What the reference CAN execute here — its
-// format table / image layout / half codec, its texture sampler and its SPIR-V reader, compiled in place into
-// oracle/_ref/ — pins oracle_formats.h and oracle_sampler.h bit for bit (tests/test_reference_*.py, tests/golden/).
-// The draw control flow in THIS file (IA, setup, coverage, interpolation, late depth/stencil, blend) remains PARITY
-// UNPINNED: it is held only by the reference source it follows and by the independent KATs in tests/test_oracle_kats.py.
+// PARITY: the reference has no tests, golden vectors or published outputs for this path and the ICD cannot
+// be built in this image (LLVM-8, Vulkan SDK, GSL, glm >= 0.9.9: SURVEY F10). What of the reference CAN execute here is compiled
+// in place into oracle/_ref/ and pins this oracle bit for bit (tests/test_reference_*.py, fixtures under tests/golden/):
+//   draw_check    CommandBuffer.Draw.cpp's own EdgeFunction, CalculatePrimitives, SetDatum, GetFragmentInput, DrawPixel, ProcessPoints,
+//                 ProcessLines, ProcessTriangles (fragment streams of 33 draws, 137 612 fragments) and ApplyBlendFactor / ApplyBlend
+//                 (5 050 states)  -> ProcessTriangles / ProcessLines / ProcessPoints / Fragment()'s interpolation / ApplyBlend below
+//   math_check    SpirvFunctions.cpp + the GLSL.std.450 templates of GlslFunctions.cpp -> oracle_spirv.h's dot / matrix / GLSL code
+//   sampler_check ImageSampler.cpp -> oracle_sampler.h        formats_check  Formats.cpp + FloatFormat.h -> oracle_formats.h
+//   spirv_check   SPIRVParser/ -> the hand-assembled shaders
+// NOT pinned by execution (the reference emits them as LLVM IR, which needs LLVM to run): the late depth / stencil epilogue and
+// attachment write of the fragment wrapper (PipelineCompiler.cpp) and the per-format UNORM / SNORM / sRGB pack / unpack arithmetic
+// (ImageCompiler.cpp) — held by the independent numpy KATs in tests/test_oracle_kats.py. glm: the checkers link the 0.9.5.3 copy
+// vendored with the reference; min / max with NaN or +-0 and normalize(vec4) follow glm >= 0.9.9 here.
 //
 // Follows, in execution order:
 //   CPVulkan/CommandBuffer.Draw.cpp:675-760  ProcessInputAssembler[Indexed]          (IA)
