@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan(CpvkBinArgs a) {
     if (threadIdx.x == 0) {
         const cpvk_u32 total = warpSums[31], longest = maxShared;
         a.offsets[tiles] = total; a.meta[0] = total; a.meta[1] = longest;
-        const bool fits = total <= a.planCapacity && (longest <= CPVK_CHUNK || longest <= a.planSortCap) && (a.meta[2] == 0 || a.planLargeCounted != 0);
+        const bool fits = total <= a.planCapacity && (longest <= CPVK_ORDER_MAX || longest <= a.planSortCap) && (a.meta[2] == 0 || a.planLargeCounted != 0);
         a.meta[3] = fits ? 0u : 1u;
         if (a.metaHost) { // the host reads the answers from here after an event / stream sync: no copy in the stream
             a.metaHost[0] = total; a.metaHost[1] = longest; a.metaHost[2] = a.meta[2]; a.metaHost[3] = fits ? 0u : 1u;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan(CpvkBinArgs a) {
 __global__ void __launch_bounds__(256) k_bin_sort(CpvkBinArgs a, cpvk_u32 capacity) {
     extern __shared__ cpvk_u32 sKeys[];
     const cpvk_u32 t = blockIdx.x;
-    if (a.meta[3] != 0 || a.meta[1] <= CPVK_CHUNK) return; // plan mismatch, or every list fits one raster chunk (ordered there)
+    if (a.meta[3] != 0 || a.meta[1] <= CPVK_ORDER_MAX) return; // plan mismatch, or every list is short enough to be ordered inside k_raster
     const cpvk_u32 begin = a.offsets[t], n = a.offsets[t + 1] - begin;
     if (n < 2) return;
     cpvk_u32* list = a.lists + begin;

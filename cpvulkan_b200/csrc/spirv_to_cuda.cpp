@@ -118,6 +118,33 @@ void Parse(Module& m, const CpvkShaderStage& stage, uint32_t model) {
         const uint32_t wc = w[i] >> 16, op = w[i] & 0xFFFF;
         if (wc == 0 || i + wc > n) throw Malformed("truncated instruction");
         const uint32_t* o = w + i + 1;
+        // operands are only read after their presence was checked (a truncated or malformed module from the application is an
+        // error, CPVK_E_SPIRV, not an out-of-bounds read), and every id a type refers to must lie below the module's bound
+        auto need = [&](uint32_t words) { if (wc < words) throw Malformed("instruction too short"); };
+        switch (op) {
+        case OpExtInstImport: case OpDecorate: case OpTypePointer: case OpTypeArray: need(4); break;
+        case OpEntryPoint: case OpMemberDecorate: need(5); break;
+        case OpTypeInt: case OpTypeVector: case OpTypeMatrix: need(4); break;
+        case OpTypeFloat: case OpTypeSampledImage: case OpTypeRuntimeArray: case OpTypeFunction: case OpUndef: case OpFunctionParameter: need(3); break;
+        case OpTypeImage: need(9); break;
+        case OpTypeVoid: case OpTypeBool: case OpTypeSampler: case OpTypeStruct: case OpLabel: need(2); break;
+        case OpConstantTrue: case OpConstantFalse: case OpConstantNull: case OpSpecConstantTrue: case OpSpecConstantFalse: case OpConstantComposite: case OpSpecConstantComposite: need(3); break;
+        case OpConstant: case OpSpecConstant: case OpVariable: need(4); break;
+        case OpFunction: need(5); break;
+        default: break;
+        }
+        switch (op) {
+        case OpTypeVector: case OpTypeMatrix: case OpTypeImage: case OpTypeSampledImage: case OpTypeRuntimeArray: case OpTypeFunction: checkId(o[1]); break;
+        case OpTypeArray: checkId(o[1]); checkId(o[2]); break;
+        case OpTypePointer: checkId(o[2]); break;
+        case OpTypeStruct: for (uint32_t k = 1; k + 1 < wc; k++) checkId(o[k]); break;
+        case OpConstant: case OpSpecConstant: case OpConstantTrue: case OpConstantFalse: case OpConstantNull: case OpSpecConstantTrue: case OpSpecConstantFalse:
+        case OpConstantComposite: case OpSpecConstantComposite: case OpUndef: case OpVariable: case OpFunction: case OpFunctionParameter: checkId(o[0]); break;
+        case OpMemberDecorate: case OpLabel: checkId(o[0]); break;
+        default: break;
+        }
+        if (op == OpTypeFunction) for (uint32_t k = 2; k + 1 < wc; k++) checkId(o[k]);
+        if (op == OpConstantComposite || op == OpSpecConstantComposite) for (uint32_t k = 2; k + 1 < wc; k++) checkId(o[k]);
         switch (op) {
         case OpExtInstImport: if (std::string(reinterpret_cast<const char*>(o + 1)) == "GLSL.std.450") m.glsl = o[0]; break;
         case OpEntryPoint: if (o[0] == model && entryName == reinterpret_cast<const char*>(o + 2)) m.entry = o[1]; break;
@@ -163,7 +190,7 @@ void Parse(Module& m, const CpvkShaderStage& stage, uint32_t model) {
                 Inst in{};
                 in.op = (uint16_t)op;
                 if (noResult) { in.ops = o; in.nops = wc - 1; }
-                else { if (wc < 3) throw Malformed("instruction too short"); in.type = o[0]; in.result = checkId(o[1]); in.ops = o + 2; in.nops = wc - 3; m.idType[in.result] = in.type; }
+                else { if (wc < 3) throw Malformed("instruction too short"); in.type = checkId(o[0]); in.result = checkId(o[1]); in.ops = o + 2; in.nops = wc - 3; m.idType[in.result] = in.type; }
                 blk->insts.push_back(in);
             }
             break;

@@ -218,7 +218,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     const cpvk_u32 tx = blockIdx.x, tyr = blockIdx.y, tile = tyr * p.tilesX + tx; // grid = (tilesX, tilesY): no division to find the tile
     const bool triangles = cpvk_prim_vertices() == 3; // points and lines are not binned: every tile walks all of them (below)
     if (triangles && p.binMeta[3] != 0) return; // the speculative launch plan did not fit this draw: the host replays it
-    const bool listsSorted = triangles && p.binMeta[1] > CPVK_CHUNK;
+    const bool listsSorted = triangles && p.binMeta[1] > CPVK_ORDER_MAX;
     const cpvk_u32 listBegin = triangles ? p.tileOffsets[tile] : 0u, listEnd = triangles ? p.tileOffsets[tile + 1] : 1u;
     const cpvk_u32 lazyMask = p.lazyMask;
     const int tileX0 = (int)tx * CPVK_TILE_W, tileY0 = (int)(tyr + p.tileRow0) * CPVK_TILE_H;
@@ -277,11 +277,13 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
         sYf[j] = ((float)(tileY0 + j) / H + hp) * 2.0f - 1.0f;
     }
     sLut[threadIdx.x] = cpvk_unorm8(threadIdx.x); // == (float)k / 255.0f for every k; CPVK_RASTER_THREADS == 256
-    // Unsorted lists always fit one chunk (the host sorts otherwise): fetch this tile's ids now so the load overlaps tile
-    // staging, and park them where the ranking pass below expects them — the staging barrier then covers both.
-    cpvk_u32 firstKey = 0xFFFFFFFFu;
+    // Unsorted lists hold at most CPVK_ORDER_MAX ids (the host sorts otherwise), two per thread: fetch them now so the load
+    // overlaps tile staging, and park them where the ordering pass below expects them — the staging barrier then covers both.
+    cpvk_u32 keyA = 0xFFFFFFFFu, keyB = 0xFFFFFFFFu;
     if (triangles && !listsSorted) {
-        if (threadIdx.x < listEnd - listBegin) firstKey = __ldg(p.tileLists + listBegin + threadIdx.x);
+        const cpvk_u32 nList = listEnd - listBegin;
+        if (threadIdx.x < nList) keyA = __ldg(p.tileLists + listBegin + threadIdx.x);
+        if (threadIdx.x + CPVK_CHUNK < nList) keyB = __ldg(p.tileLists + listBegin + CPVK_CHUNK + threadIdx.x);
     }
     // ---- stage the tile: HBM -> shared, or the packed clear value when a deferred clear is folded into this draw ----
     if (dsUsed) {
@@ -307,9 +309,9 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                                p.color[a].rowPitch, (cpvk_u32)tw * cTexel[a], (cpvk_u32)th, cTexel[a] * CPVK_TILE_W);
         }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // warp region (16 wide, 8 tall) clipped to the tile extent
-    const int rx0 = tileX0 + (warp & 1) * 16, ry0 = tileY0 + (warp >> 1) * 8;
-    const int rx1 = min(rx0 + 16, x1), ry1 = min(ry0 + 8, y1);
+    // warp region (CPVK_REGION_W wide, CPVK_REGION_H tall) clipped to the tile extent
+    const int rx0 = tileX0 + (warp & 1) * CPVK_REGION_W, ry0 = tileY0 + (warp >> 1) * CPVK_REGION_H;
+    const int rx1 = min(rx0 + CPVK_REGION_W, x1), ry1 = min(ry0 + CPVK_REGION_H, y1);
     cpvk_u32 nCov = 0, nPass = 0;
 
     // Shared-memory scratch after the tiles: the staged triangle chunk (six uint4 planes of the setup records + bboxes,
@@ -319,16 +321,17 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     cpvk_u8* sHit = cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + warp * CPVK_CHUNK; // [warps][CPVK_CHUNK] chunk-local ids
     unsigned short* sFrag = reinterpret_cast<unsigned short*>(cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * CPVK_CHUNK)
                             + warp * CPVK_FRAG_CAP;                                                  // [warps][CPVK_FRAG_CAP]
-    cpvk_u32* sSorted = reinterpret_cast<cpvk_u32*>(cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * CPVK_CHUNK); // [CPVK_CHUNK], aliases sFrag (idle until the chunk is staged)
     cpvk_u8* sMask = cpvk_smem + smemOff + 6 * CPVK_CHUNK * 16 + CPVK_CHUNK * 8 + (CPVK_RASTER_THREADS / 32) * (CPVK_CHUNK + CPVK_FRAG_CAP * 2); // [CPVK_CHUNK] warp regions a bbox meets
+    cpvk_u32* sSorted = reinterpret_cast<cpvk_u32*>(sMask + CPVK_CHUNK); // [CPVK_ORDER_MAX] the tile's whole list in API order, read chunk by chunk
     // Ordering scratch (aliases the setup planes, idle until the chunk is staged): a bitmap of the ids present in this tile's
     // list relative to the lowest one, the warps' lowest / highest ids, the warps' bit counts.
     cpvk_u32* sBits = reinterpret_cast<cpvk_u32*>(sQ);   // [CPVK_ORDER_BITS / 32]
     cpvk_u32* sRange = sBits + CPVK_ORDER_BITS / 32;     // [0..8) lowest id per warp, [8..16) highest, [16..24) set bits per warp
     if (triangles && !listsSorted) {
-        reinterpret_cast<cpvk_u32*>(sBB)[threadIdx.x] = firstKey; // sKeys of the ranking pass (fallback)
+        reinterpret_cast<cpvk_u32*>(sBB)[threadIdx.x] = keyA; reinterpret_cast<cpvk_u32*>(sBB)[CPVK_CHUNK + threadIdx.x] = keyB; // sKeys of the ranking pass (fallback): CPVK_ORDER_MAX words = the bbox plane
         reinterpret_cast<uint4*>(sBits)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u); // CPVK_ORDER_BITS == 128 bits per thread
-        const cpvk_u32 mn = __reduce_min_sync(0xFFFFFFFFu, firstKey), mx = __reduce_max_sync(0xFFFFFFFFu, firstKey == 0xFFFFFFFFu ? 0u : firstKey);
+        const cpvk_u32 mn = __reduce_min_sync(0xFFFFFFFFu, min(keyA, keyB));
+        const cpvk_u32 mx = __reduce_max_sync(0xFFFFFFFFu, max(keyA == 0xFFFFFFFFu ? 0u : keyA, keyB == 0xFFFFFFFFu ? 0u : keyB));
         if (lane == 0) { sRange[warp] = mn; sRange[8 + warp] = mx; }
     }
     __syncthreads(); // tile, pixel centres, lut and the unsorted ids are staged
@@ -540,8 +543,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                 const int bx0 = __float_as_int(r[19]), by0 = __float_as_int(r[20]), bx1 = __float_as_int(r[21]), by1 = __float_as_int(r[22]);
                 if (!(bx0 < rx1 && bx1 > rx0 && by0 < ry1 && by1 > ry0)) continue; // warp-uniform
                 #pragma unroll 1
-                for (int k = 0; k < 4; k++) {
-                    const int x = rx0 + (lane & 15), y = ry0 + (lane >> 4) + 2 * k;
+                for (int k = 0; k < CPVK_REGION_W * CPVK_REGION_H / 32; k++) { // 32 pixels of the region per step: whole rows of it
+                    const int x = rx0 + (lane & (CPVK_REGION_W - 1)), y = ry0 + lane / CPVK_REGION_W + (32 / CPVK_REGION_W) * k;
                     bool covered = x >= bx0 && x < bx1 && y >= by0 && y < by1 && x < rx1 && y < ry1;
                     float t = 0.0f;
                     if (covered) {
@@ -596,19 +599,21 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     #pragma unroll 1
     for (cpvk_u32 chunkBase = listBegin; triangles && chunkBase < listEnd; chunkBase += CPVK_CHUNK) {
         const int n = (int)min((cpvk_u32)CPVK_CHUNK, listEnd - chunkBase);
-        if (!listsSorted) {
-            // Binning claims list slots with atomics, so a tile's ids arrive in arbitrary order. When every list fits one chunk
-            // the host skips k_bin_sort and the tile orders its own list here (ids are unique; ascending id = API order).
+        if (!listsSorted && chunkBase == listBegin) {
+            // Binning claims list slots with atomics, so a tile's ids arrive in arbitrary order. Lists of up to CPVK_ORDER_MAX ids
+            // are ordered here, once, before the first chunk is staged (ids are unique; ascending id = API order); the host runs
+            // k_bin_sort only for longer ones.
             // Usual case — the ids of a tile lie within CPVK_ORDER_BITS of each other (any draw of fewer primitives, any mesh
             // with some locality): every id sets its bit in a shared-memory bitmap, each thread counts the bits of its 128-bit
-            // slice, a block-wide prefix sum gives the slice's first position, and the slice's ids are written out in order:
-            // a few dozen instructions per thread instead of one compare per pair of ids.
+            // slice, a block-wide prefix sum gives the slice's first position, and the slices are written out in order.
+            const int nAll = (int)(listEnd - listBegin);
             const uint4 mnA = reinterpret_cast<const uint4*>(sRange)[0], mnB = reinterpret_cast<const uint4*>(sRange)[1];
             const uint4 mxA = reinterpret_cast<const uint4*>(sRange)[2], mxB = reinterpret_cast<const uint4*>(sRange)[3];
             const cpvk_u32 lo = min(min(min(mnA.x, mnA.y), min(mnA.z, mnA.w)), min(min(mnB.x, mnB.y), min(mnB.z, mnB.w)));
             const cpvk_u32 hi = max(max(max(mxA.x, mxA.y), max(mxA.z, mxA.w)), max(max(mxB.x, mxB.y), max(mxB.z, mxB.w)));
             if (hi - lo < (cpvk_u32)CPVK_ORDER_BITS) { // block-uniform
-                if (firstKey != 0xFFFFFFFFu) atomicOr(sBits + ((firstKey - lo) >> 5), 1u << ((firstKey - lo) & 31u));
+                if (keyA != 0xFFFFFFFFu) atomicOr(sBits + ((keyA - lo) >> 5), 1u << ((keyA - lo) & 31u));
+                if (keyB != 0xFFFFFFFFu) atomicOr(sBits + ((keyB - lo) >> 5), 1u << ((keyB - lo) & 31u));
                 __syncthreads();
                 const uint4 bits = reinterpret_cast<const uint4*>(sBits)[threadIdx.x];
                 const cpvk_u32 cnt = (cpvk_u32)(__popc(bits.x) + __popc(bits.y)) + (cpvk_u32)(__popc(bits.z) + __popc(bits.w));
@@ -638,22 +643,25 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                 // ids too far apart for the bitmap: each id's rank (number of ids <= it, minus one) is its position. Broadcast
                 // shared-memory reads, no barriers inside the loop.
                 const cpvk_u32* sKeys = reinterpret_cast<const cpvk_u32*>(sBB);  // staged before the first barrier; reused before the bboxes are staged
-                const cpvk_u32 key = firstKey;
-                if ((int)threadIdx.x < n) {
-                    cpvk_u32 rank = 0xFFFFFFFFu;
-                    const uint4* k4 = reinterpret_cast<const uint4*>(sKeys);
-                    // rank += (v <= key): the carry of key - v (set when there is no borrow, i.e. v <= key) is added straight
-                    // into the rank, 1.5 instructions per key. The key itself is counted once, hence the start value -1.
-                    #define CPVK_RANK_STEP(v) asm("{ .reg .u32 t; sub.cc.u32 t, %2, %1; addc.u32 %0, %0, 0; }" : "+r"(rank) : "r"(v), "r"(key))
-                    for (int j = 0; j < (n + 3) / 4; j++) { const uint4 v = k4[j]; CPVK_RANK_STEP(v.x); CPVK_RANK_STEP(v.y); CPVK_RANK_STEP(v.z); CPVK_RANK_STEP(v.w); }
-                    #undef CPVK_RANK_STEP
-                    sSorted[rank] = key;
+                const uint4* k4 = reinterpret_cast<const uint4*>(sKeys);
+                // rank += (v <= key): the carry of key - v (set when there is no borrow, i.e. v <= key) is added straight
+                // into the rank, 1.5 instructions per pair. The key itself is counted once, hence the start value -1; the unused
+                // slots hold 0xFFFFFFFF and count for no real key.
+                #define CPVK_RANK_STEP(rk, v, key) asm("{ .reg .u32 t; sub.cc.u32 t, %2, %1; addc.u32 %0, %0, 0; }" : "+r"(rk) : "r"(v), "r"(key))
+                cpvk_u32 rankA = 0xFFFFFFFFu, rankB = 0xFFFFFFFFu;
+                for (int j = 0; j < (nAll + 3) / 4; j++) {
+                    const uint4 v = k4[j];
+                    CPVK_RANK_STEP(rankA, v.x, keyA); CPVK_RANK_STEP(rankA, v.y, keyA); CPVK_RANK_STEP(rankA, v.z, keyA); CPVK_RANK_STEP(rankA, v.w, keyA);
+                    if (nAll > CPVK_CHUNK) { CPVK_RANK_STEP(rankB, v.x, keyB); CPVK_RANK_STEP(rankB, v.y, keyB); CPVK_RANK_STEP(rankB, v.z, keyB); CPVK_RANK_STEP(rankB, v.w, keyB); }
                 }
+                #undef CPVK_RANK_STEP
+                if (keyA != 0xFFFFFFFFu) sSorted[rankA] = keyA;
+                if (keyB != 0xFFFFFFFFu) sSorted[rankB] = keyB;
             }
             __syncthreads();
         }
         cpvk_u32 stagedPrim = 0;
-        if ((int)threadIdx.x < n) stagedPrim = listsSorted ? __ldg(p.tileLists + chunkBase + threadIdx.x) : sSorted[threadIdx.x];
+        if ((int)threadIdx.x < n) stagedPrim = listsSorted ? __ldg(p.tileLists + chunkBase + threadIdx.x) : sSorted[(chunkBase - listBegin) + threadIdx.x];
         if ((int)threadIdx.x < n) { // CPVK_CHUNK == blockDim.x: one record per thread, 16-byte coalesced pieces
             const uint4* sp = reinterpret_cast<const uint4*>(p.setups + stagedPrim);
             #pragma unroll
@@ -665,9 +673,9 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             const int bx0 = (short)(b.x & 0xFFFFu), by0 = (short)(b.x >> 16), bx1 = (short)(b.y & 0xFFFFu), by1 = (short)(b.y >> 16);
             cpvk_u32 xb = 0, m = 0;
             #pragma unroll
-            for (int wx = 0; wx < 2; wx++) { const int a = tileX0 + wx * 16; if (bx0 < min(a + 16, x1) && bx1 > a) xb |= 1u << wx; }
+            for (int wx = 0; wx < 2; wx++) { const int a = tileX0 + wx * CPVK_REGION_W; if (bx0 < min(a + CPVK_REGION_W, x1) && bx1 > a) xb |= 1u << wx; }
             #pragma unroll
-            for (int wy = 0; wy < 4; wy++) { const int a = tileY0 + wy * 8; if (by0 < min(a + 8, y1) && by1 > a) m |= xb << (2 * wy); }
+            for (int wy = 0; wy < 4; wy++) { const int a = tileY0 + wy * CPVK_REGION_H; if (by0 < min(a + CPVK_REGION_H, y1) && by1 > a) m |= xb << (2 * wy); }
             sMask[threadIdx.x] = (cpvk_u8)m;
         }
         __syncthreads();
@@ -721,7 +729,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                         // hoists the row terms out of the pixel loop. A row's results are collected at the warp-uniform bit
                         // xx, trimmed to the lane's own width and appended at yy * cw, so candidate numbering stays
                         // row-major per lane.
-                        const cpvk_u32 rowMask = small ? ((1u << cw) - 1u) : 0u; // cw <= 16
+                        const cpvk_u32 rowMask = small ? (cw >= 32 ? 0xFFFFFFFFu : ((1u << cw) - 1u)) : 0u; // cw <= CPVK_REGION_W <= 32
                         const int rows = small ? ch : 0;
                         int shift = 0;
                         // CPVK_COVER_ROWS rows per pass: A_k(x) = (xf - ax_k) * dy_k does not depend on the row and B_k(y) = (yf - ay_k) *
@@ -799,8 +807,8 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                 // warp's fragment list in shared memory: 16 bits each = chunk-local triangle | x, y inside the warp region.
                 // The list is then shaded 32 fragments at a time. A large triangle ends the segment and is rasterised by
                 // the whole warp right after it, so fragments still reach the ROP in API order.
-                const cpvk_u32 divMagic = 1024u / (cpvk_u32)max(cw, 1) + 1u; // (c * divMagic) >> 10 == c / cw for c < 32, cw <= 16
-                const cpvk_u32 fragBase = kt | ((cpvk_u32)(cx0 - rx0) << 8) | ((cpvk_u32)(cy0 - ry0) << 12);
+                const cpvk_u32 divMagic = 1024u / (cpvk_u32)max(cw, 1) + 1u; // (c * divMagic) >> 10 == c / cw for c < 32, cw <= 32
+                const cpvk_u32 fragBase = kt | ((cpvk_u32)(cx0 - rx0) << 8) | ((cpvk_u32)(cy0 - ry0) << 13); // triangle (8 bits) | x in the region (5) | y in the region (3)
                 #pragma unroll 1
                 while (todo) {
                     const cpvk_u32 lt = largeMask & todo;
@@ -825,7 +833,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                             const cpvk_u32 c = (cpvk_u32)__ffs((int)m) - 1u;
                             m &= m - 1u;
                             const cpvk_u32 row = (c * divMagic) >> 10;
-                            sFrag[pos++] = (unsigned short)(fragBase + ((c - row * (cpvk_u32)cw) << 8) + (row << 12));
+                            sFrag[pos++] = (unsigned short)(fragBase + ((c - row * (cpvk_u32)cw) << 8) + (row << 13));
                         }
                     }
                     __syncwarp();
@@ -836,7 +844,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                         lcx0 = __shfl_sync(0xFFFFFFFFu, cx0, firstLarge); lcy0 = __shfl_sync(0xFFFFFFFFu, cy0, firstLarge);
                         lcx1 = lcx0 + __shfl_sync(0xFFFFFFFFu, cw, firstLarge); lcy1 = lcy0 + __shfl_sync(0xFFFFFFFFu, ch, firstLarge);
                         const int lw = lcx1 - lcx0;
-                        lg = lw <= 4 ? 2 : (lw <= 8 ? 3 : 4); // lanes form a (1<<lg) x (32>>lg) block of candidates
+                        lg = lw <= 4 ? 2 : (lw <= 8 ? 3 : (lw <= 16 ? 4 : 5)); // lanes form a (1<<lg) x (32>>lg) block of candidates
                     }
                     int o = 0, row0 = lcy0;
                     #pragma unroll 1
@@ -846,7 +854,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
                             active = o + lane < total;
                             if (active) {
                                 const cpvk_u32 rec = sFrag[o + lane];
-                                bkt = rec & 255u; px = rx0 - tileX0 + (int)((rec >> 8) & 15u); py = ry0 - tileY0 + (int)(rec >> 12);
+                                bkt = rec & 255u; px = rx0 - tileX0 + (int)((rec >> 8) & 31u); py = ry0 - tileY0 + (int)(rec >> 13);
                             }
                             o += 32;
                         } else if (firstLarge < 32 && row0 < lcy1) {
