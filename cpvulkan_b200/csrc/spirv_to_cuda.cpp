@@ -122,8 +122,8 @@ void Parse(Module& m, const CpvkShaderStage& stage, uint32_t model) {
         // error, CPVK_E_SPIRV, not an out-of-bounds read), and every id a type refers to must lie below the module's bound
         auto need = [&](uint32_t words) { if (wc < words) throw Malformed("instruction too short"); };
         switch (op) {
-        case OpExtInstImport: case OpDecorate: case OpTypePointer: case OpTypeArray: need(4); break;
-        case OpEntryPoint: case OpMemberDecorate: need(5); break;
+        case OpExtInstImport: case OpDecorate: need(3); break;
+        case OpTypePointer: case OpTypeArray: case OpEntryPoint: case OpMemberDecorate: need(4); break;
         case OpTypeInt: case OpTypeVector: case OpTypeMatrix: need(4); break;
         case OpTypeFloat: case OpTypeSampledImage: case OpTypeRuntimeArray: case OpTypeFunction: case OpUndef: case OpFunctionParameter: need(3); break;
         case OpTypeImage: need(9); break;

@@ -110,3 +110,42 @@ def test_every_shader_family_links(built, name):
     blob = C.string_at(cubin, n.value)
     assert blob[:4] == b"\x7fELF" and b"cpvk_k_raster" in blob and b"cpvk_k_vertex" in blob
     lib.cpvk_cuda_pipeline_destroy(None, p)
+
+
+def test_truncated_and_out_of_range_spirv_is_refused_not_read_out_of_bounds(built):
+    """Every prefix of a valid module cut inside an instruction, and modules whose type operands name ids beyond the bound,
+    must come back as an error (round-1 ADVICE: operands were indexed before their presence was checked)."""
+    import numpy as np
+    words = scenes.shader("texcube.frag").copy()
+    lib = capi.load_cuda()
+
+    def compile_words(ws):
+        m = scenes.materialize(scenes.draw_textured_cube(32, 32), scenes.HostMemory().alloc)
+        ws = np.ascontiguousarray(ws, dtype=np.uint32)
+        m.desc.fragment.spirv = ws.ctypes.data_as(C.POINTER(C.c_uint32)); m.desc.fragment.wordCount = len(ws)
+        p = C.c_void_p()
+        rc = lib.cpvk_cuda_pipeline_compile_only(C.byref(m.desc), C.byref(p))
+        if rc == 0:
+            lib.cpvk_cuda_pipeline_destroy(None, p)
+        return rc
+
+    # shorten single instructions in place (word count field reduced, following words dropped)
+    i, tried = 5, 0
+    while i < len(words):
+        wc, op = int(words[i]) >> 16, int(words[i]) & 0xFFFF
+        if wc >= 3 and op in (19, 21, 22, 23, 24, 25, 27, 28, 30, 32, 33, 43, 59, 54, 71, 72, 15):  # types, constants, variables, decorations, entry point, function
+            cut = np.concatenate([words[:i], [np.uint32(((wc - 1) << 16) | op)], words[i + 1:i + wc - 1], words[i + wc:]])
+            assert compile_words(cut) != 0 or op in (71, 15), "op %d shortened to %d words was accepted" % (op, wc - 1)
+            tried += 1
+        i += wc
+    assert tried > 10
+    # a type operand beyond the id bound
+    bad = words.copy()
+    i = 5
+    while i < len(bad):
+        wc, op = int(bad[i]) >> 16, int(bad[i]) & 0xFFFF
+        if op == 23:  # OpTypeVector: component type id
+            bad[i + 2] = 0x00FFFFFF
+            break
+        i += wc
+    assert compile_words(bad) != 0
