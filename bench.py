@@ -136,7 +136,7 @@ class Workload:
             self.l2 = ("working set (indices 12 MB + vertices 16 MB + shaded vertices 16 MB + setup records 104 MB + tile lists 5 MB + "
                        "targets 66 MB) exceeds the 126 MB L2; no explicit flush")
         else:
-            self.quads = quads or 2000
+            self.quads = quads or int(os.environ.get("CPVK_BENCH_C4_QUADS", "2000"))  # the environment knob is for tuning runs only
             self.scene = scenes.overdraw_quads(7680, 4320, quads=self.quads, tex_size=1024)
             self.prims = 2 * self.quads
             self.metric = "Gfragments/s (%s alpha-blended LINEAR-textured full-screen quads at 7680x4320 RGBA16F)" % ("2,000" if self.quads == 2000 else str(self.quads))

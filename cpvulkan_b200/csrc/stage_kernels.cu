@@ -170,6 +170,30 @@ __device__ __forceinline__ void cpvk_tile_copy(cpvk_u8* dst, cpvk_u32 dstPitch, 
     }
 }
 
+// The same copy by ONE warp (lane-strided): a warp's region of a tile on its way back to HBM, without waiting for the other warps.
+__device__ __forceinline__ void cpvk_region_copy(cpvk_u8* dst, cpvk_u32 dstPitch, const cpvk_u8* src, cpvk_u32 srcPitch, cpvk_u32 bytes, cpvk_u32 rows) {
+    const cpvk_u32 lane = threadIdx.x & 31u;
+    const cpvk_u64 align = ((cpvk_u64)dst | (cpvk_u64)src | dstPitch | srcPitch | bytes);
+    if ((align & 15) == 0) {
+        const cpvk_u32 per = bytes >> 4;
+        for (cpvk_u32 i = lane; i < per * rows; i += 32u) {
+            const cpvk_u32 r = i / per, c = i - r * per;
+            reinterpret_cast<uint4*>(dst + (cpvk_u64)r * dstPitch)[c] = reinterpret_cast<const uint4*>(src + (cpvk_u64)r * srcPitch)[c];
+        }
+    } else if ((align & 3) == 0) {
+        const cpvk_u32 per = bytes >> 2;
+        for (cpvk_u32 i = lane; i < per * rows; i += 32u) {
+            const cpvk_u32 r = i / per, c = i - r * per;
+            reinterpret_cast<cpvk_u32*>(dst + (cpvk_u64)r * dstPitch)[c] = reinterpret_cast<const cpvk_u32*>(src + (cpvk_u64)r * srcPitch)[c];
+        }
+    } else {
+        for (cpvk_u32 i = lane; i < bytes * rows; i += 32u) {
+            const cpvk_u32 r = i / bytes, c = i - r * bytes;
+            dst[(cpvk_u64)r * dstPitch + c] = src[(cpvk_u64)r * srcPitch + c];
+        }
+    }
+}
+
 // Fill a whole 32x32 shared-memory tile with one packed texel (texel size is a compile-time constant per pipeline).
 CPVK_DEV void cpvk_tile_fill(cpvk_u8* dst, cpvk_u32 texel, const cpvk_u8* one) {
     if (texel == 4 || texel == 8 || texel == 2) { // 16-byte stores of the repeated texel: a 4 KB tile is one store per thread
@@ -872,6 +896,33 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
         }
         if (chunkBase + CPVK_CHUNK < listEnd) __syncthreads(); // the staged chunk is free for the next one (after the last chunk the barrier below does it)
     }
+#ifndef CPVK_WARP_WRITEBACK
+#define CPVK_WARP_WRITEBACK 0 /* 1: every warp stores its own region without the tile-wide barrier — measured 1 % slower at C3/M1 (64-byte row segments instead of 128) */
+#endif
+#if CPVK_WARP_WRITEBACK
+    // ---- write the tile back: shared -> HBM. A warp's region was written by that warp alone, so each warp could store its own region as
+    // soon as it is done with the tile's last chunk — no barrier, nobody waits for the slowest warp of the tile (tuning variant). ----
+    __syncwarp();
+    {
+        const int wy = max(ry0, wy0); // the band's first row may cut the region
+        if (rx0 < rx1 && wy < ry1) {
+            const cpvk_u32 ox = (cpvk_u32)(rx0 - tileX0), oy = (cpvk_u32)(wy - tileY0), rw = (cpvk_u32)(rx1 - rx0), rh = (cpvk_u32)(ry1 - wy);
+            if (dsUsed && ((depthTest && depthWrite) || stencilOn || (lazyMask & 0x100u)))
+                cpvk_region_copy(reinterpret_cast<cpvk_u8*>(p.ds.address) + (cpvk_u64)wy * p.ds.rowPitch + (cpvk_u64)rx0 * dsTexel, p.ds.rowPitch,
+                                 sDepth + oy * dsPitch + ox * dsTexel, dsPitch, rw * dsTexel, rh);
+            #pragma unroll
+            for (int a = 0; a < CPVK_MAX_COLOR; a++)
+                if (sColor[a])
+                    cpvk_region_copy(reinterpret_cast<cpvk_u8*>(p.color[a].address) + (cpvk_u64)wy * p.color[a].rowPitch + (cpvk_u64)rx0 * cTexel[a], p.color[a].rowPitch,
+                                     sColor[a] + (oy * CPVK_TILE_W + ox) * cTexel[a], cTexel[a] * CPVK_TILE_W, rw * cTexel[a], rh);
+            // ---- the fused gather: the band's rows of this region go to every peer's copy of colour attachment 0 ----
+            if (p.mirrorCount && sColor[0])
+                for (cpvk_u32 m = 0; m < p.mirrorCount; m++)
+                    cpvk_region_copy(reinterpret_cast<cpvk_u8*>(p.mirror[m]) + (cpvk_u64)wy * p.color[0].rowPitch + (cpvk_u64)rx0 * cTexel[0], p.color[0].rowPitch,
+                                     sColor[0] + (oy * CPVK_TILE_W + ox) * cTexel[0], cTexel[0] * CPVK_TILE_W, rw * cTexel[0], rh);
+        }
+    }
+#else
     __syncthreads();
     // ---- write the tile back: shared -> HBM, row segments are contiguous in the linear image ----
     if (dsUsed && ((depthTest && depthWrite) || stencilOn || (lazyMask & 0x100u)))
@@ -887,6 +938,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
         for (cpvk_u32 m = 0; m < p.mirrorCount; m++)
             cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.mirror[m]) + (cpvk_u64)wy0 * p.color[0].rowPitch + (cpvk_u64)tileX0 * cTexel[0], p.color[0].rowPitch,
                            sColor[0] + skipRows * cTexel[0] * CPVK_TILE_W, cTexel[0] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[0], (cpvk_u32)th, cTexel[0] * CPVK_TILE_W);
+#endif
     if (p.stats && lane == 0 && (nCov | nPass)) {
         atomicAdd(p.stats + 0, (cpvk_u64)nCov);
         atomicAdd(p.stats + 1, (cpvk_u64)nPass);

@@ -750,10 +750,16 @@ VKFN(void) CmdExecuteCommands(VkCommandBuffer cb, uint32_t n, const VkCommandBuf
 VKFN(void) CmdFillBuffer(VkCommandBuffer cb, VkBuffer dst, VkDeviceSize offset, VkDeviceSize size, uint32_t data) { // CommandBuffer.cpp:278-330: 32-bit words
     auto* t = reinterpret_cast<Buffer*>(dst);
     RECORD(cb)([=](Device& d) {
-        const VkDeviceSize bytes = size == VK_WHOLE_SIZE ? t->size - offset : size;
-        CpvkAttachment a{t->address(offset), (uint32_t)(bytes / 4), 1, (uint32_t)(bytes & ~(VkDeviceSize)3), 98 /* R32_UINT */};
+        const VkDeviceSize bytes = (size == VK_WHOLE_SIZE ? t->size - offset : size) & ~(VkDeviceSize)3;
         CpvkClearValue cv{}; cv.uint32[0] = data;
-        if (a.width) CU_CHECK(cpvk_cuda_clear(d.cuda, &a, &cv, 0));
+        // one "image" row of R32_UINT words per piece of at most 1 GiB (the C ABI's sizes are 32-bit; attachments end at 32767 texels per
+        // axis only for draws, a clear takes any width)
+        for (VkDeviceSize done = 0; done < bytes;) {
+            const uint32_t piece = (uint32_t)std::min<VkDeviceSize>(bytes - done, (VkDeviceSize)1 << 30);
+            CpvkAttachment a{t->address(offset + done), piece / 4, 1, piece, 98 /* R32_UINT */};
+            CU_CHECK(cpvk_cuda_clear(d.cuda, &a, &cv, 0));
+            done += piece;
+        }
         TouchedByGpu(t->mem);
     });
 }
@@ -767,7 +773,16 @@ VKFN(void) CmdPipelineBarrier(VkCommandBuffer, VkPipelineStageFlags, VkPipelineS
 // transfer path: raw row copies and the blit
 VKFN(void) CmdCopyBuffer(VkCommandBuffer cb, VkBuffer src, VkBuffer dst, uint32_t n, const VkBufferCopy* regions) {
     auto* s = reinterpret_cast<Buffer*>(src); auto* t = reinterpret_cast<Buffer*>(dst); std::vector<VkBufferCopy> r(regions, regions + n);
-    RECORD(cb)([s, t, r](Device& d) { for (auto& c : r) CU_CHECK(cpvk_cuda_copy_rows(d.cuda, t->address(c.dstOffset), (uint32_t)c.size, s->address(c.srcOffset), (uint32_t)c.size, (uint32_t)c.size, 1)); TouchedByGpu(t->mem); });
+    RECORD(cb)([s, t, r](Device& d) {
+        // the C ABI's row copies take 32-bit sizes: a region of any VkDeviceSize goes as pieces of at most 1 GiB
+        for (auto& c : r)
+            for (VkDeviceSize done = 0; done < c.size;) {
+                const uint32_t piece = (uint32_t)std::min<VkDeviceSize>(c.size - done, (VkDeviceSize)1 << 30);
+                CU_CHECK(cpvk_cuda_copy_rows(d.cuda, t->address(c.dstOffset + done), piece, s->address(c.srcOffset + done), piece, piece, 1));
+                done += piece;
+            }
+        TouchedByGpu(t->mem);
+    });
 }
 VKFN(void) CmdCopyImage(VkCommandBuffer cb, VkImage src, VkImageLayout, VkImage dst, VkImageLayout, uint32_t n, const VkImageCopy* regions) { // CommandBuffer.Copy.cpp:77-200
     auto* s = reinterpret_cast<Image*>(src); auto* t = reinterpret_cast<Image*>(dst); std::vector<VkImageCopy> r(regions, regions + n);
