@@ -387,7 +387,12 @@ enum { KDYN = 0, K8 = 1, K16F = 2 };
 template <int K> __device__ __forceinline__ void cpvk_blit_load(cpvk_u32 format, const cpvk_u8* p, float v[4], const float* lut) {
     if (K == K8) {
         const cpvk_u32 t = *reinterpret_cast<const cpvk_u32*>(p);
-        const float b0 = cpvk_unorm8(t & 0xFFu), b1 = cpvk_unorm8((t >> 8) & 0xFFu), b2 = cpvk_unorm8((t >> 16) & 0xFFu), b3 = cpvk_unorm8(t >> 24);
+        float b0, b1, b2, b3;
+#ifndef CPVK_BLIT_NO_LUT
+        if (lut) { b0 = lut[t & 0xFFu]; b1 = lut[(t >> 8) & 0xFFu]; b2 = lut[(t >> 16) & 0xFFu]; b3 = lut[t >> 24]; } // LINEAR: 16 decodes per texel, the table is cheaper
+        else
+#endif
+        { b0 = cpvk_unorm8(t & 0xFFu); b1 = cpvk_unorm8((t >> 8) & 0xFFu); b2 = cpvk_unorm8((t >> 16) & 0xFFu); b3 = cpvk_unorm8(t >> 24); }
         v[0] = format == 37 ? b0 : b2; v[1] = b1; v[2] = format == 37 ? b2 : b0; v[3] = b3;
     } else if (K == K16F) {
         cpvk_unpack_half4(*reinterpret_cast<const uint2*>(p), v);
@@ -403,7 +408,8 @@ __device__ __forceinline__ cpvk_u32 cpvk_blit_pack8(cpvk_u32 format, const float
 template <int KS, int KD, int FILTER, int TPT> __global__ void __launch_bounds__(256) k_blit(CpvkBlitArgs b) {
     __shared__ float lut[256]; // (float)k / 255.0f by the IEEE divide itself, for the run-time format path
     __shared__ CpvkBlitAxis rows[CPVK_BLIT_ROWS];
-    if (KS == KDYN) lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    if (KS == KDYN || (KS == K8 && FILTER == 1)) lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    const float* const lutK = (KS == KDYN || (KS == K8 && FILTER == 1)) ? lut : nullptr;
     const int dstW = abs(b.dstX1 - b.dstX0), dstH = abs(b.dstY1 - b.dstY0);
     const cpvk_u32 stexel = cpvk_texel_size(b.src.format), dtexel = cpvk_texel_size(b.dst.format);
     const cpvk_u64 spitch = (cpvk_u64)stexel * b.src.width; // the sampler addresses a level as tightly packed rows (Formats.cpp:583-587)
@@ -437,13 +443,13 @@ template <int KS, int KD, int FILTER, int TPT> __global__ void __launch_bounds__
                 if (x4 + k >= dstW) continue;
                 float* v = value[k];
                 if (FILTER == 0) {
-                    cpvk_blit_load<KS>(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx[k].c0 * stexel, v, lut);
+                    cpvk_blit_load<KS>(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx[k].c0 * stexel, v, lutK);
                 } else {
                     CpvkVec4 i0j0, i1j0, i0j1, i1j1;
-                    cpvk_blit_load<KS>(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx[k].c0 * stexel, i0j0.v, lut);
-                    cpvk_blit_load<KS>(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx[k].c1 * stexel, i1j0.v, lut);
-                    cpvk_blit_load<KS>(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx[k].c0 * stexel, i0j1.v, lut);
-                    cpvk_blit_load<KS>(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx[k].c1 * stexel, i1j1.v, lut);
+                    cpvk_blit_load<KS>(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx[k].c0 * stexel, i0j0.v, lutK);
+                    cpvk_blit_load<KS>(b.src.format, r0 + (cpvk_u64)(cpvk_u32)cx[k].c1 * stexel, i1j0.v, lutK);
+                    cpvk_blit_load<KS>(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx[k].c0 * stexel, i0j1.v, lutK);
+                    cpvk_blit_load<KS>(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx[k].c1 * stexel, i1j1.v, lutK);
                     const CpvkVec4 ij0 = cpvk_lerp(i0j0, i1j0, cx[k].t), ij1 = cpvk_lerp(i0j1, i1j1, cx[k].t);
                     const CpvkVec4 plane = cpvk_lerp(ij0, ij1, cy.t);
                     const CpvkVec4 out = cpvk_lerp(plane, plane, cz.t); // the two z planes are the same slice
