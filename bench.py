@@ -367,7 +367,7 @@ def measure(rig, steps, warmup, sampler=None):
         rig.frame()
     torch.cuda.synchronize()
     st = dev.stats()
-    local_cov, local_pass = int(st.fragmentsCovered), int(st.fragmentsWritten)
+    local_cov, local_pass, bin_entries = int(st.fragmentsCovered), int(st.fragmentsWritten), int(st.binEntries)
     n_cov, n_pass = local_cov, local_pass
     if world > 1:
         t = torch.tensor([n_cov, n_pass], dtype=torch.int64, device="cuda")
@@ -393,7 +393,7 @@ def measure(rig, steps, warmup, sampler=None):
         dist.all_reduce(rig.token)
         torch.cuda.synchronize()
     return {"ms_step": ms_step, "blocks": blocks, "n_cov": n_cov, "n_pass": n_pass, "local_cov": local_cov, "local_pass": local_pass,
-            "launches_per_step": launches, "bin_entries": int(s2.binEntries),
+            "launches_per_step": launches, "bin_entries": bin_entries,
             "kernel_ms": {"vertex": statistics.mean(vs), "setup": statistics.mean(su), "bin": statistics.mean(bn), "raster": statistics.mean(rs)}}
 
 
@@ -420,7 +420,7 @@ def e2e_single(torch, rig, local, steps):
     scene = rig.work.scene
     names = [n for n in ("vb", "ib", "ubo") if n in scene.buffers]
     lanes = []
-    n_lanes = int(os.environ.get("CPVK_E2E_LANES", "2"))
+    n_lanes = max(2, int(os.environ.get("CPVK_E2E_LANES", "3")))  # frame k is submitted before frame k - 1 is collected: two frames at least
     for i in range(n_lanes):
         ldev = Device(local, stats=False)  # runs on its own stream
         lsod = SceneOnDevice(ldev, scene)
@@ -435,7 +435,7 @@ def e2e_single(torch, rig, local, steps):
     h2d = sum(v[1] for v in lanes[0][2].values())
     d2h = scene.color.nbytes
 
-    def step(k):
+    def submit(k):
         ldev, lsod, staged, out_host = lanes[k % n_lanes]
         ldev.sync()  # frame k - n_lanes (same lane) has been read back: its buffers are free
         for nme in names:
@@ -443,12 +443,25 @@ def e2e_single(torch, rig, local, steps):
             ldev.upload_async(lsod.m.addr[nme], ldev.allocs[src_alloc][1], nbytes)
         lsod.clear()
         lsod.draw()
+
+    def collect(k):
+        ldev, lsod, staged, out_host = lanes[k % n_lanes]
         ldev.download_into_async(out_host, lsod.m.addr["color"], d2h)
 
-    for k in range(2 * n_lanes):
-        step(k)
-    for lane in lanes:
-        lane[0].sync()
+    def run(count):
+        # software pipelining as an application with frames in flight does it: submit frame k (upload + clear + draw), then
+        # ask for frame k - 1's pixels. The read-back call has to look at frame k - 1's binning verdict first (speculative
+        # draws, include/cpvk_cuda.h) — by now that frame's upload is done and the call does not stall the host behind it,
+        # so frame k's upload and frame k - 1's read-back use the two directions of the link at the same time.
+        for k in range(count):
+            submit(k)
+            if k > 0:
+                collect(k - 1)
+        collect(count - 1)
+        for lane in lanes:
+            lane[0].sync()
+
+    run(2 * n_lanes)
     ref_frame = rig.dev.download(rig.sod.m.addr["color"], d2h)  # the read-back frame must be the frame the resident path produced
     for lane in lanes:
         got = np.ctypeslib.as_array(C.cast(lane[3], C.POINTER(C.c_uint8)), shape=(d2h,))
@@ -459,16 +472,13 @@ def e2e_single(torch, rig, local, steps):
         n = steps
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for k in range(n):
-        step(k)
-    for lane in lanes:
-        lane[0].sync()
+    run(n)
     ms = (time.perf_counter() - t0) * 1e3 / n
     for lane in lanes:
         lane[1].close()
         lane[0].close()
     return {"ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "frames_timed": n,
-            "through": "C ABI (cpvk_cuda_mem_upload / clear / draw / mem_download_async + sync) with pinned host buffers; two device objects alternate frames (double buffering)"}
+            "through": "C ABI (cpvk_cuda_mem_upload / clear / draw / mem_download_async + sync) with pinned host buffers; %d device objects alternate frames, frame k is submitted before frame k-1 is read back (frames in flight)" % n_lanes}
 
 
 def e2e_multi(torch, dist, rig, local, steps):

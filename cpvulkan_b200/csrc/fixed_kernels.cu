@@ -33,6 +33,24 @@ template <typename F> __device__ __forceinline__ void cpvk_for_each_tile_aggrega
     }
 }
 
+// The last CTA of a grid to get here stores the verdict of single-pass binning where the host reads it (mapped memory):
+// [2] deferred primitives, [3] != 0 = replay with exact sizes (a tile list overflowed, or deferred primitives turned up in
+// a draw planned without a k_bin_large pass). Totals are not known in this mode: [0] = [1] = 0.
+// Ordering: meta[2] only changes through atomics whose value the thread uses (performed before it goes on); a thread that
+// raises meta[3] fences right there (cpvk_raise_mismatch, rare), before the barrier below — so the ticket needs no fence of
+// its own, which measured 7 us of k_setup on the 1M-triangle draw.
+__device__ __forceinline__ void cpvk_raise_mismatch(cpvk_u32* meta) { *(volatile cpvk_u32*)(meta + 3) = 1u; __threadfence(); }
+__device__ __forceinline__ void cpvk_publish_when_last(cpvk_u32* ticket, cpvk_u32* meta, cpvk_u32* metaHost, bool largeDone) {
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (atomicAdd(ticket, 1u) != gridDim.x - 1) return;
+    const cpvk_u32 nLarge = *(volatile cpvk_u32*)(meta + 2);
+    cpvk_u32 mismatch = *(volatile cpvk_u32*)(meta + 3);
+    if (nLarge != 0 && !largeDone) { mismatch = 1u; *(volatile cpvk_u32*)(meta + 3) = 1u; }
+    metaHost[0] = 0u; metaHost[1] = 0u; metaHost[2] = nLarge; metaHost[3] = mismatch;
+    __threadfence_system();
+}
+
 __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
     __shared__ uint4 sRec[256 / 32][32 * 6]; // one warp's 32 records, staged so that the HBM stores are contiguous 512-byte rows
     const cpvk_u32 pRaw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -120,9 +138,49 @@ __global__ void __launch_bounds__(256) k_setup(CpvkSetupArgs a) {
         if (n > CPVK_BIN_SMALL) a.largeList[atomicAdd(a.meta + 2, 1u)] = p;
         else small = true;
     }
-    cpvk_for_each_tile_aggregated(small, tx0, ty0, tw, n, a.tilesX, [&](cpvk_u32 t, bool live, cpvk_u32 m, int lane) {
-        if (live && (int)__ffs((int)m) - 1 == lane) atomicAdd(a.counts + t, (cpvk_u32)__popc(m));
-    });
+    if (!a.directLists) {
+        cpvk_for_each_tile_aggregated(small, tx0, ty0, tw, n, a.tilesX, [&](cpvk_u32 t, bool live, cpvk_u32 m, int lane) {
+            if (live && (int)__ffs((int)m) - 1 == lane) atomicAdd(a.counts + t, (cpvk_u32)__popc(m));
+        });
+        return;
+    }
+    // single-pass binning: the counting atomic also claims the slots, ids ascending inside one claim; k_raster orders
+    // each list (at most directCap <= CPVK_ORDER_MAX ids), which restores API order exactly as after count -> scan -> fill
+    bool overflow = false;
+    {
+        // four steps of the tile walk at a time: their claims are in flight together (an atomic that returns a value costs a
+        // round trip to L2; one per step in a dependent chain was the whole cost of this mode), then the ids are stored
+        const int lane = threadIdx.x & 31;
+        const int maxN = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(small ? n : 0));
+        int cx = 0, cy = 0;
+        for (int j0 = 0; j0 < maxN; j0 += 4) {
+            cpvk_u32 t[4], m[4], base[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                t[u] = 0xFFFFFFFFu; m[u] = 0u; base[u] = 0u;
+                if (j0 + u < maxN) { // uniform
+                    if (small && j0 + u < n) {
+                        t[u] = (cpvk_u32)(ty0 + cy) * a.tilesX + (cpvk_u32)(tx0 + cx);
+                        if (++cx == tw) { cx = 0; cy++; }
+                    }
+                    m[u] = __match_any_sync(0xFFFFFFFFu, t[u]);
+                    if (t[u] != 0xFFFFFFFFu && (int)__ffs((int)m[u]) - 1 == lane) base[u] = atomicAdd(a.counts + t[u], (cpvk_u32)__popc(m[u]));
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (j0 + u < maxN) {
+                    const cpvk_u32 b = __shfl_sync(0xFFFFFFFFu, base[u], (int)__ffs((int)m[u]) - 1);
+                    if (t[u] != 0xFFFFFFFFu) {
+                        const cpvk_u32 slot = b + (cpvk_u32)__popc(m[u] & ((1u << lane) - 1u));
+                        if (slot < a.directCap) a.directLists[(size_t)t[u] * a.directCap + slot] = p; else overflow = true;
+                    }
+                }
+            }
+        }
+    }
+    if (overflow) cpvk_raise_mismatch(a.meta);
+    if (a.publish) cpvk_publish_when_last(a.ticket, a.meta, a.metaHost, false);
 }
 
 // Lowest and highest index of an indexed draw (vertex reuse, CpvkDrawParams::vcache).
@@ -163,7 +221,7 @@ __global__ void __launch_bounds__(256) k_bin(CpvkBinArgs a, int pass) {
     });
 }
 __global__ void __launch_bounds__(256) k_bin_large(CpvkBinArgs a, int pass) {
-    if (pass != 0 && a.meta[3] != 0) return;
+    if (pass == 1 && a.meta[3] != 0) return;
     const cpvk_u32 nLarge = a.meta[2];
     for (cpvk_u32 li = blockIdx.x; li < nLarge; li += gridDim.x) {
         const cpvk_u32 p = a.largeList[li];
@@ -174,9 +232,14 @@ __global__ void __launch_bounds__(256) k_bin_large(CpvkBinArgs a, int pass) {
             const int ty = ty0 + k / tw, tx = tx0 + k % tw;
             const cpvk_u32 t = (cpvk_u32)ty * a.tilesX + (cpvk_u32)tx;
             if (pass == 0) atomicAdd(a.counts + t, 1u);
-            else a.lists[atomicAdd(a.cursors + t, 1u)] = p;
+            else if (pass == 1) a.lists[atomicAdd(a.cursors + t, 1u)] = p;
+            else {
+                const cpvk_u32 slot = atomicAdd(a.counts + t, 1u);
+                if (slot < a.directCap) a.directLists[(size_t)t * a.directCap + slot] = p; else cpvk_raise_mismatch(a.meta);
+            }
         }
     }
+    if (pass == 2) cpvk_publish_when_last(a.ticket, a.meta, a.metaHost, true);
 }
 // Single-CTA exclusive scan of the per-tile counts (<= a few 10^4 tiles). offsets[tiles] = total.
 // meta[0] = total entries, meta[1] = longest list.

@@ -24,6 +24,14 @@ struct CpvkSetupArgs {
     cpvk_u32* counts;    // [tiles], zeroed by the host
     cpvk_u32* largeList; // [primCount]
     cpvk_u32* meta;      // [2] = number of deferred (large) primitives, zeroed by the host
+    // Single-pass binning (direct lists): every tile owns directCap slots at lists[tile * directCap]; the count pass claims
+    // slots with the same atomic that counts and writes the primitive id there. A tile that needs more slots raises
+    // meta[3] (counts stay exact), the rest of the draw is a no-op and the host replays count-exact binning from the scan on.
+    cpvk_u32* directLists; // null = count only
+    cpvk_u32 directCap;
+    cpvk_u32 publish;      // 1 = the last CTA to finish stores the verdict to metaHost (no k_bin_large pass follows)
+    cpvk_u32* ticket;      // CTA completion counter for `publish`, zeroed by the host
+    cpvk_u32* metaHost;
 };
 
 struct CpvkBinArgs {
@@ -41,6 +49,10 @@ struct CpvkBinArgs {
     cpvk_u32 planCapacity;     // entries `lists` can hold
     cpvk_u32 planSortCap;      // longest list k_bin_sort was sized for (0 = not launched: lists must fit one raster chunk)
     cpvk_u32 planLargeCounted; // 1 = k_bin_large's count pass ran before the scan
+    // single-pass binning of the deferred primitives (k_bin_large pass 2), see CpvkSetupArgs::directLists
+    cpvk_u32* directLists;
+    cpvk_u32 directCap;
+    cpvk_u32* ticket;
 };
 
 struct CpvkClearArgs {
@@ -61,7 +73,7 @@ struct CpvkBlitArgs {
 extern "C" {
 cudaError_t cpvk_launch_setup(const CpvkSetupArgs* a, cudaStream_t s);
 cudaError_t cpvk_launch_index_range(unsigned long long indexBuffer, unsigned indexStride, unsigned first, unsigned count, cpvk_u32* range /* [2] = {~lowest, highest}, zeroed by the caller */, cudaStream_t s);
-cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, int small, int large, cudaStream_t s); /* pass 0 = count, 1 = fill; small/large select k_bin / k_bin_large (small primitives are counted by k_setup) */
+cudaError_t cpvk_launch_bin(const CpvkBinArgs* a, int pass, int small, int large, cudaStream_t s); /* pass 0 = count, 1 = fill, 2 = count + write into the direct lists and publish the verdict (k_bin_large only); small/large select k_bin / k_bin_large (small primitives are counted by k_setup) */
 cudaError_t cpvk_launch_bin_scan(const CpvkBinArgs* a, cudaStream_t s);
 cudaError_t cpvk_launch_bin_sort(const CpvkBinArgs* a, unsigned capacity, cudaStream_t s);
 cudaError_t cpvk_launch_clear(const CpvkDevAttachment* img, const CpvkClearArgs* c, cudaStream_t s);

@@ -243,7 +243,11 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
     const bool triangles = cpvk_prim_vertices() == 3; // points and lines are not binned: every tile walks all of them (below)
     if (triangles && p.binMeta[3] != 0) return; // the speculative launch plan did not fit this draw: the host replays it
     const bool listsSorted = triangles && p.binMeta[1] > CPVK_ORDER_MAX;
-    const cpvk_u32 listBegin = triangles ? p.tileOffsets[tile] : 0u, listEnd = triangles ? p.tileOffsets[tile + 1] : 1u;
+    cpvk_u32 listBegin = 0u, listEnd = 1u;
+    if (triangles) {
+        if (p.directCap) { listBegin = tile * p.directCap; listEnd = listBegin + min(p.tileOffsets[tile], p.directCap); } // grids of up to 2^32 / directCap tiles (cpvk_abi.cpp keeps to that)
+        else { listBegin = p.tileOffsets[tile]; listEnd = p.tileOffsets[tile + 1]; }
+    }
     const cpvk_u32 lazyMask = p.lazyMask;
     const int tileX0 = (int)tx * CPVK_TILE_W, tileY0 = (int)(tyr + p.tileRow0) * CPVK_TILE_H;
     // nothing to draw and no clear to fold: done — unless mirrors are on, then even untouched tiles of the band travel
@@ -939,6 +943,7 @@ extern "C" __global__ void __launch_bounds__(CPVK_RASTER_THREADS, CPVK_RASTER_MI
             cpvk_tile_copy(reinterpret_cast<cpvk_u8*>(p.mirror[m]) + (cpvk_u64)wy0 * p.color[0].rowPitch + (cpvk_u64)tileX0 * cTexel[0], p.color[0].rowPitch,
                            sColor[0] + skipRows * cTexel[0] * CPVK_TILE_W, cTexel[0] * CPVK_TILE_W, (cpvk_u32)tw * cTexel[0], (cpvk_u32)th, cTexel[0] * CPVK_TILE_W);
 #endif
+    if (p.stats && triangles && threadIdx.x == 0 && listEnd != listBegin) atomicAdd(p.stats + 2, (cpvk_u64)(listEnd - listBegin));
     if (p.stats && lane == 0 && (nCov | nPass)) {
         atomicAdd(p.stats + 0, (cpvk_u64)nCov);
         atomicAdd(p.stats + 1, (cpvk_u64)nPass);

@@ -219,7 +219,7 @@ typedef struct CpvkDrawStats {
     uint64_t primitives;        /* assembled primitives (all instances)                          */
     uint64_t fragmentsCovered;  /* N_cov: GetFragmentInput() returned true (Draw.cpp:874-954)    */
     uint64_t fragmentsWritten;  /* N_pass: not discarded and passed depth/stencil                */
-    uint64_t binEntries;        /* (primitive, tile) pairs produced by binning                   */
+    uint64_t binEntries;        /* (primitive, tile) pairs rasterised; counted on the device, 0 with statistics off */
     float msVertex, msSetup, msBin, msRaster, msTotal; /* CUDA-event times of the last draw when timing is on */
 } CpvkDrawStats;
 

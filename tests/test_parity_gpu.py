@@ -28,7 +28,7 @@ def compare(dev, scene, check_depth=True):
         raise AssertionError("colour differs at %d pixels, first (x=%d,y=%d): oracle %s gpu %s" % (len(bad), x, y, a[y, x], b[y, x]))
     if check_depth and scene.depth is not None:
         assert np.array_equal(od, gd), "depth attachment differs"
-    return ost
+    return gst  # primitives / fragment counts are the oracle's (asserted above); binEntries exists on the GPU side only
 
 
 def test_draw_cube(dev):
@@ -197,6 +197,25 @@ def test_speculative_plan_replays(built):
             compare(d, sc)
         d.set_speculation(False)
         compare(d, seq[1])
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("quads,size", [(255, 32), (256, 32), (257, 32), (256, 64), (300, 96)])
+def test_single_pass_binning_slot_boundary(built, quads, size):
+    """Single-pass binning gives every tile CPVK_ORDER_MAX = 512 list slots (fixed_kernels.h, CpvkSetupArgs::directLists):
+    a tile with exactly 512 primitives fits, one with 514 overflows and the draw is replayed through count -> scan -> fill
+    -> sort. Either way the bytes are the oracle's, the (primitive, tile) pairs are all there, and a draw that fits
+    again afterwards goes back to the short path."""
+    from cpvulkan_b200.device import Device
+    d = Device(0, stats=True)
+    try:
+        tiles = ((size + 31) // 32) ** 2
+        for sc in (scenes.overdraw_quads(size, size, quads, 16), scenes.mesh_indexed(width=160, height=96, nx=20, ny=12),
+                   scenes.overdraw_quads(size, size, quads, 16)):
+            st = compare(d, sc, check_depth=sc.depth is not None)
+            if sc.name.startswith("overdraw"):
+                assert st.binEntries == 2 * quads * tiles
     finally:
         d.close()
 
