@@ -11,7 +11,8 @@ LINEAR-textured full-screen quads at 7680x4320 RGBA16F. A "step" is one frame: r
 With --gpus N (torchrun, one rank per GPU) the frame is split sort-first into N bands of tile rows, vertex work is
 replicated, and k_raster stores every finished tile of a rank's band straight into the presenting GPU's frame (rank 0;
 `--gather all`: into every GPU's frame) over NVLink — peer memory mapped through the C ABI's cudaIpc export / import, the
-handles exchanged with torch.distributed; a 4-byte NCCL all-reduce on the draw stream orders the GPUs after the stores.
+handles exchanged with torch.distributed; cpvk_cuda_peer_barrier on the draw stream (flag words in the same peer-mapped
+memory; `--barrier nccl`: a 4-byte NCCL all-reduce) orders the GPUs after the stores.
 Scaling is strong (fixed frame).
 
 Timing: the K steps asked for are one block, bracketed by barrier + synchronize and timed with CUDA events on the launching
@@ -280,7 +281,7 @@ def bind_near_gpu(index):
 class Rig:
     """One rank's device, scene and frame function for a workload; on N > 1 ranks also the peer mapping of the colour frame."""
 
-    def __init__(self, work, torch, dist, stream, local, rank, world, gather):
+    def __init__(self, work, torch, dist, stream, local, rank, world, gather, barrier="flags"):
         from cpvulkan_b200.device import Device, SceneOnDevice
         self.torch, self.dist, self.work, self.rank, self.world = torch, dist, work, rank, world
         self.dev = Device(local, stream=stream.cuda_stream, stats=True)
@@ -302,6 +303,21 @@ class Rig:
                 self.peers.append(addr)
                 st.mirrorColor0[i] = addr
             st.mirrorCount = len(targets)
+            # the per-frame ordering step between the GPUs: cpvk_cuda_peer_barrier on flag words every rank maps (default), or a
+            # 4-byte NCCL all-reduce (--barrier nccl)
+            self.barrier, self.sequence, self.flag_arrays = barrier, 0, []
+            if barrier == "flags":
+                mine = self.dev.alloc(64)
+                self.dev.sync()  # the zero fill of the allocation is done before any peer can signal into it
+                dist.all_gather_object(handles, self.dev.export_handle(mine))
+                for r in range(world):
+                    if r == rank:
+                        self.flag_arrays.append(mine)
+                    else:
+                        addr = self.dev.import_handle(handles[r])
+                        self.peers.append(addr)
+                        self.flag_arrays.append(addr)
+                dist.barrier()
 
     def frame(self):
         self.sod.clear(band_only=self.world > 1)
@@ -309,7 +325,11 @@ class Rig:
         if self.world > 1:
             # orders the GPUs: the collective starts on a rank after its raster kernel (and its peer stores) finished, and ends
             # everywhere only after it started everywhere
-            self.dist.all_reduce(self.token)
+            if self.barrier == "flags":
+                self.sequence += 1
+                self.dev.peer_barrier(self.flag_arrays, self.rank, self.sequence)
+            else:
+                self.dist.all_reduce(self.token)
 
     def single_gpu_frame(self):
         """The frame one GPU renders without bands, into a second image (the reference for the exchange)."""
@@ -484,33 +504,31 @@ def e2e_single(torch, rig, local, steps):
 def e2e_multi(torch, dist, rig, local, steps):
     """e2e on N > 1 GPUs (every rank takes part): per frame each rank uploads 1/N of the geometry from its own pinned buffer over
     its own PCIe link, an NCCL all-gather over NVLink completes every rank's copy (vertex work is replicated, so every GPU needs
-    all of it), the rank renders its band — peer stores and the ordering collective stay in the frame — and reads ITS band back
+    all of it), the rank renders its band — peer stores and the ordering step stay in the frame — and reads ITS band back
     into pinned host memory: the host ends up with the whole frame, one band per process, 1/N of the traffic per link in both
-    directions. The read-back of frame k overlaps frame k+1 (staging copy on the draw stream, a second device object on its own
-    stream carries it to the host; events order the two streams both ways)."""
+    directions. Frames are in flight like in e2e_single: the geometry lives in two buffer sets, frame k+1's upload + all-gather
+    run on a copy stream while frame k renders, and frame k's band travels to the host on a third stream (a second device
+    object) while frame k+1 renders; events order the streams both ways."""
     from cpvulkan_b200.device import Device
     scene, dev, sod, rank, world = rig.work.scene, rig.dev, rig.sod, rig.rank, rig.world
     stream = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream()
     names = [n for n in ("vb", "ib") if n in scene.buffers]
     shards = {}
     for nme in names:
         data = scene.buffers[nme]
         per = (data.nbytes + world - 1) // world
         per = (per + 15) // 16 * 16
-        full = torch.zeros(per * world, dtype=torch.uint8, device="cuda")     # the gathered copy the draw reads
+        fulls = [torch.zeros(per * world, dtype=torch.uint8, device="cuda") for _ in range(2)]  # the gathered copies the draws read
         host = torch.zeros(per, dtype=torch.uint8).pin_memory()
         chunk = data[rank * per:(rank + 1) * per]
         host[:len(chunk)] = torch.from_numpy(np.ascontiguousarray(chunk))
-        shards[nme] = (full, host, per, data.nbytes)
+        shards[nme] = (fulls, host, per, data.nbytes)
     ubo = scene.buffers["ubo"]
     ubo_stage = dev.alloc(ubo.nbytes, host_shadow=True)
     dev.shadow(ubo_stage)[:ubo.nbytes] = ubo
     st = sod.m.state
     saved = ({b: st.vertexBuffers[b] for b in scene.vertex_buffers}, st.indexBuffer)
-    for b, nme in scene.vertex_buffers.items():
-        st.vertexBuffers[b] = shards[nme][0].data_ptr()
-    if scene.index_buffer:
-        st.indexBuffer = shards[scene.index_buffer][0].data_ptr()
     y0, y1 = rig.band
     band_bytes = (y1 - y0) * scene.color.pitch
     band_addr = sod.m.addr["color"] + y0 * scene.color.pitch
@@ -520,18 +538,34 @@ def e2e_multi(torch, dist, rig, local, steps):
     for _ in range(2):
         staging = torch.empty(max(band_bytes, 16), dtype=torch.uint8, device="cuda")
         out_dev = dev2.alloc(max(band_bytes, 16), host_shadow=True)  # only its pinned shadow is used, as the read-back target
-        slots.append({"staging": staging, "host": dev2.allocs[out_dev][1], "copied": torch.cuda.Event(), "read": torch.cuda.Event()})
+        slots.append({"staging": staging, "host": dev2.allocs[out_dev][1], "copied": torch.cuda.Event(), "read": torch.cuda.Event(),
+                      "geo_ready": torch.cuda.Event(), "geo_free": torch.cuda.Event()})
         slots[-1]["read"].record(stream2)
+        slots[-1]["geo_free"].record(stream)
 
-    def step(k):
+    def prefetch(k):
+        """Frame k's geometry: own shard over PCIe, the rest over NVLink, on the copy stream."""
         sl = slots[k % 2]
-        for nme in names:
-            full, host, per, _ = shards[nme]
-            full[rank * per:(rank + 1) * per].copy_(host, non_blocking=True)
-            dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per])
+        copy_stream.wait_event(sl["geo_free"])  # the draw that read this buffer set (frame k - 2) is done
+        with torch.cuda.stream(copy_stream):
+            for nme in names:
+                fulls, host, per, _ = shards[nme]
+                mine = fulls[k % 2][rank * per:(rank + 1) * per]
+                mine.copy_(host, non_blocking=True)
+                dist.all_gather_into_tensor(fulls[k % 2], mine)
+            sl["geo_ready"].record(copy_stream)
+
+    def render(k):
+        sl = slots[k % 2]
+        stream.wait_event(sl["geo_ready"])
+        for b, nme in scene.vertex_buffers.items():
+            st.vertexBuffers[b] = shards[nme][0][k % 2].data_ptr()
+        if scene.index_buffer:
+            st.indexBuffer = shards[scene.index_buffer][0][k % 2].data_ptr()
         dev.flush()  # the index and vertex bytes were rewritten behind the library's back (copy_ + NCCL): drop what it remembers of them
         dev.upload_async(sod.m.addr["ubo"], dev.allocs[ubo_stage][1], ubo.nbytes)
         rig.frame()
+        sl["geo_free"].record(stream)
         if band_bytes:
             stream.wait_event(sl["read"])                       # the staging buffer's previous contents have reached the host
             dev.copy_rows(sl["staging"].data_ptr(), band_bytes, band_addr, band_bytes, band_bytes, 1)
@@ -540,8 +574,14 @@ def e2e_multi(torch, dist, rig, local, steps):
             dev2.download_into_async(sl["host"], sl["staging"].data_ptr(), band_bytes)
             sl["read"].record(stream2)
 
-    for k in range(4):
-        step(k)
+    def run(count):
+        prefetch(0)
+        for k in range(count):
+            if k + 1 < count:
+                prefetch(k + 1)  # every rank issues its collectives in this same order
+            render(k)
+
+    run(4)
     torch.cuda.synchronize()
     if band_bytes:
         want = dev.download(band_addr, band_bytes)
@@ -552,20 +592,20 @@ def e2e_multi(torch, dist, rig, local, steps):
     n = max(steps, 200) if rig.work.key == "c3" else steps
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for k in range(n):
-        step(k)
-    dist.barrier(); torch.cuda.synchronize()  # both streams have drained
+    run(n)
+    dist.barrier(); torch.cuda.synchronize()  # all streams have drained
     t = torch.tensor([(time.perf_counter() - t0) * 1e3 / n], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     for b in scene.vertex_buffers:
         st.vertexBuffers[b] = saved[0][b]
     st.indexBuffer = saved[1]
+    dev.flush()
     dev2.close()
     h2d = sum(v[3] for v in shards.values()) + ubo.nbytes * world
     return {"ms_per_step": float(t[0]), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": scene.color.nbytes, "frames_timed": n,
-            "through": "C ABI on every rank: 1/N of the geometry per rank from pinned host memory + NCCL all-gather over NVLink, clear / draw with "
-                       "the fused peer stores + ordering all-reduce, copy_rows of the rank's band to a staging buffer, mem_download_async on a second "
-                       "device object; read-back of frame k overlapped with frame k+1; max over ranks"}
+            "through": "C ABI on every rank: 1/N of the geometry per rank from pinned host memory + NCCL all-gather over NVLink (copy stream, "
+                       "two buffer sets: frame k+1's geometry arrives while frame k renders), clear / draw with the fused peer stores + the ordering "
+                       "step, copy_rows of the rank's band to a staging buffer, mem_download_async on a second device object; max over ranks"}
 
 
 def icd_leg(scene, frames=40):
@@ -610,7 +650,7 @@ def run_ours(args):
     assert stream.cuda_stream != 0
 
     work = Workload(args.config)
-    rig = Rig(work, torch, dist, stream, local, rank, world, args.gather)
+    rig = Rig(work, torch, dist, stream, local, rank, world, args.gather, args.barrier)
     if world > 1:
         verify_exchange(rig)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -649,7 +689,8 @@ def run_ours(args):
         icd = icd_leg(work.scene) if (world == 1 and work.key == "c3" and not args.no_extras) else None
         exchange = ""
         if world > 1:
-            exchange = " + bands stored by k_raster over NVLink into %s + 4-byte NCCL all-reduce" % ("every GPU's frame" if args.gather == "all" else "the presenting GPU's frame (rank 0)")
+            exchange = " + bands stored by k_raster over NVLink into %s + %s" % ("every GPU's frame" if args.gather == "all" else "the presenting GPU's frame (rank 0)",
+                                                                                     "cpvk_cuda_peer_barrier" if args.barrier == "flags" else "4-byte NCCL all-reduce")
         blocks = m["blocks"]
         line = {
             "metric": work.metric, "value": work.units(m["n_cov"]) / (ms_step * 1e-3) / work.scale, "unit": work.unit,
@@ -702,7 +743,7 @@ def secondary_configs(args, torch, dist, stream, local, rank, world, main_rig):
     if args.config == "c3":
         quads = 100
         w4 = Workload("c4", quads=quads)
-        rig = Rig(w4, torch, dist, stream, local, rank, world, args.gather)
+        rig = Rig(w4, torch, dist, stream, local, rank, world, args.gather, args.barrier)
         if world > 1:
             verify_exchange(rig)
         m = measure_short(rig, reps=3)
@@ -777,6 +818,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=["c3", "c4"], help="c3 (default): the 1M-triangle 4K draw; c4: all 2,000 blended quads at 8K")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--barrier", default="flags", choices=["flags", "nccl"], help="multi-GPU per-frame ordering step: cpvk_cuda_peer_barrier (flag words in peer-mapped memory) or a 4-byte NCCL all-reduce")
     ap.add_argument("--gather", default="one", choices=["one", "all"], help="multi-GPU exchange target of k_raster's peer stores: the presenting GPU (rank 0) or every GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the short C4 / C5 measurements (other_configs) and the ICD leg")
     args = ap.parse_args()

@@ -156,7 +156,7 @@ ABI_SYMBOLS = [
     "cpvk_cuda_launch_count", "cpvk_cuda_clear", "cpvk_cuda_copy_rows", "cpvk_cuda_blit",
     "cpvk_cuda_flush", "cpvk_cuda_device_set_lazy_clear", "cpvk_cuda_device_set_speculation", "cpvk_cuda_mem_download_async",
     "cpvk_cuda_abi_sizeof",
-    "cpvk_cuda_device_create_group", "cpvk_cuda_group_size", "cpvk_cuda_gather", "cpvk_cuda_mem_export", "cpvk_cuda_mem_import", "cpvk_cuda_mem_unimport", "cpvk_cuda_selftest_div",
+    "cpvk_cuda_device_create_group", "cpvk_cuda_group_size", "cpvk_cuda_gather", "cpvk_cuda_mem_export", "cpvk_cuda_mem_import", "cpvk_cuda_mem_unimport", "cpvk_cuda_peer_barrier", "cpvk_cuda_selftest_div",
 ]
 
 
@@ -223,6 +223,7 @@ def load_cuda():
     lib.cpvk_cuda_mem_export.argtypes = [vp, u64, vp]
     lib.cpvk_cuda_mem_import.argtypes = [vp, vp, C.POINTER(u64)]
     lib.cpvk_cuda_mem_unimport.argtypes = [vp, u64]
+    lib.cpvk_cuda_peer_barrier.argtypes = [vp, C.POINTER(u64), u32, u32, u32]
     lib.cpvk_cuda_selftest_div.argtypes = [vp, u64, u64, u32, u64, u64]
     _cuda_lib = lib
     return lib

@@ -557,6 +557,27 @@ __global__ void __launch_bounds__(256) k_selftest_div(const float* a, const floa
 }
 
 // ---- host-callable launchers (cpvk_abi.cpp is plain C++) ----
+// cpvk_cuda_peer_barrier (include/cpvk_cuda.h): lane i signals participant i, then waits for participant i's signal.
+struct CpvkPeerFlags { cpvk_u32* p[16]; };
+__global__ void __launch_bounds__(32) k_peer_barrier(CpvkPeerFlags f, cpvk_u32 count, cpvk_u32 self, cpvk_u32 sequence) {
+    const cpvk_u32 i = threadIdx.x;
+    if (i >= count || i == self) return;
+    // the kernels before this one in the stream are complete, their stores (peer memory included) performed; the release
+    // makes the flag the last thing a peer can see of them
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(f.p[i] + self), "r"(sequence) : "memory");
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        cpvk_u32 v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.p[self] + i) : "memory");
+        if ((cpvk_i32)(v - sequence) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 10000000000ull) __trap(); // a participant never arrived: fail loudly rather than hang the GPU
+        __nanosleep(40);
+    }
+}
+
 static inline unsigned cpvk_grid(unsigned long long n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 extern "C" {
@@ -600,6 +621,12 @@ cudaError_t cpvk_launch_copy_rows(unsigned long long dst, unsigned dstPitch, uns
     unsigned grid = cpvk_grid((unsigned long long)rowBytes * rows / 16 + 1, 256);
     if (grid > 148 * 16) grid = 148 * 16;
     k_copy_rows<<<grid, 256, 0, s>>>((cpvk_u8*)dst, dstPitch, (const cpvk_u8*)src, srcPitch, rowBytes, rows);
+    return cudaGetLastError();
+}
+cudaError_t cpvk_launch_peer_barrier(const unsigned long long* flagArrays, unsigned count, unsigned self, unsigned sequence, cudaStream_t s) {
+    CpvkPeerFlags f{};
+    for (unsigned i = 0; i < count && i < 16; i++) f.p[i] = reinterpret_cast<cpvk_u32*>(flagArrays[i]);
+    k_peer_barrier<<<1, 32, 0, s>>>(f, count, self, sequence);
     return cudaGetLastError();
 }
 cudaError_t cpvk_launch_selftest_div(const float* a, const float* b, unsigned n, float* shared, float* plain, cudaStream_t s) {

@@ -145,6 +145,11 @@ class Device:
     def unimport(self, addr):
         _check(self.lib, self.lib.cpvk_cuda_mem_unimport(self.handle, addr))
 
+    def peer_barrier(self, flag_arrays, self_index, sequence):
+        """cpvk_cuda_peer_barrier: device-side ordering between the GPUs of a one-process-per-GPU run."""
+        arr = (C.c_uint64 * len(flag_arrays))(*flag_arrays)
+        _check(self.lib, self.lib.cpvk_cuda_peer_barrier(self.handle, arr, len(flag_arrays), self_index, sequence))
+
     def launch_count(self):
         return int(self.lib.cpvk_cuda_launch_count(self.handle))
 

@@ -320,6 +320,16 @@ int cpvk_cuda_gather(CpvkDevice* device, const CpvkAttachment* images, uint32_t 
 int cpvk_cuda_mem_export(CpvkDevice* device, uint64_t dev, void* handle64);
 int cpvk_cuda_mem_import(CpvkDevice* device, const void* handle64, uint64_t* outDev);
 int cpvk_cuda_mem_unimport(CpvkDevice* device, uint64_t dev);
+/* The ordering step of such a run, on the device instead of through a collective library: one small kernel on the device's
+   stream that (1) stores `sequence` into word `self` of every participant's flag array — a system-scope release, so
+   everything this stream did before, k_raster's stores into peers' frames included, is visible to whoever sees the flag —
+   and (2) waits until every word of its OWN flag array has reached `sequence`. Work enqueued behind it therefore runs after
+   every participant's stream has reached its own call with this sequence number. flagArrays[i] = participant i's array as
+   addressable from this device (own allocation for i == self, cpvk_cuda_mem_import for the others), `count` <= 16 words
+   each, zero-filled (cpvk_cuda_mem_alloc does that); sequence starts at 1 and grows by one per call on every participant.
+   A participant that never arrives makes the kernel trap after 10 s (every later call on the device then fails) instead
+   of hanging the GPU. */
+int cpvk_cuda_peer_barrier(CpvkDevice* device, const uint64_t* flagArrays, uint32_t count, uint32_t self, uint32_t sequence);
 
 /* Diagnostics. The kernels divide several numerators by one denominator through one shared reciprocal (edge weights / area,
    interpolated components / denominator, position / w), claiming the bits of the IEEE `/` operator: this runs both on device
