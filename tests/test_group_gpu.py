@@ -144,35 +144,27 @@ def test_icd_on_a_group(tmp_path, built, devices):
 
 def test_peer_barrier_orders_streams(built):
     """cpvk_cuda_peer_barrier (the per-frame ordering step of one-process-per-GPU runs): a participant's work behind the barrier
-    runs after every participant's work in front of it. Two device objects with their own streams stand in for two GPUs; the
-    consumer's calls are enqueued BEFORE the producer's, so only the flag words can order them. With >= 2 GPUs the second
-    participant lives on the other GPU and signals through a peer mapping of the flags."""
-    n = gpu_count()
-    prod, cons = Device(0, stats=False), Device(1 if n >= 2 else 0, stats=False)
+    runs after every participant's work in front of it. Two device objects with their own streams on one GPU stand in for two
+    processes; the consumer's calls are enqueued BEFORE the producer's, so only the flag words can order them. (Across real
+    GPUs the flag arrays are cudaIpc mappings, which only another process can open: bench.py --gpus N runs that, and checks
+    the exchanged frame byte for byte.)"""
+    prod, cons = Device(0, stats=False), Device(0, stats=False)
     size = 1 << 20
     try:
         fp, fc = prod.alloc(64), cons.alloc(64)
         src, data, out = prod.alloc(size), prod.alloc(size), cons.alloc(size)
         prod.sync(); cons.sync()
-        if n >= 2:  # the other GPU reaches the producer's memory through the export / import pair of the C ABI
-            fp_c, fc_p, data_c = cons.import_handle(prod.export_handle(fp)), prod.import_handle(cons.export_handle(fc)), cons.import_handle(prod.export_handle(data))
-        else:
-            fp_c, fc_p, data_c = fp, fc, data
         with pytest.raises(Exception):
-            prod.peer_barrier([fp, fc_p], 2, 1)  # self outside the participants
+            prod.peer_barrier([fp, fc], 2, 1)  # self outside the participants
         for k in range(8):
             pattern = np.random.default_rng(k).integers(0, 256, size, dtype=np.uint8)
-            cons.peer_barrier([fp_c, fc], 1, 2 * k + 1)                   # waits for the producer's copy below
-            cons.copy_rows(out, size, data_c, size, size, 1)
-            cons.peer_barrier([fp_c, fc], 1, 2 * k + 2)                   # tells the producer that `data` may be overwritten
+            cons.peer_barrier([fp, fc], 1, 2 * k + 1)                     # waits for the producer's copy below
+            cons.copy_rows(out, size, data, size, size, 1)
+            cons.peer_barrier([fp, fc], 1, 2 * k + 2)                     # tells the producer that `data` may be overwritten
             prod.upload(src, pattern)
             prod.copy_rows(data, size, src, size, size, 1)
-            prod.peer_barrier([fp, fc_p], 0, 2 * k + 1)
-            prod.peer_barrier([fp, fc_p], 0, 2 * k + 2)
+            prod.peer_barrier([fp, fc], 0, 2 * k + 1)
+            prod.peer_barrier([fp, fc], 0, 2 * k + 2)
             assert np.array_equal(cons.download(out, size), pattern), "round %d: the consumer ran ahead of the producer" % k
-        if n >= 2:
-            for a in (fp_c, data_c):
-                cons.unimport(a)
-            prod.unimport(fc_p)
     finally:
         prod.close(); cons.close()
