@@ -285,6 +285,10 @@ class Rig:
         from cpvulkan_b200.device import Device, SceneOnDevice
         self.torch, self.dist, self.work, self.rank, self.world = torch, dist, work, rank, world
         self.dev = Device(local, stream=stream.cuda_stream, stats=True)
+        # front-end overlap across frames (include/cpvk_cuda.h): the bench's own stream carries nothing between two frames that
+        # writes a frame's inputs except where it calls flush() (the e2e leg on N > 1 GPUs); CPVK_OVERLAP=0 switches it off
+        if os.environ.get("CPVK_OVERLAP", "1") != "0":
+            self.dev.set_overlap(True)
         self.sod = SceneOnDevice(self.dev, work.scene)
         scene = work.scene
         self.band = band_rows(scene.color.height, rank, world) if world > 1 else None
@@ -537,17 +541,19 @@ def e2e_multi(torch, dist, rig, local, steps):
     scene, dev, sod, rank, world = rig.work.scene, rig.dev, rig.sod, rig.rank, rig.world
     stream = torch.cuda.current_stream()
     copy_stream = torch.cuda.Stream()
+    # the frame's geometry as one byte string (vertex buffers, then the index buffer, each 256-byte aligned), cut into N shards:
+    # one pinned-memory copy and one all-gather per frame whatever the number of buffers
     names = [n for n in ("vb", "ib") if n in scene.buffers]
-    shards = {}
+    offsets, total = {}, 0
     for nme in names:
-        data = scene.buffers[nme]
-        per = (data.nbytes + world - 1) // world
-        per = (per + 15) // 16 * 16
-        fulls = [torch.zeros(per * world, dtype=torch.uint8, device="cuda") for _ in range(2)]  # the gathered copies the draws read
-        host = torch.zeros(per, dtype=torch.uint8).pin_memory()
-        chunk = data[rank * per:(rank + 1) * per]
-        host[:len(chunk)] = torch.from_numpy(np.ascontiguousarray(chunk))
-        shards[nme] = (fulls, host, per, data.nbytes)
+        offsets[nme] = total
+        total += (scene.buffers[nme].nbytes + 255) // 256 * 256
+    per = ((total + world - 1) // world + 15) // 16 * 16
+    blob = np.zeros(per * world, dtype=np.uint8)
+    for nme in names:
+        blob[offsets[nme]:offsets[nme] + scene.buffers[nme].nbytes] = scene.buffers[nme]
+    fulls = [torch.zeros(per * world, dtype=torch.uint8, device="cuda") for _ in range(2)]  # the gathered copies the draws read
+    host = torch.from_numpy(blob[rank * per:(rank + 1) * per].copy()).pin_memory()
     ubo = scene.buffers["ubo"]
     ubo_stage = dev.alloc(ubo.nbytes, host_shadow=True)
     dev.shadow(ubo_stage)[:ubo.nbytes] = ubo
@@ -572,20 +578,18 @@ def e2e_multi(torch, dist, rig, local, steps):
         sl = slots[k % 2]
         copy_stream.wait_event(sl["geo_free"])  # the draw that read this buffer set (frame k - 2) is done
         with torch.cuda.stream(copy_stream):
-            for nme in names:
-                fulls, host, per, _ = shards[nme]
-                mine = fulls[k % 2][rank * per:(rank + 1) * per]
-                mine.copy_(host, non_blocking=True)
-                dist.all_gather_into_tensor(fulls[k % 2], mine)
+            mine = fulls[k % 2][rank * per:(rank + 1) * per]
+            mine.copy_(host, non_blocking=True)
+            dist.all_gather_into_tensor(fulls[k % 2], mine)
             sl["geo_ready"].record(copy_stream)
 
     def render(k):
         sl = slots[k % 2]
         stream.wait_event(sl["geo_ready"])
         for b, nme in scene.vertex_buffers.items():
-            st.vertexBuffers[b] = shards[nme][0][k % 2].data_ptr()
+            st.vertexBuffers[b] = fulls[k % 2].data_ptr() + offsets[nme]
         if scene.index_buffer:
-            st.indexBuffer = shards[scene.index_buffer][0][k % 2].data_ptr()
+            st.indexBuffer = fulls[k % 2].data_ptr() + offsets[scene.index_buffer]
         dev.flush()  # the index and vertex bytes were rewritten behind the library's back (copy_ + NCCL): drop what it remembers of them
         dev.upload_async(sod.m.addr["ubo"], dev.allocs[ubo_stage][1], ubo.nbytes)
         rig.frame()
@@ -625,7 +629,7 @@ def e2e_multi(torch, dist, rig, local, steps):
     st.indexBuffer = saved[1]
     dev.flush()
     dev2.close()
-    h2d = sum(v[3] for v in shards.values()) + ubo.nbytes * world
+    h2d = sum(scene.buffers[nme].nbytes for nme in names) + ubo.nbytes * world
     return {"ms_per_step": float(t[0]), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": scene.color.nbytes, "frames_timed": n,
             "through": "C ABI on every rank: 1/N of the geometry per rank from pinned host memory + NCCL all-gather over NVLink (copy stream, "
                        "two buffer sets: frame k+1's geometry arrives while frame k renders), clear / draw with the fused peer stores + the ordering "

@@ -154,7 +154,7 @@ ABI_SYMBOLS = [
     "cpvk_cuda_pipeline_create", "cpvk_cuda_pipeline_destroy", "cpvk_cuda_pipeline_source",
     "cpvk_cuda_pipeline_cubin", "cpvk_cuda_pipeline_compile_only", "cpvk_cuda_draw", "cpvk_cuda_last_draw_stats",
     "cpvk_cuda_launch_count", "cpvk_cuda_clear", "cpvk_cuda_copy_rows", "cpvk_cuda_blit",
-    "cpvk_cuda_flush", "cpvk_cuda_device_set_lazy_clear", "cpvk_cuda_device_set_speculation", "cpvk_cuda_mem_download_async",
+    "cpvk_cuda_flush", "cpvk_cuda_device_set_lazy_clear", "cpvk_cuda_device_set_speculation", "cpvk_cuda_device_set_overlap", "cpvk_cuda_mem_download_async",
     "cpvk_cuda_abi_sizeof",
     "cpvk_cuda_device_create_group", "cpvk_cuda_group_size", "cpvk_cuda_gather", "cpvk_cuda_mem_export", "cpvk_cuda_mem_import", "cpvk_cuda_mem_unimport", "cpvk_cuda_peer_barrier", "cpvk_cuda_selftest_div",
 ]
@@ -212,6 +212,7 @@ def load_cuda():
     lib.cpvk_cuda_mem_download_async.argtypes = [vp, vp, u64, C.c_size_t]
     lib.cpvk_cuda_device_set_lazy_clear.argtypes = [vp, C.c_int]
     lib.cpvk_cuda_device_set_speculation.argtypes = [vp, C.c_int]
+    lib.cpvk_cuda_device_set_overlap.argtypes = [vp, C.c_int]
     lib.cpvk_cuda_copy_rows.argtypes = [vp, u64, u32, u64, u32, u32, u32]
     lib.cpvk_cuda_blit.argtypes = [vp, C.POINTER(Blit)]
     lib.cpvk_cuda_abi_sizeof.argtypes = [C.c_char_p]

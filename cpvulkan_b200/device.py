@@ -55,6 +55,10 @@ class Device:
         """Speculative draw tails (default on): see cpvk_cuda_device_set_speculation in include/cpvk_cuda.h."""
         _check(self.lib, self.lib.cpvk_cuda_device_set_speculation(self.handle, int(on)))
 
+    def set_overlap(self, on):
+        """Front-end overlap across draws (default: on for the device's own stream): see cpvk_cuda_device_set_overlap."""
+        _check(self.lib, self.lib.cpvk_cuda_device_set_overlap(self.handle, int(on)))
+
     def flush(self):
         _check(self.lib, self.lib.cpvk_cuda_flush(self.handle))
 

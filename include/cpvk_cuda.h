@@ -299,6 +299,17 @@ int cpvk_cuda_flush(CpvkDevice* device);
    call — a collective, an event, a copy — is ordered after the complete draw; on the device's own stream it happens at the
    next entry point. 0 turns speculation off: every draw then waits for its counts (one host round trip). */
 int cpvk_cuda_device_set_speculation(CpvkDevice* device, int enable);
+/* Front-end overlap: the front end of a draw (descriptor copy, vertex stage, primitive setup, binning) reads only the draw's
+   inputs and writes scratch memory of its own, so it runs on an internal second stream while the PREVIOUS draw's raster
+   kernel is still busy — whenever the library can tell that nothing in flight writes those inputs: back-to-back draws with
+   no other command of this header in between (cpvk_cuda_peer_barrier excepted), no shader stores, the remembered index
+   range, and the previous draw's attachments outside every allocation (cpvk_cuda_mem_alloc) this draw's vertex buffers,
+   index buffer and descriptors point into. Everything else is ordered exactly as before; results never differ.
+   On the device's own stream this is on by default. On a stream supplied through cpvk_cuda_device_set_stream foreign work
+   may sit between two draws where the library cannot see it, so it is off unless enabled here — the caller then promises
+   to call cpvk_cuda_flush after foreign work on that stream that writes anything a later draw reads (the same promise the
+   remembered index range asks for). CPVK_OVERLAP=0 / 1 in the environment overrides the default for every device. */
+int cpvk_cuda_device_set_overlap(CpvkDevice* device, int enable);
 int cpvk_cuda_device_set_lazy_clear(CpvkDevice* device, int enable);
 
 /* ---- multi-GPU (the reference's hook is the device-group plumbing it accepts and ignores, Queue.cpp:27-29, :52-74) ----

@@ -814,3 +814,84 @@ def test_multiple_descriptor_sets_and_uniform_arrays(dev):
     stride exceeds the element size, one of them indexed dynamically."""
     compare(dev, scenes.multiple_sets(200, 150, filt=scenes.LINEAR))
     compare(dev, scenes.ubo_arrays(200, 150))
+
+
+# ---- front-end overlap (cpvk_cuda_device_set_overlap): a draw's vertex / setup / binning work runs on a second stream while the
+# previous draw's raster kernel is busy; results must not depend on it ----
+
+def test_front_end_overlap_alternating_draws(built):
+    """Back-to-back frames of two different scenes on one device (its own stream: overlap is on by default), no other command
+    in between: draw k+1's front end runs while draw k rasterises, on the other scratch set. Every frame equals the oracle's,
+    and equals the same sequence with overlap switched off."""
+    from cpvulkan_b200.device import Device, SceneOnDevice
+    a = scenes.mesh_indexed(width=640, height=400, nx=160, ny=100)
+    b = scenes.random_triangles(width=320, height=240, tris=700, seed=77, indexed=4)
+    want = {id(a): scenes.run_oracle(a), id(b): scenes.run_oracle(b)}
+    for overlap in (True, False):
+        d = Device(0, stats=False)
+        d.set_overlap(overlap)
+        sa, sb = SceneOnDevice(d, a), SceneOnDevice(d, b)
+        try:
+            for _ in range(6):
+                sa.clear(); sa.draw()
+                sb.clear(); sb.draw()
+            sa.draw()  # the same draw again on top of its own result, no clear: depth test LESS_OR_EQUAL passes again, same bytes
+            for sod, sc in ((sa, a), (sb, b)):
+                oc, od, _ = want[id(sc)]
+                assert np.array_equal(sod.read_color(), oc), "overlap=%s: colour of %s differs" % (overlap, sc.name)
+                assert np.array_equal(sod.read_depth(), od), "overlap=%s: depth of %s differs" % (overlap, sc.name)
+        finally:
+            sa.close(); sb.close(); d.close()
+
+
+def test_front_end_overlap_waits_for_a_vertex_buffer_being_rendered(built):
+    """Render to vertex buffer: draw 2 reads its vertices from the RGBA32F colour attachment draw 1 is still rendering. The
+    front end of draw 2 must not start before draw 1's raster kernel is done (the attachment lies in an allocation draw 2's
+    vertex buffer points into: no overlap)."""
+    from cpvulkan_b200.device import Device, SceneOnDevice
+    s1 = scenes.overdraw_quads(256, 256, quads=40, tex_size=64, blend=False, color_fmt=scenes.R32G32B32A32_SFLOAT)
+    s1.textures[0].image.data.reshape(-1, 4)[:, 3] = 255  # alpha 1.0: the pixels become positions with w = 1
+    o1, _, _ = scenes.run_oracle(s1)
+    tris = 300
+    s2 = scenes.random_triangles(width=200, height=160, tris=tris, seed=5, perspective=False)
+    s2.buffers["vb"] = np.ascontiguousarray(o1[:tris * 3 * 32])  # vertex i = pixels 2i (position) and 2i + 1 (colour) of draw 1's frame
+    o2c, o2d, _ = scenes.run_oracle(s2)
+    d = Device(0, stats=False)
+    a1, a2 = SceneOnDevice(d, s1), SceneOnDevice(d, s2)
+    try:
+        a2.m.state.vertexBuffers[0] = a1.m.addr["color"]
+        for _ in range(3):
+            a1.clear(); a1.draw()
+            a2.clear(); a2.draw()
+        assert np.array_equal(a1.read_color(), o1)
+        assert np.array_equal(a2.read_color(), o2c) and np.array_equal(a2.read_depth(), o2d)
+    finally:
+        a1.close(); a2.close(); d.close()
+
+
+def test_front_end_overlap_on_a_caller_stream(built):
+    """On a caller-supplied stream overlap is opt-in; with it on, uploads between frames (which change what the vertex stage
+    reads) still order the next front end behind them."""
+    import torch
+    from cpvulkan_b200.device import Device, SceneOnDevice
+    stream = torch.cuda.Stream()
+    d = Device(0, stream=stream.cuda_stream, stats=False)
+    d.set_overlap(True)
+    sc = scenes.mesh_indexed(width=480, height=320, nx=120, ny=80)
+    sod = SceneOnDevice(d, sc)
+    try:
+        for k in range(5):
+            sod.clear(); sod.draw()
+            sod.clear(); sod.draw()
+        oc, od, _ = scenes.run_oracle(sc)
+        assert np.array_equal(sod.read_color(), oc) and np.array_equal(sod.read_depth(), od)
+        # move the mesh: a new uniform matrix between two frames
+        ubo = sc.buffers["ubo"].view(np.float32).copy().reshape(4, 4)
+        ubo[0, 0] *= 0.5
+        sc.buffers["ubo"] = ubo.reshape(-1).view(np.uint8)
+        d.upload(sod.m.addr["ubo"], sc.buffers["ubo"])
+        sod.clear(); sod.draw()
+        oc, od, _ = scenes.run_oracle(sc)
+        assert np.array_equal(sod.read_color(), oc) and np.array_equal(sod.read_depth(), od)
+    finally:
+        sod.close(); d.close()
