@@ -333,6 +333,7 @@ class Rig:
                 self.sequence += 1
                 self.dev.peer_barrier(self.flag_arrays, self.rank, self.sequence)
             else:
+                self.dev.flush()  # foreign work behind a draw on this stream: the draw is validated (and replayed if need be) first
                 self.dist.all_reduce(self.token)
 
     def single_gpu_frame(self):
@@ -357,7 +358,7 @@ class Rig:
         self.dev.close()
 
 
-def timed_blocks(torch, dist, world, frame, steps, min_seconds=0.5, min_frames=200, min_blocks=5, max_blocks=400, enough_seconds=3.0):
+def timed_blocks(torch, dist, world, frame, steps, flush, min_seconds=0.5, min_frames=200, min_blocks=5, max_blocks=400, enough_seconds=3.0):
     """Blocks of exactly `steps` frames, each bracketed by barrier + synchronize and timed with CUDA events on the current
     stream; per block the max over ranks. Returns the list of block times in ms."""
     def barrier():
@@ -373,6 +374,7 @@ def timed_blocks(torch, dist, world, frame, steps, min_seconds=0.5, min_frames=2
         e0.record()
         for _ in range(steps):
             frame()
+        flush()  # the library may still owe the last draw its validation (include/cpvk_cuda.h, set_overlap): nothing foreign — this event — goes behind it before that
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -401,7 +403,7 @@ def measure(rig, steps, warmup, sampler=None):
     launches0 = dev.launch_count()
     if sampler and sampler.nvml_samples:
         sampler.mark()  # NVML samples every 2 ms: keep only those taken inside the timed region
-    blocks = timed_blocks(torch, dist, world, rig.frame, steps)
+    blocks = timed_blocks(torch, dist, world, rig.frame, steps, rig.dev.flush)
     launches = (dev.launch_count() - launches0) / (len(blocks) * steps)
     ms_step = statistics.median(blocks) / steps
     # per-kernel durations (CUDA events inside the library, a separate pass so that they do not perturb `value`)
@@ -593,6 +595,7 @@ def e2e_multi(torch, dist, rig, local, steps):
         dev.flush()  # the index and vertex bytes were rewritten behind the library's back (copy_ + NCCL): drop what it remembers of them
         dev.upload_async(sod.m.addr["ubo"], dev.allocs[ubo_stage][1], ubo.nbytes)
         rig.frame()
+        dev.flush()                                             # events of this script go behind the draw: have it validated first
         sl["geo_free"].record(stream)
         if band_bytes:
             stream.wait_event(sl["read"])                       # the staging buffer's previous contents have reached the host
@@ -850,7 +853,7 @@ def measure_short(rig, reps):
         dist.all_reduce(t)
         n_cov = int(t[0])
     rig.dev.set_stats(False)
-    blocks = timed_blocks(torch, dist, world, rig.frame, reps, min_seconds=0.0, min_frames=reps, min_blocks=3, max_blocks=3)
+    blocks = timed_blocks(torch, dist, world, rig.frame, reps, rig.dev.flush, min_seconds=0.0, min_frames=reps, min_blocks=3, max_blocks=3)
     return {"ms": statistics.median(blocks) / reps, "n_cov": n_cov}
 
 

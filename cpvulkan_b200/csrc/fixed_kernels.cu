@@ -559,9 +559,10 @@ __global__ void __launch_bounds__(256) k_selftest_div(const float* a, const floa
 // ---- host-callable launchers (cpvk_abi.cpp is plain C++) ----
 // cpvk_cuda_peer_barrier (include/cpvk_cuda.h): lane i signals participant i, then waits for participant i's signal.
 struct CpvkPeerFlags { cpvk_u32* p[16]; };
-__global__ void __launch_bounds__(32) k_peer_barrier(CpvkPeerFlags f, cpvk_u32 count, cpvk_u32 self, cpvk_u32 sequence) {
+__global__ void __launch_bounds__(32) k_peer_barrier(CpvkPeerFlags f, cpvk_u32 count, cpvk_u32 self, cpvk_u32 sequence, const cpvk_u32* verdict) {
     const cpvk_u32 i = threadIdx.x;
     if (i >= count || i == self) return;
+    if (verdict && verdict[3] != 0) return; // the draw in front of this barrier was a no-op (plan mismatch): the host replays it, then the barrier
     // the kernels before this one in the stream are complete, their stores (peer memory included) performed; the release
     // makes the flag the last thing a peer can see of them
     __threadfence_system();
@@ -623,10 +624,10 @@ cudaError_t cpvk_launch_copy_rows(unsigned long long dst, unsigned dstPitch, uns
     k_copy_rows<<<grid, 256, 0, s>>>((cpvk_u8*)dst, dstPitch, (const cpvk_u8*)src, srcPitch, rowBytes, rows);
     return cudaGetLastError();
 }
-cudaError_t cpvk_launch_peer_barrier(const unsigned long long* flagArrays, unsigned count, unsigned self, unsigned sequence, cudaStream_t s) {
+cudaError_t cpvk_launch_peer_barrier(const unsigned long long* flagArrays, unsigned count, unsigned self, unsigned sequence, const cpvk_u32* verdict, cudaStream_t s) {
     CpvkPeerFlags f{};
     for (unsigned i = 0; i < count && i < 16; i++) f.p[i] = reinterpret_cast<cpvk_u32*>(flagArrays[i]);
-    k_peer_barrier<<<1, 32, 0, s>>>(f, count, self, sequence);
+    k_peer_barrier<<<1, 32, 0, s>>>(f, count, self, sequence, verdict);
     return cudaGetLastError();
 }
 cudaError_t cpvk_launch_selftest_div(const float* a, const float* b, unsigned n, float* shared, float* plain, cudaStream_t s) {

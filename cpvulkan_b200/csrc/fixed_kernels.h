@@ -79,6 +79,6 @@ cudaError_t cpvk_launch_bin_sort(const CpvkBinArgs* a, unsigned capacity, cudaSt
 cudaError_t cpvk_launch_clear(const CpvkDevAttachment* img, const CpvkClearArgs* c, cudaStream_t s);
 cudaError_t cpvk_launch_copy_rows(unsigned long long dst, unsigned dstPitch, unsigned long long src, unsigned srcPitch, unsigned rowBytes, unsigned rows, cudaStream_t s);
 cudaError_t cpvk_launch_blit(const CpvkBlitArgs* b, cudaStream_t s);
-cudaError_t cpvk_launch_peer_barrier(const unsigned long long* flagArrays, unsigned count, unsigned self, unsigned sequence, cudaStream_t s);
+cudaError_t cpvk_launch_peer_barrier(const unsigned long long* flagArrays, unsigned count, unsigned self, unsigned sequence, const cpvk_u32* verdict /* null, or the binning words of an unsettled draw: [3] != 0 = do nothing, the host re-issues the barrier behind the replay */, cudaStream_t s);
 cudaError_t cpvk_launch_selftest_div(const float* a, const float* b, unsigned n, float* shared, float* plain, cudaStream_t s);
 }

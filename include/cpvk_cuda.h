@@ -306,9 +306,13 @@ int cpvk_cuda_device_set_speculation(CpvkDevice* device, int enable);
    range, and the previous draw's attachments outside every allocation (cpvk_cuda_mem_alloc) this draw's vertex buffers,
    index buffer and descriptors point into. Everything else is ordered exactly as before; results never differ.
    On the device's own stream this is on by default. On a stream supplied through cpvk_cuda_device_set_stream foreign work
-   may sit between two draws where the library cannot see it, so it is off unless enabled here — the caller then promises
-   to call cpvk_cuda_flush after foreign work on that stream that writes anything a later draw reads (the same promise the
-   remembered index range asks for). CPVK_OVERLAP=0 / 1 in the environment overrides the default for every device. */
+   may sit between two draws where the library cannot see it, so it is off unless enabled here. Enabling it makes the
+   library treat that stream like its own, and the caller promises two things: (1) cpvk_cuda_flush after foreign work on
+   the stream that writes anything a later draw reads (the promise the remembered index range asks for as well), and (2)
+   cpvk_cuda_flush BEFORE enqueuing foreign work that must come behind a draw (an event, a collective, a copy): the
+   validation of a speculative draw — and its replay — then waits for the next entry point of this header instead of
+   happening before cpvk_cuda_draw returns, and cpvk_cuda_flush is such an entry point.
+   CPVK_OVERLAP=0 / 1 in the environment overrides the default for every device. */
 int cpvk_cuda_device_set_overlap(CpvkDevice* device, int enable);
 int cpvk_cuda_device_set_lazy_clear(CpvkDevice* device, int enable);
 
@@ -338,6 +342,8 @@ int cpvk_cuda_mem_unimport(CpvkDevice* device, uint64_t dev);
    every participant's stream has reached its own call with this sequence number. flagArrays[i] = participant i's array as
    addressable from this device (own allocation for i == self, cpvk_cuda_mem_import for the others), `count` <= 16 words
    each, zero-filled (cpvk_cuda_mem_alloc does that); sequence starts at 1 and grows by one per call on every participant.
+   Called right behind a draw whose validation is still pending it costs no host round trip: the kernel reads the draw's
+   verdict on the device, does nothing if the draw has to be replayed, and is issued again behind the replay.
    A participant that never arrives makes the kernel trap after 10 s (every later call on the device then fails) instead
    of hanging the GPU. */
 int cpvk_cuda_peer_barrier(CpvkDevice* device, const uint64_t* flagArrays, uint32_t count, uint32_t self, uint32_t sequence);

@@ -142,29 +142,42 @@ def test_icd_on_a_group(tmp_path, built, devices):
             assert np.array_equal(gd, od), scene.name
 
 
-def test_peer_barrier_orders_streams(built):
-    """cpvk_cuda_peer_barrier (the per-frame ordering step of one-process-per-GPU runs): a participant's work behind the barrier
-    runs after every participant's work in front of it. Two device objects with their own streams on one GPU stand in for two
-    processes; the consumer's calls are enqueued BEFORE the producer's, so only the flag words can order them. (Across real
-    GPUs the flag arrays are cudaIpc mappings, which only another process can open: bench.py --gpus N runs that, and checks
-    the exchanged frame byte for byte.)"""
-    prod, cons = Device(0, stats=False), Device(0, stats=False)
-    size = 1 << 20
+def run_barrier_pair(tmp_path, scenario):
+    """Two PROCESSES on GPU 0 (tests/peer_barrier_worker.py), the way one-process-per-GPU runs use the barrier: flag arrays
+    and data reach the other side as cudaIpc mappings. (Two streams of one process would do on paper, but a kernel that
+    spins on a flag may sit in front of the other stream's work in a shared hardware queue; separate processes have their
+    own queues and the GPU time-slices between them.)"""
+    import os
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "peer_barrier_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, role, scenario, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for role in ("producer", "consumer")]
+    outs = []
     try:
-        fp, fc = prod.alloc(64), cons.alloc(64)
-        src, data, out = prod.alloc(size), prod.alloc(size), cons.alloc(size)
-        prod.sync(); cons.sync()
-        with pytest.raises(Exception):
-            prod.peer_barrier([fp, fc], 2, 1)  # self outside the participants
-        for k in range(8):
-            pattern = np.random.default_rng(k).integers(0, 256, size, dtype=np.uint8)
-            cons.peer_barrier([fp, fc], 1, 2 * k + 1)                     # waits for the producer's copy below
-            cons.copy_rows(out, size, data, size, size, 1)
-            cons.peer_barrier([fp, fc], 1, 2 * k + 2)                     # tells the producer that `data` may be overwritten
-            prod.upload(src, pattern)
-            prod.copy_rows(data, size, src, size, size, 1)
-            prod.peer_barrier([fp, fc], 0, 2 * k + 1)
-            prod.peer_barrier([fp, fc], 0, 2 * k + 2)
-            assert np.array_equal(cons.download(out, size), pattern), "round %d: the consumer ran ahead of the producer" % k
+        for pr in procs:
+            out, _ = pr.communicate(timeout=240)
+            outs.append(out)
     finally:
-        prod.close(); cons.close()
+        for pr in procs:
+            if pr.poll() is None:
+                pr.kill()
+    for pr, out in zip(procs, outs):
+        assert pr.returncode == 0, out[-3000:]
+    assert "consumer ok" in outs[1], outs[1][-3000:]
+
+
+def test_peer_barrier_orders_two_processes(built, tmp_path):
+    """cpvk_cuda_peer_barrier (the per-frame ordering step of one-process-per-GPU runs): a participant's work behind the barrier
+    runs after every participant's work in front of it — the consumer copies what the producer wrote, eight rounds, each with
+    new bytes."""
+    run_barrier_pair(tmp_path, "copy")
+
+
+def test_peer_barrier_behind_a_draw_that_is_replayed(built, tmp_path):
+    """A barrier called right behind a draw does not wait for the draw's validation: it reads the verdict on the device. The
+    producer's first draw does not fit the launch plan of a fresh device (900 triangles over four tiles: more than the 512
+    list slots of single-pass binning), so its tail and the barriers behind it are no-ops, and all are issued again when the
+    next call looks at the verdict. The consumer copies the producer's frame behind the barrier: it must be the finished
+    one (the oracle's bytes), in the replayed round and in the rounds that run the learned plan."""
+    run_barrier_pair(tmp_path, "draw")
