@@ -358,6 +358,9 @@ class Rig:
         self.dev.close()
 
 
+HOST_ISSUE_MS = []
+
+
 def timed_blocks(torch, dist, world, frame, steps, flush, min_seconds=0.5, min_frames=200, min_blocks=5, max_blocks=400, enough_seconds=3.0):
     """Blocks of exactly `steps` frames, each bracketed by barrier + synchronize and timed with CUDA events on the current
     stream; per block the max over ranks. Returns the list of block times in ms."""
@@ -372,8 +375,10 @@ def timed_blocks(torch, dist, world, frame, steps, flush, min_seconds=0.5, min_f
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for _ in range(steps):
             frame()
+        HOST_ISSUE_MS.append((time.perf_counter() - t_host) * 1e3 / steps)  # how long the host needs to issue a frame (it may wait for the GPU inside)
         flush()  # the library may still owe the last draw its validation (include/cpvk_cuda.h, set_overlap): nothing foreign — this event — goes behind it before that
         e1.record()
         barrier()
@@ -403,7 +408,9 @@ def measure(rig, steps, warmup, sampler=None):
     launches0 = dev.launch_count()
     if sampler and sampler.nvml_samples:
         sampler.mark()  # NVML samples every 2 ms: keep only those taken inside the timed region
+    del HOST_ISSUE_MS[:]
     blocks = timed_blocks(torch, dist, world, rig.frame, steps, rig.dev.flush)
+    host_issue_ms = statistics.median(HOST_ISSUE_MS)
     launches = (dev.launch_count() - launches0) / (len(blocks) * steps)
     ms_step = statistics.median(blocks) / steps
     # per-kernel durations (CUDA events inside the library, a separate pass so that they do not perturb `value`)
@@ -419,7 +426,7 @@ def measure(rig, steps, warmup, sampler=None):
         dist.all_reduce(rig.token)
         torch.cuda.synchronize()
     return {"ms_step": ms_step, "blocks": blocks, "n_cov": n_cov, "n_pass": n_pass, "local_cov": local_cov, "local_pass": local_pass,
-            "launches_per_step": launches, "bin_entries": bin_entries,
+            "launches_per_step": launches, "bin_entries": bin_entries, "host_issue_ms": host_issue_ms,
             "kernel_ms": {"vertex": statistics.mean(vs), "setup": statistics.mean(su), "bin": statistics.mean(bn), "raster": statistics.mean(rs)}}
 
 
@@ -731,7 +738,7 @@ def run_ours(args):
             "blocks": {"count": len(blocks), "frames_timed": len(blocks) * args.steps, "seconds_timed": sum(blocks) / 1e3,
                        "ms_per_step_min": min(blocks) / args.steps, "ms_per_step_median": ms_step, "ms_per_step_max": max(blocks) / args.steps},
             "mtris_per_s": work.prims / (ms_step * 1e-3) / 1e6, "gfragments_per_s": m["n_cov"] / (ms_step * 1e-3) / 1e9, "ms_per_frame": ms_step,
-            "fragments_covered": m["n_cov"], "fragments_written": m["n_pass"], "bin_entries_rank0": m["bin_entries"],
+            "fragments_covered": m["n_cov"], "fragments_written": m["n_pass"], "bin_entries_rank0": m["bin_entries"], "host_issue_ms_rank0": m["host_issue_ms"],
             "kernel_ms_rank0": m["kernel_ms"],
             "roofline": {"bound": "hbm", "kernel": "cpvk_k_raster", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "traffic": raster_traffic(work, world),

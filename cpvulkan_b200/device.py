@@ -151,8 +151,10 @@ class Device:
 
     def peer_barrier(self, flag_arrays, self_index, sequence):
         """cpvk_cuda_peer_barrier: device-side ordering between the GPUs of a one-process-per-GPU run."""
-        arr = (C.c_uint64 * len(flag_arrays))(*flag_arrays)
-        _check(self.lib, self.lib.cpvk_cuda_peer_barrier(self.handle, arr, len(flag_arrays), self_index, sequence))
+        key = tuple(flag_arrays)
+        if getattr(self, "_barrier_key", None) != key:  # the same participants frame after frame: build the argument once
+            self._barrier_key, self._barrier_arr = key, (C.c_uint64 * len(flag_arrays))(*flag_arrays)
+        _check(self.lib, self.lib.cpvk_cuda_peer_barrier(self.handle, self._barrier_arr, len(flag_arrays), self_index, sequence))
 
     def launch_count(self):
         return int(self.lib.cpvk_cuda_launch_count(self.handle))
@@ -182,12 +184,17 @@ class SceneOnDevice:
         """Render-pass clear of the attachments. band_only: just the rows of this GPU's sort-first band (the other
         rows belong to other GPUs and are overwritten by the gather)."""
         y0, y1 = self.m.state.bandY0, self.m.state.bandY1
-        for img, att in ((self.scene.color, self.m.color_attachment), (self.scene.depth, self.m.depth_attachment)):
-            if img is not None and img.clear is not None:
-                cv, is_ds = scenes.clear_value(img)
-                if band_only and y1 > y0:
-                    att = capi.Attachment(att.address + y0 * att.rowPitch, att.width, min(y1, att.height) - y0, att.rowPitch, att.format)
-                self.dev.clear(att, cv, is_ds)
+        key = (band_only, y0, y1, getattr(self.m.color_attachment, "address", 0), getattr(self.m.depth_attachment, "address", 0))
+        if getattr(self, "_clear_key", None) != key:  # a frame loop clears the same rectangles every frame: build the arguments once
+            self._clear_key, self._clear_args = key, []
+            for img, att in ((self.scene.color, self.m.color_attachment), (self.scene.depth, self.m.depth_attachment)):
+                if img is not None and img.clear is not None:
+                    cv, is_ds = scenes.clear_value(img)
+                    if band_only and y1 > y0:
+                        att = capi.Attachment(att.address + y0 * att.rowPitch, att.width, min(y1, att.height) - y0, att.rowPitch, att.format)
+                    self._clear_args.append((att, cv, is_ds))
+        for att, cv, is_ds in self._clear_args:
+            self.dev.clear(att, cv, is_ds)
 
     def draw(self):
         self.dev.draw(self.m.state)
