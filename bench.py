@@ -588,11 +588,22 @@ def e2e_multi(torch, dist, rig, local, steps):
         copy_stream.wait_event(sl["geo_free"])  # the draw that read this buffer set (frame k - 2) is done
         with torch.cuda.stream(copy_stream):
             mine = fulls[k % 2][rank * per:(rank + 1) * per]
-            mine.copy_(host, non_blocking=True)
-            dist.all_gather_into_tensor(fulls[k % 2], mine)
+            if "upload" not in skip:
+                mine.copy_(host, non_blocking=True)
+            if "allgather" not in skip:
+                dist.all_gather_into_tensor(fulls[k % 2], mine)
             sl["geo_ready"].record(copy_stream)
 
+    trace = {} if os.environ.get("CPVK_E2E_TRACE") else None  # host seconds per phase, printed by rank 0 (tuning aid)
+    skip = os.environ.get("CPVK_E2E_SKIP", "").split(",")          # tuning aid: leave out "upload", "allgather" or "readback" to see what each costs
+
+    def lap(name, t0):
+        if trace is not None:
+            trace[name] = trace.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     def render(k):
+        t = time.perf_counter()
         sl = slots[k % 2]
         stream.wait_event(sl["geo_ready"])
         for b, nme in scene.vertex_buffers.items():
@@ -600,28 +611,34 @@ def e2e_multi(torch, dist, rig, local, steps):
         if scene.index_buffer:
             st.indexBuffer = fulls[k % 2].data_ptr() + offsets[scene.index_buffer]
         dev.flush()  # the index and vertex bytes were rewritten behind the library's back (copy_ + NCCL): drop what it remembers of them
+        t = lap("flush before", t)
         dev.upload_async(sod.m.addr["ubo"], dev.allocs[ubo_stage][1], ubo.nbytes)
         rig.frame()
+        t = lap("frame", t)
         dev.flush()                                             # events of this script go behind the draw: have it validated first
+        t = lap("flush behind", t)
         sl["geo_free"].record(stream)
-        if band_bytes:
+        if band_bytes and "readback" not in skip:
             stream.wait_event(sl["read"])                       # the staging buffer's previous contents have reached the host
             dev.copy_rows(sl["staging"].data_ptr(), band_bytes, band_addr, band_bytes, band_bytes, 1)
             sl["copied"].record(stream)
             stream2.wait_event(sl["copied"])
             dev2.download_into_async(sl["host"], sl["staging"].data_ptr(), band_bytes)
             sl["read"].record(stream2)
+        lap("read-back", t)
 
     def run(count):
         prefetch(0)
         for k in range(count):
             if k + 1 < count:
+                t = time.perf_counter()
                 prefetch(k + 1)  # every rank issues its collectives in this same order
+                lap("prefetch", t)
             render(k)
 
     run(4)
     torch.cuda.synchronize()
-    if band_bytes:
+    if band_bytes and "readback" not in skip:
         want = dev.download(band_addr, band_bytes)
         for sl in slots:
             got = np.ctypeslib.as_array(C.cast(sl["host"], C.POINTER(C.c_uint8)), shape=(band_bytes,))
@@ -632,6 +649,8 @@ def e2e_multi(torch, dist, rig, local, steps):
     t0 = time.perf_counter()
     run(n)
     dist.barrier(); torch.cuda.synchronize()  # all streams have drained
+    if trace is not None and rank == 0:
+        print("e2e host ms per frame by phase: " + ", ".join("%s %.3f" % (k, v * 1e3 / (n + 4)) for k, v in trace.items()), file=sys.stderr)
     t = torch.tensor([(time.perf_counter() - t0) * 1e3 / n], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     for b in scene.vertex_buffers:
