@@ -428,7 +428,12 @@ __global__ void __launch_bounds__(256) k_copy_rows(cpvk_u8* dst, cpvk_u32 dstPit
 // loop is just taps + lerps + pack. The z axis always lands on slice 0 twice with weight 0; since both z planes are
 // then the same bits, the reference's last lerp is lerp(v, v, 0) and is evaluated as exactly that.
 struct CpvkBlitAxis { int c0, c1; float t; int dst; };
+#ifndef CPVK_BLIT_ROWS
 #define CPVK_BLIT_ROWS 32
+#endif
+#ifndef CPVK_BLIT_BATCH
+#define CPVK_BLIT_BATCH 2 /* NEAREST from 8-bit sources: rows whose texels are loaded before the first of them is converted and stored */
+#endif
 __device__ __forceinline__ CpvkBlitAxis cpvk_blit_axis(int i, int dst0, int dst1, int src0, int src1, cpvk_u32 srcSize, cpvk_u32 filter) {
     CpvkBlitAxis r;
     r.dst = dst1 < dst0 ? i + dst1 : i + dst0;
@@ -488,6 +493,8 @@ template <int KS, int KD, int FILTER, int TPT> __global__ void __launch_bounds__
     // the four columns form one aligned in-range run of the destination? (then vector stores)
     const bool run = TPT == 4 && x4 + 3 < dstW && cx[0].dst >= 0 && (cpvk_u32)cx[TPT - 1].dst < b.dst.width && cx[TPT - 1].dst == cx[0].dst + 3 &&
                      (KD == K8 || KD == K16F) && ((b.dst.address + (cpvk_u64)cx[0].dst * dtexel) & 15u) == 0u && (b.dst.rowPitch & 15u) == 0u;
+    const bool srcRun = TPT == 4 && KS == K8 && x4 + 3 < dstW && cx[1 % TPT].c0 == cx[0].c0 + 1 && cx[2 % TPT].c0 == cx[0].c0 + 2 && cx[3 % TPT].c0 == cx[0].c0 + 3 &&
+                        ((b.src.address + (cpvk_u64)(cpvk_u32)cx[0].c0 * 4u) & 15u) == 0u && (spitch & 15u) == 0u;
     for (int rowBase = (int)blockIdx.y * CPVK_BLIT_ROWS; rowBase < dstH; rowBase += (int)gridDim.y * CPVK_BLIT_ROWS) {
         __syncthreads();
         if (threadIdx.x < CPVK_BLIT_ROWS && rowBase + (int)threadIdx.x < dstH)
@@ -495,6 +502,57 @@ template <int KS, int KD, int FILTER, int TPT> __global__ void __launch_bounds__
         __syncthreads();
         if (x4 >= dstW) continue;
         const int nRows = min(CPVK_BLIT_ROWS, dstH - rowBase);
+        auto store = [&](const CpvkBlitAxis& cy, float (&value)[TPT][4]) {
+            if (cy.dst < 0 || (cpvk_u32)cy.dst >= b.dst.height) return;
+            cpvk_u8* drow = reinterpret_cast<cpvk_u8*>(b.dst.address) + (cpvk_u64)cy.dst * b.dst.rowPitch;
+            if (TPT == 4 && run && KD == K8) {
+                *reinterpret_cast<uint4*>(drow + (cpvk_u64)cx[0].dst * 4u) = make_uint4(cpvk_blit_pack8(b.dst.format, value[0]), cpvk_blit_pack8(b.dst.format, value[1 % TPT]),
+                                                                                       cpvk_blit_pack8(b.dst.format, value[2 % TPT]), cpvk_blit_pack8(b.dst.format, value[3 % TPT]));
+            } else if (TPT == 4 && run && KD == K16F) {
+                const uint2 h0 = cpvk_pack_half4(value[0]), h1 = cpvk_pack_half4(value[1 % TPT]), h2 = cpvk_pack_half4(value[2 % TPT]), h3 = cpvk_pack_half4(value[3 % TPT]);
+                uint4* d = reinterpret_cast<uint4*>(drow + (cpvk_u64)cx[0].dst * 8u);
+                d[0] = make_uint4(h0.x, h0.y, h1.x, h1.y); d[1] = make_uint4(h2.x, h2.y, h3.x, h3.y);
+            } else {
+                #pragma unroll
+                for (int k = 0; k < TPT; k++) {
+                    if (x4 + k >= dstW || cx[k].dst < 0 || (cpvk_u32)cx[k].dst >= b.dst.width) continue;
+                    cpvk_set_pixel_f32_dyn(b.dst.format, drow + (cpvk_u64)cx[k].dst * dtexel, value[k]);
+                }
+            }
+        };
+        if (FILTER == 0 && KS == K8 && CPVK_BLIT_BATCH > 1) {
+            // NEAREST from an 8-bit source is pure data movement: the texels of CPVK_BLIT_BATCH rows are requested before the first
+            // one is converted, so that a thread has that many rows of loads in flight instead of one (read-only loads: the
+            // stores of one row do not hold back the loads of the next)
+            #pragma unroll 1
+            for (int r = 0; r < nRows; r += CPVK_BLIT_BATCH) {
+                cpvk_u32 raw[CPVK_BLIT_BATCH][TPT];
+                #pragma unroll
+                for (int j = 0; j < CPVK_BLIT_BATCH; j++) {
+                    const cpvk_u8* r0 = src + (cpvk_u64)(cpvk_u32)rows[min(r + j, nRows - 1)].c0 * spitch;
+                    if (TPT == 4 && srcRun) { // the four source texels are one aligned 16-byte run (an unscaled blit): one load
+                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(r0 + (cpvk_u64)(cpvk_u32)cx[0].c0 * 4u));
+                        raw[j][0] = q.x; raw[j][1 % TPT] = q.y; raw[j][2 % TPT] = q.z; raw[j][3 % TPT] = q.w;
+                        continue;
+                    }
+                    #pragma unroll
+                    for (int k = 0; k < TPT; k++) raw[j][k] = x4 + k < dstW ? __ldg(reinterpret_cast<const cpvk_u32*>(r0 + (cpvk_u64)(cpvk_u32)cx[k].c0 * 4u)) : 0u;
+                }
+                #pragma unroll
+                for (int j = 0; j < CPVK_BLIT_BATCH; j++) {
+                    if (r + j >= nRows) break;
+                    float value[TPT][4];
+                    #pragma unroll
+                    for (int k = 0; k < TPT; k++) {
+                        const cpvk_u32 t = raw[j][k];
+                        const float b0 = cpvk_unorm8(t & 0xFFu), b1 = cpvk_unorm8((t >> 8) & 0xFFu), b2 = cpvk_unorm8((t >> 16) & 0xFFu), b3 = cpvk_unorm8(t >> 24);
+                        value[k][0] = b.src.format == 37 ? b0 : b2; value[k][1] = b1; value[k][2] = b.src.format == 37 ? b2 : b0; value[k][3] = b3;
+                    }
+                    store(rows[r + j], value);
+                }
+            }
+            continue;
+        }
         #pragma unroll 1
         for (int r = 0; r < nRows; r++) {
             const CpvkBlitAxis cy = rows[r];
@@ -522,22 +580,7 @@ template <int KS, int KD, int FILTER, int TPT> __global__ void __launch_bounds__
                 if (comps < 3) v[2] = 0.0f;
                 if (comps < 4) v[3] = 1.0f;
             }
-            if (cy.dst < 0 || (cpvk_u32)cy.dst >= b.dst.height) continue;
-            cpvk_u8* drow = reinterpret_cast<cpvk_u8*>(b.dst.address) + (cpvk_u64)cy.dst * b.dst.rowPitch;
-            if (TPT == 4 && run && KD == K8) {
-                *reinterpret_cast<uint4*>(drow + (cpvk_u64)cx[0].dst * 4u) = make_uint4(cpvk_blit_pack8(b.dst.format, value[0]), cpvk_blit_pack8(b.dst.format, value[1 % TPT]),
-                                                                                       cpvk_blit_pack8(b.dst.format, value[2 % TPT]), cpvk_blit_pack8(b.dst.format, value[3 % TPT]));
-            } else if (TPT == 4 && run && KD == K16F) {
-                const uint2 h0 = cpvk_pack_half4(value[0]), h1 = cpvk_pack_half4(value[1 % TPT]), h2 = cpvk_pack_half4(value[2 % TPT]), h3 = cpvk_pack_half4(value[3 % TPT]);
-                uint4* d = reinterpret_cast<uint4*>(drow + (cpvk_u64)cx[0].dst * 8u);
-                d[0] = make_uint4(h0.x, h0.y, h1.x, h1.y); d[1] = make_uint4(h2.x, h2.y, h3.x, h3.y);
-            } else {
-                #pragma unroll
-                for (int k = 0; k < TPT; k++) {
-                    if (x4 + k >= dstW || cx[k].dst < 0 || (cpvk_u32)cx[k].dst >= b.dst.width) continue;
-                    cpvk_set_pixel_f32_dyn(b.dst.format, drow + (cpvk_u64)cx[k].dst * dtexel, value[k]);
-                }
-            }
+            store(cy, value);
         }
     }
 }
