@@ -573,7 +573,7 @@ template <int KS, int KD, int FILTER, int TPT> __global__ void __launch_bounds__
                     cpvk_blit_load<KS>(b.src.format, r1 + (cpvk_u64)(cpvk_u32)cx[k].c1 * stexel, i1j1.v, lutK);
                     const CpvkVec4 ij0 = cpvk_lerp(i0j0, i1j0, cx[k].t), ij1 = cpvk_lerp(i0j1, i1j1, cx[k].t);
                     const CpvkVec4 plane = cpvk_lerp(ij0, ij1, cy.t);
-                    const CpvkVec4 out = cpvk_lerp(plane, plane, cz.t); // the two z planes are the same slice
+                    const CpvkVec4 out = cpvk_lerp_same(plane, cz.t); // the two z planes are the same slice
                     v[0] = out.v[0]; v[1] = out.v[1]; v[2] = out.v[2]; v[3] = out.v[3];
                 }
                 if (comps < 2) v[1] = 0.0f; // SampleImage (ImageSampler.cpp:581-673): absent channels read 0, 0, 1
