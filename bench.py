@@ -396,6 +396,7 @@ def measure(rig, steps, warmup, sampler=None):
     torch, dist, world, dev = rig.torch, rig.dist, rig.world, rig.dev
     for _ in range(max(warmup, 3)):
         rig.frame()
+    dev.flush()  # synchronize() below is not a call of the library: the last draw is validated (and replayed, with its barrier) first
     torch.cuda.synchronize()
     st = dev.stats()
     local_cov, local_pass, bin_entries = int(st.fragmentsCovered), int(st.fragmentsWritten), int(st.binEntries)
@@ -434,6 +435,7 @@ def verify_exchange(rig):
     """N > 1: the frame rank 0 holds after the exchange must be, byte for byte, the frame one GPU renders without bands."""
     torch = rig.torch
     rig.frame()
+    rig.dev.flush()  # before work that is not the library's: a first frame usually does not fit the launch plan and is replayed here
     torch.cuda.synchronize()
     rig.dist.barrier()
     if rig.rank == 0:
@@ -871,6 +873,7 @@ def measure_short(rig, reps):
     torch, dist, world = rig.torch, rig.dist, rig.world
     for _ in range(2):
         rig.frame()
+    rig.dev.flush()
     torch.cuda.synchronize()
     st = rig.dev.stats()
     n_cov = int(st.fragmentsCovered)
