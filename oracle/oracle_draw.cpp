@@ -11,6 +11,8 @@
 //                 (5 050 states)  -> ProcessTriangles / ProcessLines / ProcessPoints / Fragment()'s interpolation / ApplyBlend below
 //   math_check    SpirvFunctions.cpp + the GLSL.std.450 templates of GlslFunctions.cpp -> oracle_spirv.h's dot / matrix / GLSL code
 //   sampler_check ImageSampler.cpp -> oracle_sampler.h        formats_check  Formats.cpp + FloatFormat.h -> oracle_formats.h
+//   blit_check    CommandBuffer.cpp's own BlitImageCommand::Process (:57-232) on real Image objects -> cpvk_oracle_blit below (36 blits:
+//                 scaled, flipped, offset, one-texel, both filters)
 //   spirv_check   SPIRVParser/ -> the hand-assembled shaders
 // NOT pinned by execution (the reference emits them as LLVM IR, which needs LLVM to run): the late depth / stencil epilogue and
 // attachment write of the fragment wrapper (PipelineCompiler.cpp) and the per-format UNORM / SNORM / sRGB pack / unpack arithmetic

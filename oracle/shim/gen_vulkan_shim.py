@@ -159,6 +159,12 @@ typedef VkFlags VkPipelineStageFlags;
 typedef VkFlags VkAccessFlags;
 typedef VkFlags VkDependencyFlags;
 """)
+
+# ---- what the sliced BlitImageCommand::Process of CPVulkan/CommandBuffer.cpp needs (oracle/_ref/blit_check) ----
+o.append("""typedef enum VkImageAspectFlagBits { VK_IMAGE_ASPECT_COLOR_BIT = 1, VK_IMAGE_ASPECT_DEPTH_BIT = 2, VK_IMAGE_ASPECT_STENCIL_BIT = 4, VK_IMAGE_ASPECT_METADATA_BIT = 8 } VkImageAspectFlagBits;
+typedef struct VkImageSubresourceLayers { VkImageAspectFlags aspectMask; uint32_t mipLevel, baseArrayLayer, layerCount; } VkImageSubresourceLayers;
+typedef struct VkImageBlit { VkImageSubresourceLayers srcSubresource; VkOffset3D srcOffsets[2]; VkImageSubresourceLayers dstSubresource; VkOffset3D dstOffsets[2]; } VkImageBlit;
+""")
 here = os.path.dirname(os.path.abspath(__file__))
 open(os.path.join(here, "vulkan", "vulkan_core.h"), "w").write("".join(o))
 open(os.path.join(here, "vulkan", "vulkan.h"), "w").write("#pragma once\n#include \"vulkan_core.h\"\n")

@@ -10,6 +10,8 @@ tests/test_reference_formats.py checks the oracle against these files everywhere
 the files still equal what the reference binary prints."""
 import os
 import subprocess
+import sys
+import tempfile
 
 import numpy as np
 
@@ -174,7 +176,29 @@ def math_golden():
     print("math: %d cases" % len(hdr))
 
 
+def blit_golden():
+    """vkCmdBlitImage: the destinations oracle/_ref/blit_check (BlitImageCommand::Process compiled in place) produces for the
+    seeded cases of tests/ref_blit_cases.py."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import ref_blit_cases
+    cs = ref_blit_cases.cases()
+    check = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "blit_check")
+    with tempfile.TemporaryDirectory() as tmp:
+        inp, outp = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+        open(inp, "wb").write(ref_blit_cases.payload(cs))
+        subprocess.run([check, inp, outp], check=True)
+        raw = np.fromfile(outp, dtype=np.uint32)
+    out, off = {"count": np.array(len(cs))}, 0
+    for i, (h, src, dst) in enumerate(cs):
+        out["dst_%d" % i] = raw[off:off + dst.size].copy()
+        off += dst.size
+    assert off == len(raw)
+    np.savez_compressed(os.path.join(HERE, "ref_blit.npz"), **out)
+    print("blit: %d cases, %d destination texels" % (len(cs), off // 4))
+
+
 def main():
+    blit_golden()
     draw_golden()
     math_golden()
     sampler_golden()
