@@ -11,6 +11,7 @@
 //                 (5 050 states)  -> ProcessTriangles / ProcessLines / ProcessPoints / Fragment()'s interpolation / ApplyBlend below
 //   math_check    SpirvFunctions.cpp + the GLSL.std.450 templates of GlslFunctions.cpp -> oracle_spirv.h's dot / matrix / GLSL code
 //   sampler_check ImageSampler.cpp -> oracle_sampler.h        formats_check  Formats.cpp + FloatFormat.h -> oracle_formats.h
+//                 draw_check ia: ProcessInputAssembler / ProcessInputAssemblerIndexed (109 draws) -> AssembledVertexId below
 //   blit_check    CommandBuffer.cpp's own BlitImageCommand::Process (:57-232) on real Image objects -> cpvk_oracle_blit below (36 blits:
 //                 scaled, flipped, offset, one-texel, both filters)
 //   spirv_check   SPIRVParser/ -> the hand-assembled shaders
@@ -362,23 +363,25 @@ void CheckSupported(const CpvkPipelineDesc& d) {
     if (d.rasterizationSamples > 1) Fail("multisampling");
 }
 
+// IA: ProcessInputAssembler (Draw.cpp:675-688) / ProcessIndexedVertices + ProcessInputAssemblerIndexed (:690-760): the vertex id the
+// vertex stage sees for raw vertex i. Pinned against those functions themselves (tests/test_reference_draw.py, draw_check ia).
+uint32_t AssembledVertexId(const CpvkDrawState& st, uint32_t i) {
+    if (st.indexStride == 0) return st.first + i;
+    const uint8_t* ib = (const uint8_t*)(uintptr_t)st.indexBuffer;
+    uint32_t index = 0;
+    const uint64_t k = (uint64_t)st.first + i;
+    if (st.indexStride == 1) index = ib[k];
+    else if (st.indexStride == 2) { uint16_t t; std::memcpy(&t, ib + 2 * k, 2); index = t; }
+    else { std::memcpy(&index, ib + 4 * k, 4); }
+    return (uint32_t)st.vertexOffset + index;
+}
+
 void RunVertexStage(DrawContext& c, uint32_t instance, uint32_t n) {
     const CpvkDrawState& st = *c.st;
     Module& m = c.vs.mod;
     c.vertexStorage.assign((size_t)n * c.vs.outputStride, 0);
     for (uint32_t i = 0; i < n; i++) {
-        // IA: Draw.cpp:675-688 / :690-711
-        uint32_t vertexId;
-        if (st.indexStride == 0) vertexId = st.first + i;
-        else {
-            const uint8_t* ib = (const uint8_t*)(uintptr_t)st.indexBuffer;
-            uint32_t index = 0;
-            const uint64_t k = (uint64_t)st.first + i;
-            if (st.indexStride == 1) index = ib[k];
-            else if (st.indexStride == 2) { uint16_t t; std::memcpy(&t, ib + 2 * k, 2); index = t; }
-            else { std::memcpy(&index, ib + 4 * k, 4); }
-            vertexId = (uint32_t)st.vertexOffset + index;
-        }
+        const uint32_t vertexId = AssembledVertexId(st, i);
         c.vsi.BeginInvocation();
         if (c.vs.vertexIndexVar) *c.vsi.VarData(c.vs.vertexIndexVar) = vertexId;
         if (c.vs.instanceIndexVar) *c.vsi.VarData(c.vs.instanceIndexVar) = instance;
@@ -787,6 +790,13 @@ int64_t cpvk_oracle_raster_records(float width, float height, float minDepth, fl
 
 // ApplyBlend on its own (Draw.cpp:1105-1262), the counterpart of oracle/ref_draw_check.cpp `blend`: state = the eight
 // VkPipelineColorBlendAttachmentState members in order; source / destination / constant / out are float[4].
+// Test hook: the vertex ids input assembly produces for a draw state (only count, first, vertexOffset and the index binding are read).
+int cpvk_oracle_input_assembly(const CpvkDrawState* st, uint32_t* outVertexIds) {
+    if (!st || !outVertexIds) return 1;
+    for (uint32_t i = 0; i < st->count; i++) outVertexIds[i] = AssembledVertexId(*st, i);
+    return 0;
+}
+
 int cpvk_oracle_apply_blend(const uint32_t state[8], const float* source, const float* destination, const float* constant, float* out) {
     try {
         CpvkBlendAttachment b{};

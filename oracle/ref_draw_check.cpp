@@ -27,6 +27,10 @@
 #include <unordered_map>
 #include <vector>
 
+#include <Base.h>
+#define private public // Buffer keeps its fields private and offers no constructor outside the ICD ("ia" mode binds an index buffer)
+#include <Buffer.h>
+#undef private
 #include <DeviceState.h>
 #include <Formats.h>
 #include <PipelineData.h>
@@ -200,6 +204,42 @@ static int MainRaster(const char* inPath, const char* outPath) {
     return out ? 0 : 2;
 }
 
+// ia <input> <output>
+// input:  u32 nCases, then per case u32 {indexed, first, count, vertexOffset, indexStride, topology, bindingOffset, bufferBytes} and
+//         bufferBytes bytes (the index buffer; none when not indexed).
+// output: per case u32 nVertices, then nVertices x {rawId, vertexId}: what ProcessInputAssembler / ProcessInputAssemblerIndexed
+//         (Draw.cpp:675-760) hand to the vertex stage.
+static int MainIa(const char* inPath, const char* outPath) {
+    std::ifstream in(inPath, std::ios::binary);
+    if (!in) return 2;
+    std::ofstream out(outPath, std::ios::binary);
+    uint32_t nCases;
+    if (!Read(in, &nCases)) return 2;
+    for (uint32_t c = 0; c < nCases; c++) {
+        uint32_t u[8];
+        if (!Read(in, u, 8)) return 2;
+        std::vector<uint8_t> bytes(u[7] + 16);
+        if (u[7] && !Read(in, bytes.data(), u[7])) return 2;
+        auto state = std::make_unique<DeviceState>();
+        state->jit = nullptr;
+        GraphicsPipeline pipeline;
+        pipeline.inputAssemblyState.Topology = static_cast<VkPrimitiveTopology>(u[5]);
+        pipeline.inputAssemblyState.PrimitiveRestartEnable = false; // the reference aborts on it (Draw.cpp:697-700)
+        state->graphicsPipelineState.pipeline = &pipeline;
+        Buffer buffer;
+        buffer.data = gsl::span<uint8_t>(bytes.data(), (std::ptrdiff_t)bytes.size());
+        buffer.size = bytes.size();
+        state->graphicsPipelineState.indexBinding = &buffer;           // vkCmdBindIndexBuffer, CommandBuffer.cpp
+        state->graphicsPipelineState.indexBindingOffset = u[6];
+        state->graphicsPipelineState.indexBindingStride = u[4];
+        const AssemblerOutput a = u[0] ? ProcessInputAssemblerIndexed(state.get(), u[1], u[2], u[3]) : ProcessInputAssembler(state.get(), u[1], u[2]);
+        const uint32_t n = (uint32_t)a.vertices.size();
+        out.write(reinterpret_cast<const char*>(&n), 4);
+        for (const VertexInput& v : a.vertices) { const uint32_t w[2] = {v.rawId, v.vertexId}; out.write(reinterpret_cast<const char*>(w), 8); }
+    }
+    return out ? 0 : 2;
+}
+
 // blend <input> <output>
 // input:  u32 nCases, then per case 8 x u32 (VkPipelineColorBlendAttachmentState in member order) + source[4], destination[4],
 //         constant[4] as f32.  output: per case ApplyBlend<glm::vec4>(source, destination, constant, state) as 4 x f32 bits.
@@ -228,6 +268,7 @@ static int MainBlend(const char* inPath, const char* outPath) {
 int main(int argc, char** argv) {
     if (argc == 4 && !std::strcmp(argv[1], "raster")) return MainRaster(argv[2], argv[3]);
     if (argc == 4 && !std::strcmp(argv[1], "blend")) return MainBlend(argv[2], argv[3]);
-    std::fprintf(stderr, "usage: draw_check raster|blend <input> <output>\n");
+    if (argc == 4 && !std::strcmp(argv[1], "ia")) return MainIa(argv[2], argv[3]);
+    std::fprintf(stderr, "usage: draw_check raster|blend|ia <input> <output>\n");
     return 2;
 }

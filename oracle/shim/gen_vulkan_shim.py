@@ -165,6 +165,12 @@ o.append("""typedef enum VkImageAspectFlagBits { VK_IMAGE_ASPECT_COLOR_BIT = 1, 
 typedef struct VkImageSubresourceLayers { VkImageAspectFlags aspectMask; uint32_t mipLevel, baseArrayLayer, layerCount; } VkImageSubresourceLayers;
 typedef struct VkImageBlit { VkImageSubresourceLayers srcSubresource; VkOffset3D srcOffsets[2]; VkImageSubresourceLayers dstSubresource; VkOffset3D dstOffsets[2]; } VkImageBlit;
 """)
+# ---- CPVulkan/Buffer.h (the index buffer bound in draw_check's "ia" mode): names its declarations mention ----
+o.append("""typedef VkFlags VkBufferCreateFlags;
+typedef VkFlags VkBufferUsageFlags;
+typedef struct VkMemoryRequirements2 VkMemoryRequirements2;
+typedef struct VkBufferCreateInfo VkBufferCreateInfo;
+""")
 here = os.path.dirname(os.path.abspath(__file__))
 open(os.path.join(here, "vulkan", "vulkan_core.h"), "w").write("".join(o))
 open(os.path.join(here, "vulkan", "vulkan.h"), "w").write("#pragma once\n#include \"vulkan_core.h\"\n")

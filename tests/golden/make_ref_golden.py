@@ -176,6 +176,19 @@ def math_golden():
     print("math: %d cases" % len(hdr))
 
 
+def ia_golden():
+    """Input assembly: the (rawId, vertexId) pairs ProcessInputAssembler[Indexed] (draw_check ia) produce for tests/ref_ia_cases.py."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import ref_ia_cases
+    cs = ref_ia_cases.cases()
+    pairs = ref_ia_cases.parse(run_draw_check("ia", ref_ia_cases.payload(cs)), len(cs))
+    out = {"count": np.array(len(cs))}
+    for i, p in enumerate(pairs):
+        out["pairs_%d" % i] = p
+    np.savez_compressed(os.path.join(HERE, "ref_ia.npz"), **out)
+    print("ia: %d cases, %d vertices" % (len(cs), sum(len(p) for p in pairs)))
+
+
 def blit_golden():
     """vkCmdBlitImage: the destinations oracle/_ref/blit_check (BlitImageCommand::Process compiled in place) produces for the
     seeded cases of tests/ref_blit_cases.py."""
@@ -198,6 +211,7 @@ def blit_golden():
 
 
 def main():
+    ia_golden()
     blit_golden()
     draw_golden()
     math_golden()
