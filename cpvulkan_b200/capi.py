@@ -259,6 +259,8 @@ def load_oracle():
     lib.cpvk_oracle_unpack_depth.restype = None
     lib.cpvk_oracle_sample.argtypes = [C.POINTER(Descriptor), vp, u32, f32, vp]
     lib.cpvk_oracle_sample.restype = None
+    lib.cpvk_oracle_fetch.argtypes = [C.POINTER(Descriptor), vp, u32, vp]
+    lib.cpvk_oracle_fetch.restype = None
     lib.cpvk_oracle_float_to_half.argtypes = [f32]
     lib.cpvk_oracle_float_to_half.restype = C.c_uint16
     lib.cpvk_oracle_half_to_float.argtypes = [C.c_uint16]

@@ -10,6 +10,8 @@
 //                 ProcessLines, ProcessTriangles (fragment streams of 33 draws, 137 612 fragments) and ApplyBlendFactor / ApplyBlend
 //                 (5 050 states)  -> ProcessTriangles / ProcessLines / ProcessPoints / Fragment()'s interpolation / ApplyBlend below
 //   math_check    SpirvFunctions.cpp + the GLSL.std.450 templates of GlslFunctions.cpp -> oracle_spirv.h's dot / matrix / GLSL code
+//   image_check   GlslFunctions.cpp's own GetImageData / Swizzle / ImageSampleExplicitLod / ImageFetch (:324-737, 80 bindings x 24 coordinates)
+//                 -> oracle_sampler.h's ImageSampleExplicitLod / ImageFetch
 //   sampler_check ImageSampler.cpp -> oracle_sampler.h        formats_check  Formats.cpp + FloatFormat.h -> oracle_formats.h
 //                 draw_check ia: ProcessInputAssembler / ProcessInputAssemblerIndexed (109 draws) -> AssembledVertexId below
 //   blit_check    CommandBuffer.cpp's own BlitImageCommand::Process (:57-232) on real Image objects -> cpvk_oracle_blit below (36 blits:
@@ -914,6 +916,13 @@ void cpvk_oracle_unpack_depth(uint32_t format, const uint8_t* in, uint32_t count
 void cpvk_oracle_sample(const CpvkDescriptor* d, const float* coords, uint32_t count, float lod, float* out) {
     for (uint32_t i = 0; i < count; i++) {
         const Vec4f r = ImageSampleExplicitLod(*d, coords + 3 * (size_t)i, lod);
+        std::memcpy(out + 4 * (size_t)i, r.v, 16);
+    }
+}
+// Test hook: ImageFetch (oracle_sampler.h) on caller-supplied integer coordinates (three per fetch), image or texel-buffer descriptor.
+void cpvk_oracle_fetch(const CpvkDescriptor* d, const int32_t* coords, uint32_t count, float* out) {
+    for (uint32_t i = 0; i < count; i++) {
+        const Vec4f r = ImageFetch(*d, coords + 3 * (size_t)i);
         std::memcpy(out + 4 * (size_t)i, r.v, 16);
     }
 }

@@ -171,6 +171,20 @@ typedef VkFlags VkBufferUsageFlags;
 typedef struct VkMemoryRequirements2 VkMemoryRequirements2;
 typedef struct VkBufferCreateInfo VkBufferCreateInfo;
 """)
+# ---- CPVulkan/ImageView.h, BufferView.h, DescriptorSet.h and the sliced image functions of GlslFunctions.cpp (oracle/_ref/image_check) ----
+o.append("""typedef enum VkComponentSwizzle { VK_COMPONENT_SWIZZLE_IDENTITY = 0, VK_COMPONENT_SWIZZLE_ZERO = 1, VK_COMPONENT_SWIZZLE_ONE = 2, VK_COMPONENT_SWIZZLE_R = 3, VK_COMPONENT_SWIZZLE_G = 4, VK_COMPONENT_SWIZZLE_B = 5, VK_COMPONENT_SWIZZLE_A = 6 } VkComponentSwizzle;
+typedef struct VkComponentMapping { VkComponentSwizzle r, g, b, a; } VkComponentMapping;
+typedef struct VkImageSubresourceRange { VkImageAspectFlags aspectMask; uint32_t baseMipLevel, levelCount, baseArrayLayer, layerCount; } VkImageSubresourceRange;
+typedef enum VkImageViewType { VK_IMAGE_VIEW_TYPE_1D = 0, VK_IMAGE_VIEW_TYPE_2D = 1, VK_IMAGE_VIEW_TYPE_3D = 2, VK_IMAGE_VIEW_TYPE_CUBE = 3, VK_IMAGE_VIEW_TYPE_1D_ARRAY = 4, VK_IMAGE_VIEW_TYPE_2D_ARRAY = 5, VK_IMAGE_VIEW_TYPE_CUBE_ARRAY = 6 } VkImageViewType;
+#define VK_REMAINING_MIP_LEVELS (~0U)
+#define VK_REMAINING_ARRAY_LAYERS (~0U)
+typedef struct VkImageViewCreateInfo VkImageViewCreateInfo;
+typedef struct VkBufferViewCreateInfo VkBufferViewCreateInfo;
+typedef enum VkDescriptorType { VK_DESCRIPTOR_TYPE_SAMPLER = 0, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER = 1, VK_DESCRIPTOR_TYPE_SAMPLED_IMAGE = 2, VK_DESCRIPTOR_TYPE_STORAGE_IMAGE = 3, VK_DESCRIPTOR_TYPE_UNIFORM_TEXEL_BUFFER = 4, VK_DESCRIPTOR_TYPE_STORAGE_TEXEL_BUFFER = 5, VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER = 6, VK_DESCRIPTOR_TYPE_STORAGE_BUFFER = 7, VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC = 8, VK_DESCRIPTOR_TYPE_STORAGE_BUFFER_DYNAMIC = 9, VK_DESCRIPTOR_TYPE_INPUT_ATTACHMENT = 10 } VkDescriptorType;
+typedef struct VkDescriptorBufferInfo { VkBuffer buffer; VkDeviceSize offset, range; } VkDescriptorBufferInfo;
+typedef struct VkWriteDescriptorSet VkWriteDescriptorSet;
+typedef struct VkCopyDescriptorSet VkCopyDescriptorSet;
+""")
 here = os.path.dirname(os.path.abspath(__file__))
 open(os.path.join(here, "vulkan", "vulkan_core.h"), "w").write("".join(o))
 open(os.path.join(here, "vulkan", "vulkan.h"), "w").write("#pragma once\n#include \"vulkan_core.h\"\n")

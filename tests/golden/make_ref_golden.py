@@ -176,6 +176,26 @@ def math_golden():
     print("math: %d cases" % len(hdr))
 
 
+def image_golden():
+    """The shader-side image functions (GlslFunctions.cpp:324-737) run by oracle/_ref/image_check on tests/ref_image_cases.py."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import ref_image_cases
+    cs = ref_image_cases.cases()
+    check = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "image_check")
+    with tempfile.TemporaryDirectory() as tmp:
+        inp, outp = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+        open(inp, "wb").write(ref_image_cases.payload(cs))
+        subprocess.run([check, inp, outp], check=True)
+        raw = np.fromfile(outp, dtype=np.uint32)
+    out, off = {"count": np.array(len(cs))}, 0
+    for i, (hdr, f3, data, coords) in enumerate(cs):
+        out["result_%d" % i] = raw[off:off + 4 * len(coords)].reshape(-1, 4).copy()
+        off += 4 * len(coords)
+    assert off == len(raw)
+    np.savez_compressed(os.path.join(HERE, "ref_image.npz"), **out)
+    print("image: %d cases, %d results" % (len(cs), off // 4))
+
+
 def ia_golden():
     """Input assembly: the (rawId, vertexId) pairs ProcessInputAssembler[Indexed] (draw_check ia) produce for tests/ref_ia_cases.py."""
     sys.path.insert(0, os.path.dirname(HERE))
@@ -211,6 +231,7 @@ def blit_golden():
 
 
 def main():
+    image_golden()
     ia_golden()
     blit_golden()
     draw_golden()
