@@ -247,6 +247,7 @@ def load_oracle():
     lib.cpvk_oracle_copy_rows.argtypes = [u64, u32, u64, u32, u32, u32]
     lib.cpvk_oracle_blit.argtypes = [C.POINTER(Blit)]
     lib.cpvk_oracle_input_assembly.argtypes = [C.POINTER(DrawState), vp]
+    lib.cpvk_oracle_fragment_inputs.argtypes = [vp, u32, vp, u32]
     lib.cpvk_oracle_blit_window.argtypes = [C.POINTER(Blit), i32, i32, i32, i32]
     lib.cpvk_oracle_format_info.argtypes = [u32, C.POINTER(u32 * 4)]
     lib.cpvk_oracle_pack_f32.argtypes = [u32, vp, u32, vp]

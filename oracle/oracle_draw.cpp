@@ -16,6 +16,8 @@
 //                 draw_check ia: ProcessInputAssembler / ProcessInputAssemblerIndexed (109 draws) -> AssembledVertexId below
 //   blit_check    CommandBuffer.cpp's own BlitImageCommand::Process (:57-232) on real Image objects -> cpvk_oracle_blit below (36 blits:
 //                 scaled, flipped, offset, one-texel, both filters)
+//   interface_check  Draw.cpp's own GetVariableFormat / GetVariableSize / GetVariablePointers on modules loaded by SPIRVParser/ -> Reflect's
+//                 fragment inputs (Location, format, interpolation, size, offset) for every fragment shader in the tree
 //   spirv_check   SPIRVParser/ -> the hand-assembled shaders
 // NOT pinned by execution (the reference emits them as LLVM IR, which needs LLVM to run): the late depth / stencil epilogue and
 // attachment write of the fragment wrapper (PipelineCompiler.cpp) and the per-format UNORM / SNORM / sRGB pack / unpack arithmetic
@@ -792,6 +794,28 @@ int64_t cpvk_oracle_raster_records(float width, float height, float minDepth, fl
 
 // ApplyBlend on its own (Draw.cpp:1105-1262), the counterpart of oracle/ref_draw_check.cpp `blend`: state = the eight
 // VkPipelineColorBlendAttachmentState members in order; source / destination / constant / out are float[4].
+// Test hook: the fragment stage's view of its inputs — per input Location, the format SetDatum interpolates it as, interpolation
+// kind, size and byte offset inside the vertex stage's record (Reflect above = GetVariablePointers, Draw.cpp:420-565, called
+// with inputSize = sizeof(VertexBuiltinOutput) as ProcessFragmentShader does, :1613-1619). out = {count, then 5 words per input,
+// then the final inputSize}; returns the number of words written or a negative value.
+int cpvk_oracle_fragment_inputs(const uint32_t* spirv, uint32_t wordCount, uint32_t* out, uint32_t capacityWords) {
+    try {
+        StageInfo s;
+        Parse(s.mod, spirv, wordCount, "main", 4, nullptr, 0);
+        Reflect(s, false);
+        const uint32_t need = 2 + 5 * (uint32_t)s.inputs.size();
+        if (need > capacityWords) return -2;
+        uint32_t k = 0, end = 24;
+        out[k++] = (uint32_t)s.inputs.size();
+        for (const InOut& io : s.inputs) {
+            out[k++] = io.location; out[k++] = VariableFormat(s.mod, io.type); out[k++] = io.interpolation; out[k++] = io.size; out[k++] = io.offset;
+            end = io.offset + io.size;
+        }
+        out[k++] = end;
+        return (int)k;
+    } catch (const std::exception& e) { g_error = e.what(); return -1; }
+}
+
 // Test hook: the vertex ids input assembly produces for a draw state (only count, first, vertexOffset and the index binding are read).
 int cpvk_oracle_input_assembly(const CpvkDrawState* st, uint32_t* outVertexIds) {
     if (!st || !outVertexIds) return 1;

@@ -30,6 +30,7 @@ EXPECTED = {  # (storage class, Location) in module order; storage: 0 UniformCon
     "glslmath.frag": (4, [(3, 0), (1, 0)]),
     "flat.frag": (4, [(3, 0), (1, 0)]),
     "nopersp.frag": (4, [(3, 0), (1, 0)]),
+    "varyings.frag": (4, [(3, 0), (1, 4), (1, 0), (1, 2), (1, 1), (1, 3), (1, 5)]),  # test-only (tests/test_reference_interface.py)
     "fragcoord.frag": (4, [(3, 0), (1, 0), (1, -1)]),                                                # gl_FragCoord: Input, no Location
     "multisets.frag": (4, [(3, 0), (0, -1), (1, 0)]),                                                # the sampler in descriptor set 1
     "uboarray.vert": (0, [(3, 0), (1, 1), (3, -1), (2, -1), (2, -1), (1, 0)]),                      # two uniform blocks (sets 0 and 1), arrays with ArrayStride
